@@ -1,0 +1,184 @@
+// Kernel 4 -- merge: fold L sorted candidate lists per query into the final best-first top-k, convert keys to
+// the distances faiss returns (squared L2 ascending / inner product descending; vector_database.py:181),
+// translate local row ids to global int64 ids, and gather the neighbour labels for the kNN label vote.
+// The same kernel merges (a) the S per-chunk lists of one GPU and (b) the G per-shard lists after the
+// all-gather of the multi-GPU path (IdxT = int64 there).
+//
+// Kernel 5 -- exact re-rank: re-score [Q, kc] candidates in fp32 against the fp32 master rows and sort them,
+// which makes the split-precision tensor-core path return exact-fp32 neighbours.
+#pragma once
+#include "common.cuh"
+
+namespace rdb {
+
+constexpr int MERGE_LPL = 8;  // lists per lane -> up to 256 lists per query
+
+struct MergeHead {
+  uint32_t ok;     // ordered key, 0 = exhausted
+  long long id;    // lower wins on equal key
+};
+__device__ __forceinline__ bool head_better(uint32_t ok_a, long long id_a, uint32_t ok_b, long long id_b) {
+  return (ok_a > ok_b) || (ok_a == ok_b && id_a < id_b);
+}
+
+// key_in [Q][L][kc], idx_in [Q][L][kc] sorted best-first per list, idx < 0 = empty slot (only at list tails).
+// lbl_in [Q][L][kc] (optional, labels that travelled with the candidates) or labels[] indexed by local id.
+// metric_l2: dist = max(0, qnorm[q] - key) else dist = key.
+// out_* [Q][kout]; missing results: id -1, dist +inf (L2) / -inf (IP), label 0 (faiss convention).
+template <typename IdxT>
+__global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restrict__ key_in,
+                                                          const IdxT* __restrict__ idx_in,
+                                                          const float* __restrict__ lbl_in, int Q, int L, int kc,
+                                                          int kout, int metric_l2, const float* __restrict__ qnorm,
+                                                          long long id_offset, const float* __restrict__ labels,
+                                                          float* __restrict__ out_dist,
+                                                          long long* __restrict__ out_idx,
+                                                          float* __restrict__ out_lbl,
+                                                          float* __restrict__ out_key) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const long long qbase = (long long)q * L * kc;
+
+  int ptr[MERGE_LPL];
+  uint32_t hok[MERGE_LPL];
+  long long hid[MERGE_LPL];
+  float hkey[MERGE_LPL];
+#pragma unroll
+  for (int i = 0; i < MERGE_LPL; ++i) {
+    ptr[i] = 0; hok[i] = 0; hid[i] = 0x7FFFFFFFFFFFFFFFll; hkey[i] = 0.f;
+    const int l = lane + 32 * i;
+    if (l < L && kc > 0) {
+      const long long id = (long long)idx_in[qbase + (long long)l * kc];
+      if (id >= 0) { hkey[i] = key_in[qbase + (long long)l * kc]; hok[i] = ordered_f32(hkey[i]); hid[i] = id; }
+    }
+  }
+
+  for (int r = 0; r < kout; ++r) {
+    // lane-local best head
+    uint32_t bok = 0; long long bid = 0x7FFFFFFFFFFFFFFFll; int bi = 0;
+#pragma unroll
+    for (int i = 0; i < MERGE_LPL; ++i)
+      if (head_better(hok[i], hid[i], bok, bid)) { bok = hok[i]; bid = hid[i]; bi = i; }
+    // warp arg-best
+    uint32_t wok = bok; long long wid = bid; int wl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t ook = __shfl_xor_sync(0xffffffffu, wok, o);
+      const long long oid = __shfl_xor_sync(0xffffffffu, wid, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+      if (head_better(ook, oid, wok, wid) || (ook == wok && oid == wid && ol < wl)) { wok = ook; wid = oid; wl = ol; }
+    }
+    const long long o = (long long)q * kout + r;
+    if (wok == 0) {
+      if (lane == 0) {
+        if (out_dist) out_dist[o] = metric_l2 ? CUDART_INF_F : -CUDART_INF_F;
+        out_idx[o] = -1;
+        if (out_lbl) out_lbl[o] = 0.f;
+        if (out_key) out_key[o] = -CUDART_INF_F;
+      }
+      continue;
+    }
+    if (lane == wl) {
+      // emit + advance the winning list
+      float kv = 0.f; int p = 0;
+#pragma unroll
+      for (int i = 0; i < MERGE_LPL; ++i) if (i == bi) { kv = hkey[i]; p = ptr[i]; }
+      const int l = lane + 32 * bi;
+      const long long src = qbase + (long long)l * kc + p;
+      if (out_dist) {
+        float d = kv;
+        if (metric_l2) d = fmaxf(0.f, qnorm[q] - kv);
+        out_dist[o] = d;
+      }
+      out_idx[o] = wid + id_offset;   // wid is a local id when id_offset != 0, already global otherwise
+      if (out_key) out_key[o] = kv;
+      if (out_lbl) out_lbl[o] = lbl_in ? lbl_in[src] : (labels ? labels[wid] : 0.f);
+      ++p;
+      uint32_t nok = 0; long long nid = 0x7FFFFFFFFFFFFFFFll; float nkey = 0.f;
+      if (p < kc) {
+        const long long id = (long long)idx_in[src + 1];
+        if (id >= 0) { nkey = key_in[src + 1]; nok = ordered_f32(nkey); nid = id; }
+      }
+#pragma unroll
+      for (int i = 0; i < MERGE_LPL; ++i) if (i == bi) { ptr[i] = p; hok[i] = nok; hid[i] = nid; hkey[i] = nkey; }
+    }
+    __syncwarp();
+  }
+}
+
+// Exact fp32 re-rank.  One warp per query.
+//   cand_idx [Q][kc] local ids (from the approximate pass, -1 = empty), cand_key [Q][kc] approximate keys
+//   qf [Q, D] fp32 (already normalised), master [N, D] fp32, ynorm [N]
+// Writes exact keys back in best-first order (key desc, id asc) into out_key/out_idx [Q][kc] and a per-query
+// certificate: cert[q] = 1 iff  exact_key[kout-1] - approx_key_worst > margin[q], i.e. no row outside the
+// candidate set can belong to the exact top-kout given the approximate scorer's error bound `eps * |q| |y|max`.
+template <bool L2>
+__global__ void __launch_bounds__(128) rerank_exact_kernel(const int* __restrict__ cand_idx,
+                                                           const float* __restrict__ cand_key, int Q, int kc, int kout,
+                                                           const float* __restrict__ qf,
+                                                           const float* __restrict__ master,
+                                                           const float* __restrict__ ynorm, int D, float eps_scale,
+                                                           const float* __restrict__ qnorm, float ynorm_max_sqrt,
+                                                           float* __restrict__ out_key, int* __restrict__ out_idx,
+                                                           int* __restrict__ cert) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const float* qr = qf + (long long)q * D;
+  float my_key = -CUDART_INF_F;
+  int my_id = -1;
+  float approx_worst = CUDART_INF_F;   // smallest approximate key among the candidates (the admission threshold)
+  int nvalid = 0;
+  for (int j = 0; j < kc; ++j) {
+    const int id = cand_idx[(long long)q * kc + j];
+    if (id < 0) continue;
+    ++nvalid;
+    approx_worst = fminf(approx_worst, cand_key[(long long)q * kc + j]);
+    const float* yr = master + (long long)id * D;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s = fmaf(qr[c], __ldg(yr + c), s);
+    s = warp_sum(s);
+    const float key = L2 ? fmaf(2.0f, s, -ynorm[id]) : s;
+    if (lane == j) { my_key = key; my_id = id; }
+  }
+  // rank by counting (kc <= 32)
+  const uint32_t mok = (my_id >= 0) ? ordered_f32(my_key) : 0u;
+  const long long mid = (my_id >= 0) ? my_id : 0x7FFFFFFFFFFFFFFFll;
+  int rank = 0;
+  for (int j = 0; j < kc; ++j) {
+    const uint32_t ook = __shfl_sync(0xffffffffu, mok, j);
+    const long long oid = __shfl_sync(0xffffffffu, mid, j);
+    if (j != lane && head_better(ook, oid, mok, mid)) ++rank;
+  }
+  // distinct ranks for invalid slots: count invalid lanes below me
+  const uint32_t invalid_mask = __ballot_sync(0xffffffffu, lane < kc && my_id < 0);
+  if (lane < kc) {
+    int pos = rank;
+    if (my_id < 0) pos = nvalid + __popc(invalid_mask & ((1u << lane) - 1u));
+    out_key[(long long)q * kc + pos] = (my_id >= 0) ? my_key : -CUDART_INF_F;
+    out_idx[(long long)q * kc + pos] = my_id;
+  }
+  // certificate
+  const int kth_lane_rank = kout - 1;
+  const uint32_t has = __ballot_sync(0xffffffffu, lane < kc && my_id >= 0 && rank == kth_lane_rank);
+  float kth_key = -CUDART_INF_F;
+  if (has) kth_key = __shfl_sync(0xffffffffu, my_key, __ffs(has) - 1);
+  if (lane == 0 && cert) {
+    // |approx - exact| <= eps_scale * |q| * |y|  (x2 for the L2 key = 2 q.y - |y|^2)
+    const float bound = eps_scale * sqrtf(qnorm[q]) * ynorm_max_sqrt * (L2 ? 2.0f : 1.0f);
+    // a row outside the candidate set has approx key <= approx_worst, hence exact key <= approx_worst + bound
+    cert[q] = (nvalid < kc) ? 1 : ((kth_key > approx_worst + bound) ? 1 : 0);
+  }
+}
+
+// sum of neighbour labels per query over the first kvote results (the "kNN label vote" evidence)
+__global__ void label_vote_kernel(const float* __restrict__ lbl, int Q, int k, int kvote, float* __restrict__ vote) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  float s = 0.f;
+  for (int j = 0; j < kvote && j < k; ++j) s += lbl[(long long)q * k + j];
+  vote[q] = s;
+}
+
+}  // namespace rdb

@@ -1,0 +1,727 @@
+// Host side of the C ABI declared in include/radad_flat.h (sm_100a only; no CPU fallback).
+//
+// Device layout of one index (one GPU, one row shard):
+//   master f32 [cap, D]     fp32 rows            (RDB_STORE_F32, or 16-bit stores with RDB_FLAG_KEEP_F32_MASTER)
+//   hi     16b [cap, Dp]    bf16/f16 rows, K-major, pitch Dp = round_up(D, 8) (TMA needs 16-byte row strides)
+//   lo     16b [cap, Dp]    bf16(x - hi) residual (RDB_STORE_F32 only: split-precision tensor-core scorer)
+//   ynorm  f32 [cap]        |y|^2 of the values the scorer sees;   cap is a multiple of 256 (tile padding)
+//   labels f32 [n]          neighbour labels for the kNN vote
+// Everything a search needs beyond that lives in grow-only scratch owned by the handle, so a steady-state
+// search performs no allocation.
+#include "../../include/radad_flat.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "ingest.cuh"
+#include "merge.cuh"
+#include "score_simt.cuh"
+#include "score_tc.cuh"
+
+using namespace rdb;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    size_t want = need + need / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); want = need; e = cudaMalloc(&p, want); }
+    if (e == cudaSuccess) bytes = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+}  // namespace
+
+struct rdb_handle {
+  int d = 0, dp = 0, metric = 0, store = 0, device = 0;
+  unsigned flags = 0;
+  int64_t n = 0, cap = 0, id_offset = 0, nlabels = 0;
+  float* master = nullptr;
+  void* hi = nullptr;
+  void* lo = nullptr;
+  float* ynorm = nullptr;
+  float* labels = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  int last_algo = 0, last_S = 0;
+  int num_sms = 148;
+  int64_t launches = 0;
+  std::string err;
+  std::mutex mu;
+  // scratch
+  DevBuf add_stage, q_stage, qf, qhi, qlo, qnorm, cand_key, cand_idx, o_dist, o_idx, o_lbl, ids_stage, rec_stage;
+  bool has_master() const { return store == RDB_STORE_F32 || (flags & RDB_FLAG_KEEP_F32_MASTER); }
+  bool has_hi() const { return true; }
+  bool has_lo() const { return store == RDB_STORE_F32; }
+  bool f16() const { return store == RDB_STORE_F16; }
+};
+
+namespace {
+
+int fail(rdb_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(h, expr)                                                                              \
+  do {                                                                                                 \
+    cudaError_t e_ = (expr);                                                                           \
+    if (e_ != cudaSuccess) {                                                                           \
+      cudaGetLastError();                                                                              \
+      return fail(h, e_ == cudaErrorMemoryAllocation ? RDB_ERR_NOMEM : RDB_ERR_CUDA,                   \
+                  std::string(#expr) + ": " + cudaGetErrorString(e_));                                 \
+    }                                                                                                  \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------------- storage
+int grow_to(rdb_handle* h, int64_t need, bool exact = false) {
+  if (need <= h->cap) return RDB_OK;
+  int64_t cap = exact ? need : std::max<int64_t>(need, h->cap + h->cap / 2);
+  cap = round_up(std::max<int64_t>(cap, 256), 256);
+  if (cap >= (int64_t(1) << 31)) return fail(h, RDB_ERR_UNSUPPORTED, "more than 2^31-1 rows per shard");
+  const size_t D = h->d, Dp = h->dp;
+  float* master = nullptr; void* hi = nullptr; void* lo = nullptr; float* ynorm = nullptr;
+  auto cleanup = [&] { cudaFree(master); cudaFree(hi); cudaFree(lo); cudaFree(ynorm); cudaGetLastError(); };
+  cudaError_t e = cudaSuccess;
+  if (h->has_master()) e = cudaMalloc(&master, size_t(cap) * D * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&hi, size_t(cap) * Dp * 2);
+  if (e == cudaSuccess && h->has_lo()) e = cudaMalloc(&lo, size_t(cap) * Dp * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&ynorm, size_t(cap) * 4);
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(h, RDB_ERR_NOMEM, std::string("device allocation for ") + std::to_string(cap) + " rows failed: " +
+                                      cudaGetErrorString(e));
+  }
+  cudaStream_t s = h->stream;
+  if (h->n > 0) {
+    if (master) cudaMemcpyAsync(master, h->master, size_t(h->n) * D * 4, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(hi, h->hi, size_t(h->n) * Dp * 2, cudaMemcpyDeviceToDevice, s);
+    if (lo) cudaMemcpyAsync(lo, h->lo, size_t(h->n) * Dp * 2, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(ynorm, h->ynorm, size_t(h->n) * 4, cudaMemcpyDeviceToDevice, s);
+  }
+  cudaMemsetAsync(ynorm + h->n, 0, size_t(cap - h->n) * 4, s);
+  cudaError_t es = cudaStreamSynchronize(s);
+  if (es != cudaSuccess) { cleanup(); return fail(h, RDB_ERR_CUDA, std::string("grow copy: ") + cudaGetErrorString(es)); }
+  cudaFree(h->master); cudaFree(h->hi); cudaFree(h->lo); cudaFree(h->ynorm);
+  h->master = master; h->hi = hi; h->lo = lo; h->ynorm = ynorm; h->cap = cap;
+  return RDB_OK;
+}
+
+// launch the fused ingest kernel (also used to prepare queries)
+int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int norm_of_hi, float* master, void* hi,
+                  void* lo, float* norm2) {
+  if (n <= 0) return RDB_OK;
+  const int D = h->d, Dp = h->dp;
+  const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int warps_per_block = 8;
+  int64_t blocks = std::min<int64_t>((n + warps_per_block - 1) / warps_per_block, int64_t(h->num_sms) * 16);
+  dim3 grid((unsigned)blocks), block(256);
+  cudaStream_t s = h->stream;
+  if (h->f16()) {
+    if (vec4) ingest_rows_kernel<__half, true><<<grid, block, 0, s>>>(x, n, D, Dp, normalize, norm_of_hi, master, (__half*)hi, (__half*)lo, norm2);
+    else      ingest_rows_kernel<__half, false><<<grid, block, 0, s>>>(x, n, D, Dp, normalize, norm_of_hi, master, (__half*)hi, (__half*)lo, norm2);
+  } else {
+    if (vec4) ingest_rows_kernel<__nv_bfloat16, true><<<grid, block, 0, s>>>(x, n, D, Dp, normalize, norm_of_hi, master, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, norm2);
+    else      ingest_rows_kernel<__nv_bfloat16, false><<<grid, block, 0, s>>>(x, n, D, Dp, normalize, norm_of_hi, master, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, norm2);
+  }
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return RDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- scheduling
+// Split the database into S chunks so that nqt * S work units fill the machine in whole waves.
+// cost model: waves * (tiles_per_chunk + per-unit overhead);  `slots` = concurrently resident CTAs.
+int choose_splits(int64_t nqt, int64_t ntiles, int slots, int max_lists, int min_tiles, int* tiles_per_chunk) {
+  int64_t maxS = std::min<int64_t>(std::min<int64_t>(max_lists, ntiles), std::max<int64_t>(1, ntiles / min_tiles));
+  double best = 1e300;
+  int bestS = 1;
+  int64_t best_tpc = ntiles;
+  for (int64_t S = 1; S <= maxS; ++S) {
+    const int64_t tpc = (ntiles + S - 1) / S;
+    const int64_t S2 = (ntiles + tpc - 1) / tpc;
+    if (S2 != S) continue;
+    const int64_t units = nqt * S2;
+    const int64_t waves = (units + slots - 1) / slots;
+    const double cost = double(waves) * (double(tpc) + 2.0);
+    if (cost < best * 0.999) { best = cost; bestS = int(S2); best_tpc = tpc; }
+  }
+  *tiles_per_chunk = int(best_tpc);
+  return bestS;
+}
+
+// ---------------------------------------------------------------------------------------------- scorers
+template <int KT, bool L2, typename T, bool ALIGNED>
+int launch_simt_t(rdb_handle* h, const T* Q, const T* Y, int nq, int ld, int nqt, int S, int rows_per_chunk,
+                  float* ck, int* ci, int kout) {
+  auto kern = score_select_simt_kernel<KT, L2, T, ALIGNED>;
+  CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt_smem_bytes()));
+  kern<<<dim3(unsigned(nqt) * unsigned(S)), dim3(256), simt_smem_bytes(), h->stream>>>(
+      Q, Y, h->ynorm, nq, int(h->n), h->d, ld, nqt, S, rows_per_chunk, ck, ci, kout);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return RDB_OK;
+}
+
+template <int KT, bool L2>
+int launch_simt_k(rdb_handle* h, int nq, int nqt, int S, int rows_per_chunk, float* ck, int* ci, int kout) {
+  if (h->store == RDB_STORE_F32) {
+    const float* Q = h->qf.as<float>();
+    if (h->d % 4 == 0) return launch_simt_t<KT, L2, float, true>(h, Q, h->master, nq, h->d, nqt, S, rows_per_chunk, ck, ci, kout);
+    return launch_simt_t<KT, L2, float, false>(h, Q, h->master, nq, h->d, nqt, S, rows_per_chunk, ck, ci, kout);
+  }
+  if (h->f16())
+    return launch_simt_t<KT, L2, __half, true>(h, h->qhi.as<__half>(), (const __half*)h->hi, nq, h->dp, nqt, S, rows_per_chunk, ck, ci, kout);
+  return launch_simt_t<KT, L2, __nv_bfloat16, true>(h, h->qhi.as<__nv_bfloat16>(), (const __nv_bfloat16*)h->hi, nq, h->dp, nqt, S, rows_per_chunk, ck, ci, kout);
+}
+
+int launch_simt(rdb_handle* h, int nq, int k, int nqt, int S, int rows_per_chunk, float* ck, int* ci) {
+  const bool l2 = h->metric == RDB_METRIC_L2;
+#define SIMT_CASE(KT)                                                                          \
+  return l2 ? launch_simt_k<KT, true>(h, nq, nqt, S, rows_per_chunk, ck, ci, k)                \
+            : launch_simt_k<KT, false>(h, nq, nqt, S, rows_per_chunk, ck, ci, k)
+  if (k <= 16) { SIMT_CASE(16); }
+  if (k <= 32) { SIMT_CASE(32); }
+  if (k <= 64) { SIMT_CASE(64); }
+  SIMT_CASE(128);
+#undef SIMT_CASE
+}
+
+int encode_2d(rdb_handle* h, CUtensorMap* m, const void* base, int64_t rows, int D, int Dp, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(h, RDB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cuuint64_t(D), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(Dp) * 2};
+  cuuint32_t box[2] = {cuuint32_t(TC_BK), cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, h->f16() ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, RDB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
+  return RDB_OK;
+}
+
+int launch_tc(rdb_handle* h, int nq, int k, int nqt, int S, int tiles_per_chunk, int ntiles, int nterms, float* ck,
+              int* ci) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = encode_2d(h, &p.tmap_q[0], h->qhi.p, nq, h->d, h->dp, TC_BM))) return rc;
+  if ((rc = encode_2d(h, &p.tmap_y[0], h->hi, h->n, h->d, h->dp, TC_BN))) return rc;
+  if (nterms == 3) {
+    if ((rc = encode_2d(h, &p.tmap_q[1], h->qlo.p, nq, h->d, h->dp, TC_BM))) return rc;
+    if ((rc = encode_2d(h, &p.tmap_y[1], h->lo, h->n, h->d, h->dp, TC_BN))) return rc;
+  } else {
+    p.tmap_q[1] = p.tmap_q[0];
+    p.tmap_y[1] = p.tmap_y[0];
+  }
+  p.ynorm = h->ynorm; p.cand_key = ck; p.cand_idx = ci;
+  p.nq = nq; p.N = int(h->n); p.D = h->d;
+  p.nqt = nqt; p.S = S; p.tiles_per_chunk = tiles_per_chunk; p.ntiles = ntiles; p.kout = k;
+  p.num_units = nqt * S; p.nterms = nterms;
+  p.idesc = make_idesc_f16(TC_BM, TC_BN, h->f16() ? 0 : 1);
+  const int grid = std::min(p.num_units, h->num_sms);
+  const bool l2 = h->metric == RDB_METRIC_L2;
+#define TC_LAUNCH(KT, L2V)                                                                                       \
+  do {                                                                                                           \
+    auto kern = score_select_tc_kernel<KT, L2V>;                                                                 \
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes())); \
+    kern<<<dim3(grid), dim3(TC_THREADS), tc_smem_bytes(), h->stream>>>(p);                                       \
+  } while (0)
+  if (k <= 16) { if (l2) TC_LAUNCH(16, true); else TC_LAUNCH(16, false); }
+  else         { if (l2) TC_LAUNCH(32, true); else TC_LAUNCH(32, false); }
+#undef TC_LAUNCH
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return RDB_OK;
+}
+
+constexpr int64_t kQueryBatch = 65536;
+constexpr int kMaxK = 128;
+constexpr int kMaxKTc = 32;
+
+// One search over the local shard.  shard_mode: out_a receives merge keys instead of distances.
+int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int normalize, int algo, bool shard_mode,
+                float* out_a, int64_t* out_idx, float* out_lbl, float* out_qnorm) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  if (nq < 0 || k < 1 || (!q && nq > 0) || !out_a || !out_idx)
+    return fail(h, RDB_ERR_INVALID, "search: bad arguments (nq >= 0, k >= 1, non-null buffers)");
+  if (k > kMaxK) return fail(h, RDB_ERR_UNSUPPORTED, "search: k > 128 is not supported");
+  if (nq == 0) return RDB_OK;
+  const int D = h->d, Dp = h->dp;
+  const bool host = mem == RDB_MEM_HOST;
+  const bool l2 = h->metric == RDB_METRIC_L2;
+  const bool sixteen = h->store != RDB_STORE_F32;
+  const bool tc_ok = sixteen && k <= kMaxKTc && h->n >= 1024;
+  if (algo == RDB_ALGO_AUTO) algo = tc_ok ? RDB_ALGO_TC : RDB_ALGO_SIMT;
+  if (algo == RDB_ALGO_TC && !(sixteen && k <= kMaxKTc && h->n >= TC_BN))
+    return fail(h, RDB_ERR_UNSUPPORTED, "search: tensor-core scorer needs a 16-bit store, k <= 32 and ntotal >= 256");
+  const float* labels = (h->labels && h->nlabels == h->n) ? h->labels : nullptr;
+  cudaStream_t s = h->stream;
+
+  for (int64_t b0 = 0; b0 < nq; b0 += kQueryBatch) {
+    const int nb = int(std::min<int64_t>(kQueryBatch, nq - b0));
+    const float* qsrc = q + b0 * D;
+    if (host) {
+      CUDA_TRY(h, h->q_stage.ensure(size_t(nb) * D * 4));
+      CUDA_TRY(h, cudaMemcpyAsync(h->q_stage.p, qsrc, size_t(nb) * D * 4, cudaMemcpyHostToDevice, s));
+      qsrc = h->q_stage.as<float>();
+    }
+    // ---- query prep: normalise, |q|^2, convert (same fused kernel as ingest)
+    CUDA_TRY(h, h->qnorm.ensure(size_t(nb) * 4));
+    int rc;
+    if (sixteen) {
+      CUDA_TRY(h, h->qhi.ensure(size_t(nb) * Dp * 2));
+      if ((rc = launch_ingest(h, qsrc, nb, normalize, 1, nullptr, h->qhi.p, nullptr, h->qnorm.as<float>()))) return rc;
+    } else {
+      CUDA_TRY(h, h->qf.ensure(size_t(nb) * D * 4));
+      if ((rc = launch_ingest(h, qsrc, nb, normalize, 0, h->qf.as<float>(), nullptr, nullptr, h->qnorm.as<float>()))) return rc;
+    }
+    // ---- score + select
+    int L = 0;
+    const int nqt = (nb + 127) / 128;
+    if (h->n > 0) {
+      int S, tpc;
+      if (algo == RDB_ALGO_TC) {
+        const int ntiles = int((h->n + TC_BN - 1) / TC_BN);
+        S = choose_splits(nqt, ntiles, h->num_sms, 256, 4, &tpc);
+        L = S;
+        CUDA_TRY(h, h->cand_key.ensure(size_t(nb) * L * k * 4));
+        CUDA_TRY(h, h->cand_idx.ensure(size_t(nb) * L * k * 4));
+        cudaEventRecord(h->ev0, s);
+        if ((rc = launch_tc(h, nb, k, nqt, S, tpc, ntiles, 1, h->cand_key.as<float>(), h->cand_idx.as<int>()))) return rc;
+        cudaEventRecord(h->ev1, s);
+      } else {
+        const int ntiles = int((h->n + SIMT_BN - 1) / SIMT_BN);
+        S = choose_splits(nqt, ntiles, 2 * h->num_sms, 256 / SIMT_LISTS, 2, &tpc);
+        L = S * SIMT_LISTS;
+        CUDA_TRY(h, h->cand_key.ensure(size_t(nb) * L * k * 4));
+        CUDA_TRY(h, h->cand_idx.ensure(size_t(nb) * L * k * 4));
+        cudaEventRecord(h->ev0, s);
+        if ((rc = launch_simt(h, nb, k, nqt, S, tpc * SIMT_BN, h->cand_key.as<float>(), h->cand_idx.as<int>()))) return rc;
+        cudaEventRecord(h->ev1, s);
+      }
+      h->ev_valid = true; h->last_algo = algo; h->last_S = S;
+    }
+    // ---- merge
+    float* d_a = out_a + b0 * k;
+    int64_t* d_i = out_idx + b0 * k;
+    float* d_l = out_lbl ? out_lbl + b0 * k : nullptr;
+    if (host) {
+      CUDA_TRY(h, h->o_dist.ensure(size_t(nb) * k * 4));
+      CUDA_TRY(h, h->o_idx.ensure(size_t(nb) * k * 8));
+      if (out_lbl) CUDA_TRY(h, h->o_lbl.ensure(size_t(nb) * k * 4));
+      d_a = h->o_dist.as<float>(); d_i = h->o_idx.as<int64_t>(); d_l = out_lbl ? h->o_lbl.as<float>() : nullptr;
+    }
+    {
+      const int warps = 4;
+      dim3 grid((nb + warps - 1) / warps), block(32 * warps);
+      merge_lists_kernel<int><<<grid, block, 0, s>>>(
+          h->cand_key.as<float>(), h->cand_idx.as<int>(), nullptr, nb, L, k, k, l2 ? 1 : 0, h->qnorm.as<float>(),
+          h->id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l,
+          shard_mode ? d_a : nullptr);
+      h->launches++;
+      CUDA_TRY(h, cudaGetLastError());
+    }
+    if (out_qnorm)
+      CUDA_TRY(h, cudaMemcpyAsync(out_qnorm + b0, h->qnorm.p, size_t(nb) * 4,
+                                  host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+    if (host) {
+      CUDA_TRY(h, cudaMemcpyAsync(out_a + b0 * k, d_a, size_t(nb) * k * 4, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(h, cudaMemcpyAsync(out_idx + b0 * k, d_i, size_t(nb) * k * 8, cudaMemcpyDeviceToHost, s));
+      if (out_lbl) CUDA_TRY(h, cudaMemcpyAsync(out_lbl + b0 * k, d_l, size_t(nb) * k * 4, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(h, cudaStreamSynchronize(s));   // scratch is reused by the next batch
+    }
+  }
+  return RDB_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int rdb_abi_version(void) { return 1; }
+
+const char* rdb_last_error(rdb_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int rdb_create(int d, int metric, int store_dtype, int device, unsigned flags, rdb_handle** out) {
+  if (!out) return fail(nullptr, RDB_ERR_INVALID, "rdb_create: out is null");
+  *out = nullptr;
+  if (d < 1 || d > (1 << 20)) return fail(nullptr, RDB_ERR_INVALID, "rdb_create: dimension out of range");
+  if (metric != RDB_METRIC_L2 && metric != RDB_METRIC_IP) return fail(nullptr, RDB_ERR_INVALID, "rdb_create: unknown metric");
+  if (store_dtype < RDB_STORE_F32 || store_dtype > RDB_STORE_F16) return fail(nullptr, RDB_ERR_INVALID, "rdb_create: unknown store dtype");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, RDB_ERR_CUDA, "rdb_create: no CUDA device available (this index has no CPU fallback)");
+  }
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  if (device >= ndev) return fail(nullptr, RDB_ERR_INVALID, "rdb_create: device ordinal out of range");
+  cudaDeviceProp prop;
+  CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, RDB_ERR_UNSUPPORTED, std::string("rdb_create: built for sm_100a (B200); device is sm_") +
+                                                  std::to_string(prop.major) + std::to_string(prop.minor));
+  rdb_handle* h = new rdb_handle();
+  h->d = d; h->dp = int(round_up(d, 8)); h->metric = metric; h->store = store_dtype; h->device = device; h->flags = flags;
+  h->num_sms = prop.multiProcessorCount;
+  DeviceGuard dg(device);
+  cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+  if (e != cudaSuccess) { delete h; cudaGetLastError(); return fail(nullptr, RDB_ERR_CUDA, std::string("rdb_create: ") + cudaGetErrorString(e)); }
+  h->stream = h->own_stream;
+  *out = h;
+  return RDB_OK;
+}
+
+int rdb_destroy(rdb_handle* h) {
+  if (!h) return RDB_OK;
+  {
+    DeviceGuard dg(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->master); cudaFree(h->hi); cudaFree(h->lo); cudaFree(h->ynorm); cudaFree(h->labels);
+    for (DevBuf* b : {&h->add_stage, &h->q_stage, &h->qf, &h->qhi, &h->qlo, &h->qnorm, &h->cand_key, &h->cand_idx,
+                      &h->o_dist, &h->o_idx, &h->o_lbl, &h->ids_stage, &h->rec_stage})
+      b->release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    cudaGetLastError();
+  }
+  delete h;
+  return RDB_OK;
+}
+
+int rdb_set_stream(rdb_handle* h, void* cuda_stream) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return RDB_OK;
+}
+
+int rdb_sync(rdb_handle* h) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  DeviceGuard dg(h->device);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return RDB_OK;
+}
+
+int rdb_reserve(rdb_handle* h, int64_t n_total) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  return grow_to(h, n_total, /*exact=*/true);
+}
+
+int rdb_add(rdb_handle* h, const float* x, int64_t n, int mem, int normalize) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  if (n < 0 || (n > 0 && !x)) return fail(h, RDB_ERR_INVALID, "add: bad arguments");
+  if (n == 0) return RDB_OK;
+  int rc = grow_to(h, h->n + n);
+  if (rc) return rc;
+  const size_t D = h->d, Dp = h->dp;
+  const int es = 2;
+  const int norm_of_hi = h->store != RDB_STORE_F32;
+  // host input is staged in slices so the staging buffer stays bounded (256 MiB)
+  const int64_t slice = (mem == RDB_MEM_HOST) ? std::max<int64_t>(1, (int64_t(256) << 20) / int64_t(D * 4)) : n;
+  for (int64_t s0 = 0; s0 < n; s0 += slice) {
+    const int64_t m = std::min(slice, n - s0);
+    const float* src = x + s0 * D;
+    if (mem == RDB_MEM_HOST) {
+      CUDA_TRY(h, h->add_stage.ensure(size_t(m) * D * 4));
+      CUDA_TRY(h, cudaMemcpyAsync(h->add_stage.p, src, size_t(m) * D * 4, cudaMemcpyHostToDevice, h->stream));
+      src = h->add_stage.as<float>();
+    }
+    const int64_t row0 = h->n + s0;
+    float* master = h->has_master() ? h->master + row0 * D : nullptr;
+    void* hi = reinterpret_cast<char*>(h->hi) + size_t(row0) * Dp * es;
+    void* lo = h->has_lo() ? reinterpret_cast<char*>(h->lo) + size_t(row0) * Dp * es : nullptr;
+    if ((rc = launch_ingest(h, src, m, normalize, norm_of_hi, master, hi, lo, h->ynorm + row0))) return rc;
+    if (mem == RDB_MEM_HOST) CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // staging buffer reuse
+  }
+  h->n += n;
+  return RDB_OK;
+}
+
+int rdb_search(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int normalize, float* out_dist,
+               int64_t* out_idx, float* out_labels) {
+  return search_impl(h, q, nq, k, mem, normalize, RDB_ALGO_AUTO, false, out_dist, out_idx, out_labels, nullptr);
+}
+
+int rdb_search_algo(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int normalize, int algo,
+                    float* out_dist, int64_t* out_idx, float* out_labels) {
+  return search_impl(h, q, nq, k, mem, normalize, algo, false, out_dist, out_idx, out_labels, nullptr);
+}
+
+int rdb_search_shard(rdb_handle* h, const float* q_dev, int64_t nq, int k, int normalize, float* out_key,
+                     int64_t* out_idx, float* out_labels, float* out_qnorm) {
+  return search_impl(h, q_dev, nq, k, RDB_MEM_DEVICE, normalize, RDB_ALGO_AUTO, true, out_key, out_idx, out_labels,
+                     out_qnorm);
+}
+
+int rdb_merge_shards(rdb_handle* h, const float* key, const int64_t* idx, const float* labels, int64_t nq, int nlists,
+                     int k, const float* qnorm, float* out_dist, int64_t* out_idx, float* out_labels) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  if (nq < 0 || k < 1 || nlists < 1 || nlists > 32 * MERGE_LPL || !key || !idx || !out_dist || !out_idx)
+    return fail(h, RDB_ERR_INVALID, "merge_shards: bad arguments");
+  if (h->metric == RDB_METRIC_L2 && !qnorm) return fail(h, RDB_ERR_INVALID, "merge_shards: L2 needs qnorm");
+  if (nq == 0) return RDB_OK;
+  const int warps = 4;
+  dim3 grid(unsigned((nq + warps - 1) / warps)), block(32 * warps);
+  merge_lists_kernel<long long><<<grid, block, 0, h->stream>>>(
+      key, reinterpret_cast<const long long*>(idx), labels, int(nq), nlists, k, k, h->metric == RDB_METRIC_L2 ? 1 : 0,
+      qnorm, 0, nullptr, out_dist, reinterpret_cast<long long*>(out_idx), out_labels, nullptr);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return RDB_OK;
+}
+
+int rdb_reconstruct_batch(rdb_handle* h, const int64_t* ids, int64_t n, int mem, float* out) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  if (n < 0 || (n > 0 && (!ids || !out))) return fail(h, RDB_ERR_INVALID, "reconstruct_batch: bad arguments");
+  if (n == 0) return RDB_OK;
+  const size_t D = h->d;
+  const long long* d_ids = reinterpret_cast<const long long*>(ids);
+  float* d_out = out;
+  if (mem == RDB_MEM_HOST) {
+    CUDA_TRY(h, h->ids_stage.ensure(size_t(n) * 8));
+    CUDA_TRY(h, h->rec_stage.ensure(size_t(n) * D * 4));
+    CUDA_TRY(h, cudaMemcpyAsync(h->ids_stage.p, ids, size_t(n) * 8, cudaMemcpyHostToDevice, h->stream));
+    d_ids = h->ids_stage.as<long long>();
+    d_out = h->rec_stage.as<float>();
+  }
+  const int warps = 8;
+  dim3 grid(unsigned((n + warps - 1) / warps)), block(32 * warps);
+  const float* master = h->has_master() ? h->master : nullptr;
+  if (h->f16()) gather_rows_kernel<__half><<<grid, block, 0, h->stream>>>(d_ids, n, h->n, h->d, h->dp, master, (const __half*)h->hi, h->id_offset, 0, d_out);
+  else gather_rows_kernel<__nv_bfloat16><<<grid, block, 0, h->stream>>>(d_ids, n, h->n, h->d, h->dp, master, (const __nv_bfloat16*)h->hi, h->id_offset, 0, d_out);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  if (mem == RDB_MEM_HOST) {
+    CUDA_TRY(h, cudaMemcpyAsync(out, d_out, size_t(n) * D * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return RDB_OK;
+}
+
+int rdb_reconstruct(rdb_handle* h, int64_t id, float* out) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  if (id - h->id_offset < 0 || id - h->id_offset >= h->n)
+    return fail(h, RDB_ERR_INVALID, "reconstruct: id " + std::to_string(id) + " out of range");
+  return rdb_reconstruct_batch(h, &id, 1, RDB_MEM_HOST, out);
+}
+
+int rdb_set_labels(rdb_handle* h, const float* labels, int64_t n) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  if (n < 0 || (n > 0 && !labels)) return fail(h, RDB_ERR_INVALID, "set_labels: bad arguments");
+  cudaStreamSynchronize(h->stream);
+  cudaFree(h->labels); h->labels = nullptr; h->nlabels = 0;
+  if (n == 0) return RDB_OK;
+  CUDA_TRY(h, cudaMalloc(&h->labels, size_t(n) * 4));
+  CUDA_TRY(h, cudaMemcpyAsync(h->labels, labels, size_t(n) * 4, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->nlabels = n;
+  return RDB_OK;
+}
+
+int rdb_label_vote(rdb_handle* h, const float* lbl, int64_t nq, int k, int kvote, int mem, float* vote) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  if (nq < 0 || k < 1 || !lbl || !vote) return fail(h, RDB_ERR_INVALID, "label_vote: bad arguments");
+  if (nq == 0) return RDB_OK;
+  const float* d_l = lbl; float* d_v = vote;
+  if (mem == RDB_MEM_HOST) {
+    CUDA_TRY(h, h->o_lbl.ensure(size_t(nq) * k * 4));
+    CUDA_TRY(h, h->o_dist.ensure(size_t(nq) * 4));
+    CUDA_TRY(h, cudaMemcpyAsync(h->o_lbl.p, lbl, size_t(nq) * k * 4, cudaMemcpyHostToDevice, h->stream));
+    d_l = h->o_lbl.as<float>(); d_v = h->o_dist.as<float>();
+  }
+  label_vote_kernel<<<unsigned((nq + 255) / 256), 256, 0, h->stream>>>(d_l, int(nq), k, kvote, d_v);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  if (mem == RDB_MEM_HOST) {
+    CUDA_TRY(h, cudaMemcpyAsync(vote, d_v, size_t(nq) * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return RDB_OK;
+}
+
+int64_t rdb_ntotal(rdb_handle* h) { return h ? h->n : 0; }
+int rdb_dim(rdb_handle* h) { return h ? h->d : 0; }
+int rdb_metric(rdb_handle* h) { return h ? h->metric : -1; }
+int rdb_store_dtype(rdb_handle* h) { return h ? h->store : -1; }
+int64_t rdb_launch_count(rdb_handle* h) { return h ? h->launches : 0; }
+
+int rdb_set_id_offset(rdb_handle* h, int64_t offset) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  h->id_offset = offset;
+  return RDB_OK;
+}
+
+int rdb_last_kernel_ms(rdb_handle* h, float* ms, int* algo, int* nsplits) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  if (!h->ev_valid) return fail(h, RDB_ERR_INVALID, "no search has run yet");
+  DeviceGuard dg(h->device);
+  CUDA_TRY(h, cudaEventSynchronize(h->ev1));
+  float t = 0.f;
+  CUDA_TRY(h, cudaEventElapsedTime(&t, h->ev0, h->ev1));
+  if (ms) *ms = t;
+  if (algo) *algo = h->last_algo;
+  if (nsplits) *nsplits = h->last_S;
+  return RDB_OK;
+}
+
+int rdb_mem_info(rdb_handle* h, size_t* index_bytes, size_t* free_bytes, size_t* total_bytes) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  DeviceGuard dg(h->device);
+  size_t fr = 0, tot = 0;
+  CUDA_TRY(h, cudaMemGetInfo(&fr, &tot));
+  size_t ib = 0;
+  if (h->has_master()) ib += size_t(h->cap) * h->d * 4;
+  ib += size_t(h->cap) * h->dp * 2 * (h->has_lo() ? 2 : 1);
+  ib += size_t(h->cap) * 4 + size_t(h->nlabels) * 4;
+  if (index_bytes) *index_bytes = ib;
+  if (free_bytes) *free_bytes = fr;
+  if (total_bytes) *total_bytes = tot;
+  return RDB_OK;
+}
+
+// ---- faiss IndexFlat on-disk layout (faiss/impl/index_write.cpp, v1.10): u32 fourcc, i32 d, i64 ntotal,
+//      i64 dummy, i64 dummy, u8 is_trained, i32 metric_type (0 = IP, 1 = L2), u64 count (= ntotal * d floats), data.
+static uint32_t fourcc(const char* s) { return uint32_t(uint8_t(s[0])) | uint32_t(uint8_t(s[1])) << 8 | uint32_t(uint8_t(s[2])) << 16 | uint32_t(uint8_t(s[3])) << 24; }
+
+int rdb_serialize(rdb_handle* h, const char* path) {
+  if (!h || !path) return fail(h, RDB_ERR_INVALID, "serialize: bad arguments");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(h, RDB_ERR_IO, std::string("serialize: cannot open ") + path);
+  const uint32_t cc = fourcc(h->metric == RDB_METRIC_IP ? "IxFI" : "IxF2");
+  const int32_t d = h->d; const int64_t n = h->n, dummy = 1 << 20; const uint8_t trained = 1;
+  const int32_t metric = h->metric == RDB_METRIC_IP ? 0 : 1; const uint64_t count = uint64_t(n) * uint64_t(d);
+  bool ok = fwrite(&cc, 4, 1, f) == 1 && fwrite(&d, 4, 1, f) == 1 && fwrite(&n, 8, 1, f) == 1 &&
+            fwrite(&dummy, 8, 1, f) == 1 && fwrite(&dummy, 8, 1, f) == 1 && fwrite(&trained, 1, 1, f) == 1 &&
+            fwrite(&metric, 4, 1, f) == 1 && fwrite(&count, 8, 1, f) == 1;
+  const int64_t chunk = std::max<int64_t>(1, (int64_t(64) << 20) / (int64_t(d) * 4));
+  std::vector<float> host(size_t(std::min(chunk, std::max<int64_t>(n, 1))) * d);
+  for (int64_t r0 = 0; ok && r0 < n; r0 += chunk) {
+    const int64_t m = std::min(chunk, n - r0);
+    const float* src;
+    if (h->has_master()) src = h->master + r0 * d;
+    else {
+      if (h->rec_stage.ensure(size_t(m) * d * 4) != cudaSuccess) { ok = false; break; }
+      const int warps = 8;
+      dim3 grid(unsigned((m + warps - 1) / warps)), block(32 * warps);
+      if (h->f16()) gather_rows_kernel<__half><<<grid, block, 0, h->stream>>>(nullptr, m, h->n, h->d, h->dp, nullptr, (const __half*)h->hi, 0, r0, h->rec_stage.as<float>());
+      else gather_rows_kernel<__nv_bfloat16><<<grid, block, 0, h->stream>>>(nullptr, m, h->n, h->d, h->dp, nullptr, (const __nv_bfloat16*)h->hi, 0, r0, h->rec_stage.as<float>());
+      h->launches++;
+      src = h->rec_stage.as<float>();
+    }
+    if (cudaMemcpyAsync(host.data(), src, size_t(m) * d * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+    ok = fwrite(host.data(), 4, size_t(m) * d, f) == size_t(m) * d;
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) return fail(h, RDB_ERR_IO, std::string("serialize: write to ") + path + " failed");
+  return RDB_OK;
+}
+
+int rdb_deserialize(const char* path, int store_dtype, int device, unsigned flags, rdb_handle** out) {
+  if (!path || !out) return fail(nullptr, RDB_ERR_INVALID, "deserialize: bad arguments");
+  *out = nullptr;
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(nullptr, RDB_ERR_IO, std::string("deserialize: cannot open ") + path);
+  uint32_t cc = 0; int32_t d = 0, metric = 0; int64_t n = 0, dummy = 0; uint8_t trained = 0; uint64_t count = 0;
+  bool ok = fread(&cc, 4, 1, f) == 1 && fread(&d, 4, 1, f) == 1 && fread(&n, 8, 1, f) == 1 &&
+            fread(&dummy, 8, 1, f) == 1 && fread(&dummy, 8, 1, f) == 1 && fread(&trained, 1, 1, f) == 1 &&
+            fread(&metric, 4, 1, f) == 1;
+  if (ok && metric > 1) { float arg; ok = fread(&arg, 4, 1, f) == 1; }
+  ok = ok && fread(&count, 8, 1, f) == 1;
+  if (!ok || (cc != fourcc("IxF2") && cc != fourcc("IxFI") && cc != fourcc("IxFl")) || d < 1 || n < 0 ||
+      count != uint64_t(n) * uint64_t(d)) {
+    fclose(f);
+    return fail(nullptr, RDB_ERR_IO, std::string("deserialize: ") + path + " is not a faiss IndexFlat file");
+  }
+  if (metric != 0 && metric != 1) { fclose(f); return fail(nullptr, RDB_ERR_UNSUPPORTED, "deserialize: metric type not L2/IP"); }
+  rdb_handle* h = nullptr;
+  int rc = rdb_create(d, metric == 0 ? RDB_METRIC_IP : RDB_METRIC_L2, store_dtype, device, flags, &h);
+  if (rc) { fclose(f); return rc; }
+  rc = rdb_reserve(h, n);
+  const int64_t chunk = std::max<int64_t>(1, (int64_t(64) << 20) / (int64_t(d) * 4));
+  std::vector<float> host(size_t(std::min(chunk, std::max<int64_t>(n, 1))) * d);
+  for (int64_t r0 = 0; rc == RDB_OK && r0 < n; r0 += chunk) {
+    const int64_t m = std::min(chunk, n - r0);
+    if (fread(host.data(), 4, size_t(m) * d, f) != size_t(m) * d) { rc = fail(nullptr, RDB_ERR_IO, "deserialize: truncated file"); break; }
+    rc = rdb_add(h, host.data(), m, RDB_MEM_HOST, 0);
+    if (rc) g_err = h->err;
+  }
+  fclose(f);
+  if (rc) { rdb_destroy(h); return rc; }
+  *out = h;
+  return RDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+// Kernel 2 -- score + select on tcgen05 tensor cores (the headline path).
+//
+// S = Q[nq, D] x Y[N, D]^T is never written to HBM.  A persistent, warp-specialised CTA owns one 128-query
+// tile (the 128 TMEM lanes) and walks a contiguous chunk of database rows in 256-row tiles:
+//
+//   warp 0   TMA producer : K-slices (64 bf16 = one 128-byte swizzle atom) of the query tile and the DB tile
+//                           into a 4-stage shared-memory ring (mbarrier full/empty).
+//   warp 1   MMA issuer   : one elected thread issues tcgen05.mma.kind::f16 (M=128, N=256, K=16), fp32
+//                           accumulators double-buffered in TMEM (2 x 256 of 512 columns).
+//   warps 2-5 epilogue    : tcgen05.ld 32x32b -> each thread owns ONE query row, applies the L2 fix-up
+//                           (key = 2 q.y - |y|^2), threshold-filters against its running k-th best and inserts
+//                           the rare survivors into a register-resident sorted list.  MMA of tile t+1
+//                           overlaps selection of tile t.
+//
+// Work units are (query tile, DB chunk) pairs, ordered chunk-major so that the CTAs running concurrently
+// stream the SAME database tiles (served from L2 after the first fetch) against different query tiles.
+// Each unit writes its [128, kout] partial result; merge.cuh folds the S partial lists per query.
+//
+// Split-precision mode (nterms = 3) scores fp32 data as q_lo.y_hi + q_hi.y_lo + q_hi.y_hi with
+// hi = bf16(x), lo = bf16(x - hi): relative error <= 3 * 2^-18 |q||y| before the exact fp32 re-rank.
+//
+// Reference being replaced: faiss GpuIndexFlat::search reached from vector_database.py:181.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace rdb {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 256;
+constexpr int TC_BK = 64;
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 512;
+constexpr size_t tc_smem_bytes() { return size_t(TC_STAGES) * TC_STAGE_BYTES + 256 + 1024; }
+
+struct TcParams {
+  CUtensorMap tmap_q[2];  // [0] = hi, [1] = lo   bf16/f16 [nq, D], box {64, 128}, SWIZZLE_128B
+  CUtensorMap tmap_y[2];  // [0] = hi, [1] = lo   bf16/f16 [N,  D], box {64, 256}, SWIZZLE_128B
+  const float* ynorm;     // [N] |y|^2 (L2 only)
+  float* cand_key;        // [nq][S][kout]
+  int* cand_idx;          // [nq][S][kout]  local row ids, -1 = empty
+  int nq, N, D;
+  int nqt, S, tiles_per_chunk, ntiles, kout, num_units, nterms;
+  uint32_t idesc;
+};
+
+// value of element j (dynamic) of a register array, as a 31-select tree (keeps the array in registers)
+__device__ __forceinline__ float sel32(const float (&v)[32], int j) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+  float b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+  float c[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+  const float d0 = (j & 8) ? c[1] : c[0];
+  const float d1 = (j & 8) ? c[3] : c[2];
+  return (j & 16) ? d1 : d0;
+}
+
+__device__ __forceinline__ void tc_load_yn(float4 (&y)[8], const float* __restrict__ ynorm, int col0) {
+  const float4* yn4 = reinterpret_cast<const float4*>(ynorm + col0);  // col0 % 32 == 0; ynorm is padded to tiles
+#pragma unroll
+  for (int g = 0; g < 8; ++g) y[g] = __ldg(yn4 + g);
+}
+
+template <int KT, bool L2>
+__device__ __forceinline__ void tc_process32(uint32_t (&r)[32], TopK<KT>& top, const float4 (&y)[8],
+                                             int col0 /*global row id of column 0 of this group*/, int nvalid) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (L2) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      v[4 * g + 0] = fmaf(2.0f, v[4 * g + 0], -y[g].x);
+      v[4 * g + 1] = fmaf(2.0f, v[4 * g + 1], -y[g].y);
+      v[4 * g + 2] = fmaf(2.0f, v[4 * g + 2], -y[g].z);
+      v[4 * g + 3] = fmaf(2.0f, v[4 * g + 3], -y[g].w);
+    }
+  }
+  const float worst = top.worst();
+  uint32_t mask = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) mask |= (v[j] > worst) ? (1u << j) : 0u;
+  if (nvalid < 32) mask &= (nvalid <= 0) ? 0u : (0xFFFFFFFFu >> (32 - nvalid));
+  while (mask) {
+    const int j = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const float x = sel32(v, j);
+    if (x > top.worst()) top.insert(x, col0 + j);
+  }
+  __syncwarp();
+}
+
+template <int KT, bool L2>
+__global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tfull_bar = empty_bar + TC_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_q[0]);
+    tma_prefetch_desc(&p.tmap_y[0]);
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int nks = (p.D + TC_BK - 1) / TC_BK;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        const int qtile = unit % p.nqt, chunk = unit / p.nqt;
+        const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
+        for (int t = t0; t < t1; ++t) {
+          for (int term = 0; term < p.nterms; ++term) {
+            // nterms == 1: (hi, hi).  nterms == 3: (lo, hi), (hi, lo), (hi, hi) -- small terms first.
+            const int qsel = (p.nterms == 3 && term == 0) ? 1 : 0;
+            const int ysel = (p.nterms == 3 && term == 1) ? 1 : 0;
+            for (int ks = 0; ks < nks; ++ks) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * TC_STAGE_BYTES;
+              mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+              tma_load_2d(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, kEvictLast);
+              tma_load_2d(sa + TC_A_BYTES, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK, t * TC_BN, kEvictNormal);
+              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        const int chunk = unit / p.nqt;
+        const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + uint32_t(acc * TC_BN);
+          const int nslices = nks * p.nterms;
+          for (int ks = 0; ks < nslices; ++ks) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+            const uint64_t da = make_sw128_kmajor_desc(sa);
+            const uint64_t db = make_sw128_kmajor_desc(sa + TC_A_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / 16; ++kk) {
+              // +32 bytes per K=16 step inside the 128-byte swizzle atom (descriptor address unit = 16 B)
+              umma_f16_ss(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), p.idesc, (ks | kk) != 0);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: fused top-k
+    const int ew = warp & 3;                 // TMEM lane group this warp may access
+    const int row = ew * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      const int qtile = unit % p.nqt, chunk = unit / p.nqt;
+      const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
+      TopK<KT> top;
+      top.init();
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * TC_BN);
+        const int n0 = t * TC_BN;
+        const int nvalid = p.N - n0;         // >= 256 for full tiles
+        uint32_t ra[32], rb[32];
+        float4 ya[8], yb[8];
+        if (L2) tc_load_yn(ya, p.ynorm, n0);
+        tmem_ld_32x32(taddr, ra);
+#pragma unroll
+        for (int c = 0; c < TC_BN / 32; c += 2) {
+          if (L2) tc_load_yn(yb, p.ynorm, n0 + (c + 1) * 32);
+          tmem_ld_wait_regs(ra);
+          tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+          tc_process32<KT, L2>(ra, top, ya, n0 + c * 32, nvalid - c * 32);
+          if (L2 && c + 2 < TC_BN / 32) tc_load_yn(ya, p.ynorm, n0 + (c + 2) * 32);
+          tmem_ld_wait_regs(rb);
+          if (c + 2 < TC_BN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+          else {
+            // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          tc_process32<KT, L2>(rb, top, yb, n0 + (c + 1) * 32, nvalid - (c + 1) * 32);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      const long long q = (long long)qtile * TC_BM + row;
+      if (q < p.nq) {
+        const long long base = (q * p.S + chunk) * (long long)p.kout;
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+          if (j < p.kout) { p.cand_key[base + j] = top.key[j]; p.cand_idx[base + j] = top.idx[j]; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+}
+
+}  // namespace rdb

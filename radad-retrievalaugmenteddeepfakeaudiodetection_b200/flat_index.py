@@ -1,0 +1,272 @@
+"""``FlatIndex`` -- the object behind ``VectorDatabase.index``.
+
+Duck type of the faiss flat index the reference reaches through ``self.index``
+(``vector_database.py:138,151,169,181,210``; ``pipeline.py:465,503,1039``; ``app.py:75,246``):
+``add(x)``, ``search(q, k) -> (D, I)``, ``reconstruct(i)``, ``ntotal``, ``d``, ``is_trained``,
+``train(x)``, ``nprobe``.  All arithmetic runs in ``libradad_flat.so`` (hand-written sm_100a CUDA)
+through the C ABI of ``include/radad_flat.h``; numpy arrays are accepted at the reference boundary,
+torch CUDA tensors on the device-resident fast path (no host round trip).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import (ALGO_AUTO, ALGO_SIMT, ALGO_TC, FLAG_KEEP_F32_MASTER, MEM_DEVICE, MEM_HOST, METRIC_IP,
+                    METRIC_L2, STORE_BF16, STORE_F16, STORE_F32)
+
+_STORE_BY_NAME = {"f32": STORE_F32, "fp32": STORE_F32, "float32": STORE_F32,
+                  "bf16": STORE_BF16, "bfloat16": STORE_BF16,
+                  "f16": STORE_F16, "fp16": STORE_F16, "float16": STORE_F16}
+_STORE_NAME = {STORE_F32: "f32", STORE_BF16: "bf16", STORE_F16: "f16"}
+ALGO_BY_NAME = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC}
+
+
+def _is_cuda_tensor(x) -> bool:
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+class FlatIndex:
+    """Exact flat nearest-neighbour index on one B200 (one row shard)."""
+
+    is_trained = True          # faiss flat indexes need no training (vector_database.py:124)
+
+    def __init__(self, d: int, metric: int = METRIC_L2, store="f32", device: Optional[int] = None,
+                 keep_f32_master: bool = False, _handle=None):
+        self._lib = _cabi.load()
+        self._h = ctypes.c_void_p()
+        self._stream_set = None
+        self.nprobe = 1        # accepted and ignored: the flat index is exhaustive (vector_database.py:176-177)
+        if _handle is not None:
+            self._h = _handle
+        else:
+            st = store if isinstance(store, int) else _STORE_BY_NAME[str(store).lower()]
+            flags = FLAG_KEEP_F32_MASTER if keep_f32_master else 0
+            _cabi.check(self._lib.rdb_create(int(d), int(metric), int(st), -1 if device is None else int(device),
+                                             flags, ctypes.byref(self._h)))
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def ntotal(self) -> int:
+        return int(self._lib.rdb_ntotal(self._h))
+
+    @property
+    def d(self) -> int:
+        return int(self._lib.rdb_dim(self._h))
+
+    @property
+    def metric(self) -> int:
+        return int(self._lib.rdb_metric(self._h))
+
+    @property
+    def metric_type(self) -> int:           # faiss numbering: METRIC_INNER_PRODUCT = 0, METRIC_L2 = 1
+        return 0 if self.metric == METRIC_IP else 1
+
+    @property
+    def store(self) -> str:
+        return _STORE_NAME[int(self._lib.rdb_store_dtype(self._h))]
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.rdb_launch_count(self._h))
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc):
+        _cabi.check(rc, self._h)
+
+    def _use_torch_stream(self, torch):
+        s = torch.cuda.current_stream().cuda_stream
+        if self._stream_set != s:
+            self._check(self._lib.rdb_set_stream(self._h, ctypes.c_void_p(s)))
+            self._stream_set = s
+
+    def _use_own_stream(self):
+        if self._stream_set is not None:
+            self._check(self._lib.rdb_set_stream(self._h, None))
+            self._stream_set = None
+
+    def _as_host_f32(self, x) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise RuntimeError(f"expected float32 [n, {self.d}], got {x.shape}")   # faiss asserts on d
+        return x
+
+    # ------------------------------------------------------------------ faiss surface
+    def train(self, x) -> None:             # no-op (vector_database.py:128)
+        return None
+
+    def reserve(self, n_total: int) -> None:
+        self._check(self._lib.rdb_reserve(self._h, int(n_total)))
+
+    def add(self, x, normalize: bool = False) -> None:
+        """index.add(x) (vector_database.py:138); ``normalize`` fuses _maybe_normalize (:100-105)."""
+        if _is_cuda_tensor(x):
+            import torch
+            x = x.detach().to(torch.float32).contiguous()
+            if x.dim() != 2 or x.shape[1] != self.d:
+                raise RuntimeError(f"expected float32 [n, {self.d}], got {tuple(x.shape)}")
+            self._use_torch_stream(torch)
+            self._check(self._lib.rdb_add(self._h, ctypes.c_void_p(x.data_ptr()), x.shape[0], MEM_DEVICE,
+                                          int(bool(normalize))))
+            return
+        x = self._as_host_f32(x)
+        self._use_own_stream()
+        self._check(self._lib.rdb_add(self._h, x.ctypes.data_as(ctypes.c_void_p), x.shape[0], MEM_HOST,
+                                      int(bool(normalize))))
+
+    def search(self, q, k: int, normalize: bool = False, algo=ALGO_AUTO, return_labels: bool = False):
+        """index.search(q, k) -> (distances float32[nq,k], ids int64[nq,k]) best-first
+        (vector_database.py:181).  torch CUDA queries give torch CUDA results."""
+        k = int(k)
+        algo = ALGO_BY_NAME[algo] if isinstance(algo, str) else int(algo)
+        if _is_cuda_tensor(q):
+            import torch
+            q = q.detach().to(torch.float32).contiguous()
+            if q.dim() != 2 or q.shape[1] != self.d:
+                raise RuntimeError(f"expected float32 [nq, {self.d}], got {tuple(q.shape)}")
+            nq = q.shape[0]
+            D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+            I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+            L = torch.empty((nq, k), dtype=torch.float32, device=q.device) if return_labels else None
+            self._use_torch_stream(torch)
+            self._check(self._lib.rdb_search_algo(
+                self._h, ctypes.c_void_p(q.data_ptr()), nq, k, MEM_DEVICE, int(bool(normalize)), algo,
+                ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
+                ctypes.c_void_p(L.data_ptr()) if L is not None else None))
+            return (D, I, L) if return_labels else (D, I)
+        q = self._as_host_f32(q)
+        nq = q.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        L = np.empty((nq, k), dtype=np.float32) if return_labels else None
+        self._use_own_stream()
+        self._check(self._lib.rdb_search_algo(
+            self._h, q.ctypes.data_as(ctypes.c_void_p), nq, k, MEM_HOST, int(bool(normalize)), algo,
+            D.ctypes.data_as(ctypes.c_void_p), I.ctypes.data_as(ctypes.c_void_p),
+            L.ctypes.data_as(ctypes.c_void_p) if L is not None else None))
+        return (D, I, L) if return_labels else (D, I)
+
+    def reconstruct(self, i: int) -> np.ndarray:
+        """index.reconstruct(i) -> float32[d] (pipeline.py:503)."""
+        out = np.empty((self.d,), dtype=np.float32)
+        self._use_own_stream()
+        self._check(self._lib.rdb_reconstruct(self._h, int(i), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def reconstruct_batch(self, ids):
+        """Rows ``ids`` in one kernel; ids < 0 / out of range give zero rows (pipeline.py:511-512)."""
+        if _is_cuda_tensor(ids):
+            import torch
+            ids = ids.detach().to(torch.int64).contiguous()
+            out = torch.empty(tuple(ids.shape) + (self.d,), dtype=torch.float32, device=ids.device)
+            self._use_torch_stream(torch)
+            self._check(self._lib.rdb_reconstruct_batch(self._h, ctypes.c_void_p(ids.data_ptr()), ids.numel(),
+                                                        MEM_DEVICE, ctypes.c_void_p(out.data_ptr())))
+            return out
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        out = np.empty(ids.shape + (self.d,), dtype=np.float32)
+        self._use_own_stream()
+        self._check(self._lib.rdb_reconstruct_batch(self._h, ids.ctypes.data_as(ctypes.c_void_p), ids.size, MEM_HOST,
+                                                    out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    # ------------------------------------------------------------------ additive API
+    def set_labels(self, labels) -> None:
+        lab = np.ascontiguousarray(labels, dtype=np.float32).reshape(-1)
+        self._use_own_stream()
+        self._check(self._lib.rdb_set_labels(self._h, lab.ctypes.data_as(ctypes.c_void_p), lab.size))
+
+    def set_id_offset(self, offset: int) -> None:
+        self._check(self._lib.rdb_set_id_offset(self._h, int(offset)))
+
+    def search_shard(self, q, k: int, normalize: bool = False):
+        """Per-shard candidates in merge form (torch CUDA in/out): (key, gid, labels, qnorm)."""
+        import torch
+        q = q.detach().to(torch.float32).contiguous()
+        nq = q.shape[0]
+        key = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        gid = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        lab = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        qn = torch.empty((nq,), dtype=torch.float32, device=q.device)
+        self._use_torch_stream(torch)
+        self._check(self._lib.rdb_search_shard(self._h, ctypes.c_void_p(q.data_ptr()), nq, int(k),
+                                               int(bool(normalize)), ctypes.c_void_p(key.data_ptr()),
+                                               ctypes.c_void_p(gid.data_ptr()), ctypes.c_void_p(lab.data_ptr()),
+                                               ctypes.c_void_p(qn.data_ptr())))
+        return key, gid, lab, qn
+
+    def merge_shards(self, key, gid, lab, qnorm):
+        """Merge [nq, nlists, k] candidate lists (torch CUDA) -> (D, I, L) as an unsharded search."""
+        import torch
+        nq, nlists, k = key.shape
+        key, gid, lab = key.contiguous(), gid.contiguous(), lab.contiguous()
+        D = torch.empty((nq, k), dtype=torch.float32, device=key.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=key.device)
+        L = torch.empty((nq, k), dtype=torch.float32, device=key.device)
+        self._use_torch_stream(torch)
+        self._check(self._lib.rdb_merge_shards(self._h, ctypes.c_void_p(key.data_ptr()),
+                                               ctypes.c_void_p(gid.data_ptr()), ctypes.c_void_p(lab.data_ptr()), nq,
+                                               nlists, k, ctypes.c_void_p(qnorm.data_ptr()),
+                                               ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
+                                               ctypes.c_void_p(L.data_ptr())))
+        return D, I, L
+
+    def label_vote(self, labels_nq_k, kvote: int):
+        if _is_cuda_tensor(labels_nq_k):
+            import torch
+            lab = labels_nq_k.contiguous()
+            vote = torch.empty((lab.shape[0],), dtype=torch.float32, device=lab.device)
+            self._use_torch_stream(torch)
+            self._check(self._lib.rdb_label_vote(self._h, ctypes.c_void_p(lab.data_ptr()), lab.shape[0],
+                                                 lab.shape[1], int(kvote), MEM_DEVICE,
+                                                 ctypes.c_void_p(vote.data_ptr())))
+            return vote
+        lab = np.ascontiguousarray(labels_nq_k, dtype=np.float32)
+        vote = np.empty((lab.shape[0],), dtype=np.float32)
+        self._use_own_stream()
+        self._check(self._lib.rdb_label_vote(self._h, lab.ctypes.data_as(ctypes.c_void_p), lab.shape[0],
+                                             lab.shape[1], int(kvote), MEM_HOST,
+                                             vote.ctypes.data_as(ctypes.c_void_p)))
+        return vote
+
+    def sync(self) -> None:
+        self._check(self._lib.rdb_sync(self._h))
+
+    def last_kernel_ms(self) -> Tuple[float, str, int]:
+        ms, algo, ns = ctypes.c_float(), ctypes.c_int(), ctypes.c_int()
+        self._check(self._lib.rdb_last_kernel_ms(self._h, ctypes.byref(ms), ctypes.byref(algo), ctypes.byref(ns)))
+        return float(ms.value), {ALGO_SIMT: "simt", ALGO_TC: "tc"}.get(algo.value, "?"), int(ns.value)
+
+    def mem_info(self):
+        a, b, c = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        self._check(self._lib.rdb_mem_info(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"index_bytes": int(a.value), "free": int(b.value), "total": int(c.value)}
+
+    # ------------------------------------------------------------------ persistence (faiss IndexFlat layout)
+    def save(self, path: str) -> None:
+        self._use_own_stream()
+        self._check(self._lib.rdb_serialize(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path: str, store="f32", device: Optional[int] = None, keep_f32_master: bool = False):
+        lib = _cabi.load()
+        h = ctypes.c_void_p()
+        st = store if isinstance(store, int) else _STORE_BY_NAME[str(store).lower()]
+        _cabi.check(lib.rdb_deserialize(str(path).encode(), int(st), -1 if device is None else int(device),
+                                        FLAG_KEEP_F32_MASTER if keep_f32_master else 0, ctypes.byref(h)))
+        return cls(0, _handle=h)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        h, self._h = self._h, ctypes.c_void_p()
+        if h:
+            self._lib.rdb_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass

@@ -1,0 +1,307 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the golden vectors and the oracle.
+
+Tolerances (BASELINE.json north_star): neighbour ids identical except for ties within 1e-5 relative distance
+for fp32 storage / 1e-3 for bf16 storage; integer-lattice inputs (exact arithmetic) must match BIT-EXACTLY,
+ties broken by the lowest id.
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, Cfg
+
+pytestmark = pytest.mark.gpu
+SEARCH = sorted(glob.glob(os.path.join(GOLDEN, "search_*.npz")))
+TOL_F32, TOL_BF16 = 1e-5, 1e-3
+
+
+def _load(path):
+    z = np.load(path, allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def _fill(vdb, g):
+    n = g["xb"].shape[0]
+    vdb.add_vectors(g["xb"], [f"/data/spk{i % 13}/utt_{i:05d}.wav" for i in range(n)],
+                    [int(v) for v in g["labels"]], {"speaker_id": [f"spk{i % 13}" for i in range(n)]})
+
+
+@pytest.mark.parametrize("path", SEARCH, ids=[os.path.basename(p)[7:-4] for p in SEARCH])
+def test_golden_fp32(pkg, oracle, path, tmp_path):
+    """fp32 store: the drop-in VectorDatabase reproduces what the reference wrapper returned."""
+    g = _load(path)
+    cfg = Cfg(tmp_path / "g", str(g["index_type"]), normalize_for_ip=bool(g["normalize_for_ip"]),
+              vector_add_batch_size=256)
+    vdb = pkg.VectorDatabase(cfg)
+    _fill(vdb, g)
+    k = int(g["k"])
+    D, I = vdb.search_batch(g["xq"], k=k)
+    assert D.dtype == np.float32 and I.dtype == np.int64
+    assert D.shape == g["dist"].shape and I.shape == g["idx"].shape
+    assert vdb.index.ntotal == int(g["ntotal"]) and bool(vdb._cosine) == bool(g["cosine"])
+    assert len(vdb.vector_paths) == int(g["n_paths"])
+    name = os.path.basename(path)
+    metric = oracle.METRIC_IP if str(g["index_type"]) == "IP" else oracle.METRIC_L2
+    if "lattice" in name or "kat_tiny" in name:
+        np.testing.assert_array_equal(I, g["idx"])
+        np.testing.assert_array_equal(D, g["dist"])
+    else:
+        ref = oracle.FlatIndexOracle(g["xb"].shape[1], metric)
+        ref.add(oracle.maybe_normalize(g["xb"], bool(g["cosine"])))
+        qn = oracle.maybe_normalize(g["xq"], bool(g["cosine"]))
+        st = oracle.compare_topk(D, I, g["dist"], g["idx"], lambda ids: ref.exact_scores(qn, ids), metric,
+                                 tol=TOL_F32, abs_floor=2e-5 if metric == oracle.METRIC_L2 else 1e-6)
+        assert st["recall"] == 1.0
+    d1, i1 = vdb.search(g["xq"][0], k=k)
+    assert d1.shape == g["dist_single"].shape
+    np.testing.assert_array_equal(i1, g["idx_single"])
+    dd, di = vdb.search_batch(g["xq"][:2])
+    np.testing.assert_array_equal(di, g["idx_default"])
+    rec = np.stack([vdb.index.reconstruct(int(i)) for i in I[0]])
+    np.testing.assert_allclose(rec, g["recon_row0"], rtol=1e-6, atol=1e-7)
+    # labels gathered on the device == labels[idx]
+    D2, I2, L2 = vdb.search_batch_with_labels(g["xq"], k=k)
+    np.testing.assert_array_equal(I2, I)
+    np.testing.assert_array_equal(L2, g["labels"][I].astype(np.float32))
+
+
+@pytest.mark.parametrize("store", ["bf16", "f16"])
+@pytest.mark.parametrize("algo", ["simt", "tc"])
+@pytest.mark.parametrize("name", ["lattice_l2", "lattice_ip"])
+def test_lattice_bit_exact_16bit_stores(pkg, name, algo, store):
+    """{-2..2} lattice: every product and sum is exact in bf16/f16 x fp32 -> tensor-core and CUDA-core scorers
+    must return the golden ids and distances bit-for-bit (duplicate rows exercise the lowest-id tie rule)."""
+    g = _load(os.path.join(GOLDEN, f"search_{name}.npz"))
+    metric = pkg.METRIC_IP if name.endswith("ip") else pkg.METRIC_L2
+    idx = pkg.FlatIndex(g["xb"].shape[1], metric, store)
+    idx.add(g["xb"][:300])
+    idx.add(g["xb"][300:])
+    D, I = idx.search(g["xq"], int(g["k"]), algo=algo)
+    np.testing.assert_array_equal(I, g["idx"])
+    np.testing.assert_array_equal(D, g["dist"])
+
+
+def _gauss(n, d, seed):
+    return np.random.default_rng(seed).standard_normal((n, d)).astype(np.float32)
+
+
+CASES = [
+    # name            N      D     Q    k   metric cos    store   algo
+    ("c1_cos_f32",    20000, 768,  1000, 10, "IP", True,  "f32",  "simt"),   # BASELINE configs[0]
+    ("l2_f32_ragged", 5003,  200,  77,   15, "L2", False, "f32",  "simt"),
+    ("ip_f32_oddD",   3001,  101,  33,   7,  "IP", False, "f32",  "simt"),   # D % 4 != 0
+    ("l2_bf16_tc",    50000, 768,  512,  10, "L2", False, "bf16", "tc"),
+    ("cos_bf16_tc",   50000, 768,  300,  10, "IP", True,  "bf16", "tc"),
+    ("l2_bf16_tc_k32", 9000, 256,  130,  32, "L2", False, "bf16", "tc"),
+    ("ip_bf16_tc_k1", 4097,  64,   129,  1,  "IP", False, "bf16", "tc"),
+    ("l2_bf16_oddD",  6000,  100,  64,   15, "L2", False, "bf16", "tc"),     # D % 8 != 0 -> padded pitch
+    ("l2_f16_tc",     8000,  320,  96,   16, "L2", False, "f16",  "tc"),
+    ("refD_bf16_tc",  2048,  5376, 256,  15, "L2", False, "bf16", "tc"),     # reference D = 7*768, Q, k
+    ("refD_f32",      1500,  3584, 40,   15, "L2", False, "f32",  "simt"),   # Whisper D = 7*512
+    ("l2_bf16_simt",  7000,  192,  70,   17, "L2", False, "bf16", "simt"),
+    ("ip_bf16_simt_k100", 5000, 128, 50, 100, "IP", False, "bf16", "simt"),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_seeded_gaussian_vs_oracle(pkg, oracle, case):
+    name, N, Dm, Q, k, metric_s, cos, store, algo = case
+    metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
+    xb, xq = _gauss(N, Dm, 1234), _gauss(Q, Dm, 5678)
+    xq[::7] = xb[: len(xq[::7])] + 0.05 * _gauss(len(xq[::7]), Dm, 9)      # near-duplicates of DB rows
+    xq[1] = xb[5]                                                            # exact self-match (distance 0)
+    idx = pkg.FlatIndex(Dm, metric, store)
+    for s in range(0, N, 4096):
+        idx.add(xb[s:s + 4096], normalize=cos)
+    D, I = idx.search(xq, k, normalize=cos, algo=algo)
+    # oracle sees the same stored values: normalise in fp32, then the store's rounding
+    ref = oracle.FlatIndexOracle(Dm, metric, store=store)
+    ref.add(oracle.maybe_normalize(xb, cos))
+    qn = oracle.maybe_normalize(xq, cos)
+    Dr, Ir = ref.search(qn, min(k + 8, N), direct=False)
+    tol = TOL_F32 if store == "f32" else TOL_BF16
+    floor = (2e-5 if store == "f32" else 2e-3) * (float(Dm) ** 0.5 if metric == pkg.METRIC_L2 and not cos else 1.0) \
+        if metric == pkg.METRIC_L2 else 1e-6
+    st = oracle.compare_topk(D, I, Dr, Ir, lambda ids: ref.exact_scores(qn, ids), metric, tol=tol, abs_floor=floor)
+    assert st["recall"] >= 0.999, st
+    # the stored rows come back as the oracle's rounded rows
+    rec = idx.reconstruct_batch(I[0])
+    np.testing.assert_allclose(rec, ref.reconstruct_batch(I[0]), rtol=2e-6 if store == "f32" else 1e-2, atol=1e-7)
+
+
+def test_wrapper_behaviour(pkg, tmp_path):
+    with open(os.path.join(GOLDEN, "wrapper_behaviour.json")) as f:
+        beh = json.load(f)
+    cfg = Cfg(tmp_path / "w", "L2")
+    vdb = pkg.VectorDatabase(cfg)
+    assert vdb.index is None and vdb.gpu_index is None and vdb.vector_paths == [] and vdb.vector_metadata == {}
+    assert vdb.db_path.endswith("faiss_index.bin") and vdb.metadata_path.endswith("metadata.pkl")
+    with pytest.raises(ValueError) as e:
+        vdb.search_batch(np.zeros((1, 8), np.float32))
+    assert str(e.value) == beh["empty_search_error"]
+    vdb.add_vectors(np.zeros((0, 8), np.float32), [], [], {})
+    assert (vdb.index is None) == beh["index_none_after_empty_add"]
+    xb = _gauss(10, 8, 1)
+    vdb.add_vectors_batch(xb, [f"p{i}" for i in range(10)], list(range(10)),
+                          {"split": 7, "speaker_id": [f"s{i}" for i in range(10)]}, batch_size=4)
+    assert vdb.vector_metadata["split"] == beh["meta_split"]
+    assert vdb.vector_metadata["speaker_id"] == beh["meta_speaker"]
+    assert vdb.vector_labels == beh["labels"] and vdb.index.ntotal == 10 and vdb.index.d == 8
+    d0, i0 = vdb.search_batch(xb[:2], k=0)
+    assert [list(d0.shape), list(i0.shape)] == beh["k0_shapes"]
+    assert [str(d0.dtype), str(i0.dtype)] == beh["k0_dtypes"]
+    dk, ik = vdb.search_batch(xb[:3], k=50)                       # k clamped to ntotal (:169)
+    assert dk.shape == (3, 10) and sorted(ik[0].tolist()) == list(range(10))
+    assert ik[0, 0] == 0 and dk[0, 0] == 0.0
+    vdb.save()
+    with open(vdb.metadata_path, "rb") as f:
+        import pickle
+        assert sorted(pickle.load(f).keys()) == beh["pickle_keys"]
+    v2 = pkg.VectorDatabase(cfg)
+    v2.load()
+    assert v2.index.ntotal == beh["loaded_ntotal"] and hasattr(v2, "_cosine") == beh["loaded_has_cosine_attr"]
+    assert v2.vector_labels == beh["loaded_labels"]
+    d2, i2 = v2.search_batch(xb[:3], k=4)
+    d1, i1 = vdb.search_batch(xb[:3], k=4)
+    np.testing.assert_array_equal(i1, i2)
+    np.testing.assert_array_equal(d1, d2)
+    np.testing.assert_array_equal(v2.index.reconstruct(3), xb[3])
+    with pytest.raises(ValueError) as e:
+        pkg.VectorDatabase(Cfg(tmp_path / "b", "HNSW")).create_index(8)
+    assert str(e.value) == beh["bad_type_error"]
+    mem = vdb.get_gpu_memory_usage()
+    assert set(mem) == {"used", "total", "utilization"} and 0 < mem["utilization"] < 1
+    # a failing slice is logged and skipped, lists not extended (:147-149)
+    vdb.add_vectors_batch(_gauss(3, 9, 2), ["a", "b", "c"], [1, 1, 1], {})
+    assert vdb.index.ntotal == 10 and len(vdb.vector_paths) == 10
+    v3 = pkg.VectorDatabase(Cfg(tmp_path / "nothing", "L2"))
+    v3.load()                                                     # missing files: warn, never raise
+    assert v3.index is None
+
+
+def test_cosine_after_load_quirk(pkg, tmp_path):
+    g = _load(os.path.join(GOLDEN, "quirk_cosine_after_load.npz"))
+    cfg = Cfg(tmp_path / "q", "IP")
+    vdb = pkg.VectorDatabase(cfg)
+    vdb.add_vectors(g["xb"], [f"p{i}" for i in range(200)], [0] * 200, {})
+    d_b, i_b = vdb.search_batch(g["xq"], k=5)
+    vdb.save()
+    v2 = pkg.VectorDatabase(cfg)
+    v2.load()
+    d_a, i_a = v2.search_batch(g["xq"], k=5)
+    np.testing.assert_array_equal(i_b, g["i_before"])
+    np.testing.assert_array_equal(i_a, g["i_after"])
+    np.testing.assert_allclose(d_b, g["d_before"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(d_a, g["d_after"], rtol=1e-5, atol=1e-6)
+    cfg.restore_cosine_on_load = True                             # opt-in fix
+    v3 = pkg.VectorDatabase(cfg)
+    v3.load()
+    d_f, i_f = v3.search_batch(g["xq"], k=5)
+    np.testing.assert_array_equal(i_f, g["i_before"])
+
+
+def test_faiss_file_layout(pkg, tmp_path):
+    """faiss IndexFlat layout: fourcc, d, ntotal, 2 dummies, is_trained, metric_type, count, fp32 rows."""
+    import struct
+    xb = _gauss(37, 12, 4)
+    idx = pkg.FlatIndex(12, pkg.METRIC_IP, "f32")
+    idx.add(xb)
+    p = str(tmp_path / "faiss_index.bin")
+    idx.save(p)
+    raw = open(p, "rb").read()
+    assert raw[:4] == b"IxFI"
+    d, n, _, _, trained, metric, count = struct.unpack_from("<iqqqBiQ", raw, 4)
+    assert (d, n, trained, metric, count) == (12, 37, 1, 0, 37 * 12)
+    body = np.frombuffer(raw, dtype=np.float32, offset=4 + 4 + 8 + 8 + 8 + 1 + 4 + 8)
+    np.testing.assert_array_equal(body.reshape(37, 12), xb)
+    back = pkg.FlatIndex.load(p, "bf16")
+    assert back.ntotal == 37 and back.d == 12 and back.metric == pkg.METRIC_IP and back.store == "bf16"
+
+
+@pytest.mark.parametrize("name", ["retrieve_l2", "retrieve_cos"])
+def test_retrieve_similar_vectors_matches_reference_caller(pkg, name, tmp_path):
+    """Our device-resident retrieve_similar_vectors vs what the reference's pipeline.py:449-532 returned."""
+    import torch
+    g = _load(os.path.join(GOLDEN, f"{name}.npz"))
+    K, D = int(g["K"]), g["xb"].shape[1]
+    cfg = Cfg(tmp_path / "r", str(g["index_type"]), top_k=K)
+    vdb = pkg.VectorDatabase(cfg)
+    paths = [str(p) for p in g["paths"]]
+    labels = [torch.tensor(int(l)) for l in g["labels"]]           # 0-d tensors, as pipeline.py:436-441 stores
+    vdb.add_vectors(g["xb"], paths, labels, {"speaker_id": ["s"] * len(paths)})
+    qpaths = [str(p) for p in g["qpaths"]]
+    train_ids = {str(s) for s in g["train_ids"]}
+    q = torch.from_numpy(g["q"]).cuda()
+    for tag, kw in (("excl_paths", dict(query_paths=qpaths, exclude_self=True)),
+                    ("excl_train", dict(query_paths=None, exclude_self=True, training_file_ids=train_ids)),
+                    ("noexcl", dict(query_paths=qpaths, exclude_self=False))):
+        vec, lbl, pth, dst = pkg.retrieve_similar_vectors(vdb, q, K, D, return_info=True, return_distances=True, **kw)
+        assert vec.is_cuda and vec.dtype == torch.float32 and tuple(vec.shape) == (len(qpaths), K, D)
+        assert [list(r) for r in pth] == [list(map(str, r)) for r in g[f"{tag}_paths"]]
+        np.testing.assert_array_equal(lbl.cpu().numpy(), g[f"{tag}_lbl"])
+        # identical neighbour tensors => identical RADADModel logits downstream
+        np.testing.assert_allclose(vec.cpu().numpy(), g[f"{tag}_vec"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(dst.cpu().numpy(), g[f"{tag}_dist"], rtol=1e-4, atol=2e-4, equal_nan=True)
+    # return arities (pipeline.py:526-532)
+    assert len(pkg.retrieve_similar_vectors(vdb, q, K, D, query_paths=qpaths)) == 2
+    assert len(pkg.retrieve_similar_vectors(vdb, q, K, D, query_paths=qpaths, return_info=True)) == 3
+    assert len(pkg.retrieve_similar_vectors(vdb, q, K, D, query_paths=qpaths, return_distances=True)) == 3
+    empty = pkg.VectorDatabase(Cfg(tmp_path / "e", "L2", top_k=K))
+    v, l, p, d = pkg.retrieve_similar_vectors(empty, q, K, D, return_info=True, return_distances=True)
+    assert float(v.abs().sum()) == 0 and p[0] == [""] * K and bool(torch.isnan(d).all())
+
+
+def test_device_tensor_path_and_vote(pkg):
+    import torch
+    xb, xq = _gauss(3000, 64, 1), _gauss(40, 64, 2)
+    labels = (np.arange(3000) % 3 == 0).astype(np.float32)
+    a = pkg.FlatIndex(64, pkg.METRIC_L2, "bf16")
+    a.add(xb)
+    a.set_labels(labels)
+    b = pkg.FlatIndex(64, pkg.METRIC_L2, "bf16")
+    b.add(torch.from_numpy(xb).cuda())                             # ingest straight from a CUDA tensor (f4)
+    b.set_labels(labels)
+    Dh, Ih, Lh = a.search(xq, 10, return_labels=True)
+    Dd, Id, Ld = b.search(torch.from_numpy(xq).cuda(), 10, return_labels=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(Id.cpu().numpy(), Ih)
+    np.testing.assert_array_equal(Dd.cpu().numpy(), Dh)
+    np.testing.assert_array_equal(Lh, labels[Ih])
+    vote = b.label_vote(Ld, 5)
+    np.testing.assert_allclose(vote.cpu().numpy(), labels[Ih][:, :5].sum(1))
+
+
+def test_sharded_single_process_equals_unsharded(pkg):
+    """Row shards + merge kernel == unsharded search (G = 4 shards emulated on one GPU, no collective)."""
+    import torch
+    N, Dm, Q, k = 10007, 128, 65, 10
+    xb, xq = _gauss(N, Dm, 1), _gauss(Q, Dm, 2)
+    xb[5000] = xb[3]
+    xq[0] = xb[3]                                                  # tie across shards -> lowest global id first
+    labels = (np.arange(N) % 2).astype(np.float32)
+    full = pkg.FlatIndex(Dm, pkg.METRIC_L2, "bf16")
+    full.add(xb)
+    full.set_labels(labels)
+    Df, If, Lf = full.search(xq, k, return_labels=True)
+    G = 4
+    keys, gids, labs = [], [], []
+    q = torch.from_numpy(xq).cuda()
+    shards = []
+    for r in range(G):
+        s, e = pkg.shard_bounds(N, G, r)
+        sh = pkg.FlatIndex(Dm, pkg.METRIC_L2, "bf16")
+        sh.set_id_offset(s)
+        sh.add(xb[s:e])
+        sh.set_labels(labels[s:e])
+        kk, gg, ll, qn = sh.search_shard(q, k)
+        keys.append(kk), gids.append(gg), labs.append(ll)
+        shards.append(sh)
+    D, I, L = shards[0].merge_shards(torch.stack(keys, 1), torch.stack(gids, 1), torch.stack(labs, 1), qn)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(I.cpu().numpy(), If)
+    np.testing.assert_array_equal(D.cpu().numpy(), Df)
+    np.testing.assert_array_equal(L.cpu().numpy(), Lf)
+    assert If[0, 0] == 3 and If[0, 1] == 5000

@@ -1,0 +1,59 @@
+"""CPU: host-side logic that needs no GPU -- shard partitioning, candidate packing, comparator, the
+device-resident retrieval's basename coding."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_shard_bounds_cover_and_order(pkg):
+    for n in (0, 1, 7, 256, 10_000_000, 99_999_999):
+        for g in (1, 2, 4, 8):
+            spans = [pkg.shard_bounds(n, g, r) for r in range(g)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 and a0 <= a1 and b0 <= b1
+            assert max(e - s for s, e in spans) == -(-n // g)
+
+
+def test_pack_unpack_roundtrip(pkg):
+    from importlib import import_module
+    sh = import_module(pkg.__name__ + ".sharded")
+    g = torch.Generator().manual_seed(0)
+    key = torch.randn(5, 7, generator=g)
+    key[0, 0] = float("-inf")
+    gid = torch.randint(-1, 2**40, (5, 7), generator=g, dtype=torch.int64)
+    lab = torch.randint(0, 2, (5, 7), generator=g).float()
+    p = sh.pack_candidates(key, gid, lab)
+    assert p.dtype == torch.int32 and p.shape == (5, 7, 4)
+    k2, g2, l2 = sh.unpack_candidates(p)
+    assert torch.equal(k2, key) and torch.equal(g2, gid) and torch.equal(l2, lab)
+
+
+def test_comparator_accepts_ties_and_rejects_errors(oracle):
+    rng = np.random.default_rng(3)
+    xb = rng.standard_normal((500, 16)).astype(np.float32)
+    xb[100] = xb[7]                       # exact duplicate -> tie
+    q = xb[[7, 20]].copy()
+    idx = oracle.FlatIndexOracle(16, oracle.METRIC_L2)
+    idx.add(xb)
+    D, I = idx.search(q, 13)
+    exact = lambda ids: idx.exact_scores(q, ids)   # noqa: E731
+    st = oracle.compare_topk(D[:, :5], I[:, :5], D, I, exact, oracle.METRIC_L2, 1e-5)
+    assert st["recall"] == 1.0
+    swapped = I[:, :5].copy()
+    swapped[0, [0, 1]] = swapped[0, [1, 0]]        # ids 7 and 100 tie at distance 0: either order is fine
+    oracle.compare_topk(D[:, :5], swapped, D, I, exact, oracle.METRIC_L2, 1e-5)
+    wrong = I[:, :5].copy()
+    wrong[1, 4] = 499 if 499 not in I[1] else 498
+    with pytest.raises(AssertionError):
+        oracle.compare_topk(D[:, :5], wrong, D, I, exact, oracle.METRIC_L2, 1e-5)
+
+
+def test_basename_codes(pkg):
+    from importlib import import_module
+    r = import_module(pkg.__name__ + ".retrieval")
+
+    class V:
+        vector_paths = ["/a/x.wav", "/b/x.wav", "/a/y.wav"]
+    codes, table = r._basename_codes(V)
+    assert codes.tolist() == [0, 0, 1] and table == {"x.wav": 0, "y.wav": 1}
