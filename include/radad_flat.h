@@ -55,9 +55,12 @@ int rdb_destroy(rdb_handle* h);
 /* Last error message of this handle (or of the calling thread when h == NULL).  Never NULL. */
 const char* rdb_last_error(rdb_handle* h);
 
-/* Use a caller-owned CUDA stream (cudaStream_t) for all work of this handle; NULL restores the handle's own
- * stream.  rdb_sync blocks until the handle's stream is idle. */
+/* Use a caller-owned CUDA stream (cudaStream_t) for all work of this handle.  The value is used as is: NULL is
+ * the legacy default stream (what torch.cuda.current_stream().cuda_stream returns by default).
+ * rdb_use_own_stream goes back to the handle's private non-blocking stream (the state after rdb_create).
+ * rdb_sync blocks until the handle's current stream is idle. */
 int rdb_set_stream(rdb_handle* h, void* cuda_stream);
+int rdb_use_own_stream(rdb_handle* h);
 int rdb_sync(rdb_handle* h);
 
 /* Pre-size device storage for `n_total` rows (optional; add grows geometrically otherwise). */

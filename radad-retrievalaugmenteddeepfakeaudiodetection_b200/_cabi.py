@@ -31,6 +31,7 @@ SIGNATURES = {
     "rdb_destroy": (c_int, [_h]),
     "rdb_last_error": (c_char_p, [_h]),
     "rdb_set_stream": (c_int, [_h, c_void_p]),
+    "rdb_use_own_stream": (c_int, [_h]),
     "rdb_sync": (c_int, [_h]),
     "rdb_reserve": (c_int, [_h, c_int64]),
     "rdb_add": (c_int, [_h, c_void_p, c_int64, c_int, c_int]),

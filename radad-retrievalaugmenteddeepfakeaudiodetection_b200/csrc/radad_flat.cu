@@ -449,7 +449,16 @@ int rdb_set_stream(rdb_handle* h, void* cuda_stream) {
   std::lock_guard<std::mutex> lock(h->mu);
   DeviceGuard dg(h->device);
   cudaStreamSynchronize(h->stream);
-  h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);   // NULL == legacy default stream
+  return RDB_OK;
+}
+
+int rdb_use_own_stream(rdb_handle* h) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->stream = h->own_stream;
   return RDB_OK;
 }
 

@@ -38,7 +38,7 @@ class FlatIndex:
                  keep_f32_master: bool = False, _handle=None):
         self._lib = _cabi.load()
         self._h = ctypes.c_void_p()
-        self._stream_set = None
+        self._stream_set = "own"
         self.nprobe = 1        # accepted and ignored: the flat index is exhaustive (vector_database.py:176-177)
         if _handle is not None:
             self._h = _handle
@@ -84,9 +84,9 @@ class FlatIndex:
             self._stream_set = s
 
     def _use_own_stream(self):
-        if self._stream_set is not None:
-            self._check(self._lib.rdb_set_stream(self._h, None))
-            self._stream_set = None
+        if self._stream_set != "own":
+            self._check(self._lib.rdb_use_own_stream(self._h))
+            self._stream_set = "own"
 
     def _as_host_f32(self, x) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float32)

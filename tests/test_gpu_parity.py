@@ -123,8 +123,14 @@ def test_seeded_gaussian_vs_oracle(pkg, oracle, case):
     qn = oracle.maybe_normalize(xq, cos)
     Dr, Ir = ref.search(qn, min(k + 8, N), direct=False)
     tol = TOL_F32 if store == "f32" else TOL_BF16
-    floor = (2e-5 if store == "f32" else 2e-3) * (float(Dm) ** 0.5 if metric == pkg.METRIC_L2 and not cos else 1.0) \
-        if metric == pkg.METRIC_L2 else 1e-6
+    # L2 is evaluated as |q|^2 + |y|^2 - 2 q.y (as faiss does): near-duplicates cancel catastrophically, so the
+    # absolute error floor scales with the magnitude of the cancelled terms -- a few fp32 ulps for the exact path,
+    # ~2^-15 for the tensor cores (their fp32 accumulation truncates: measured 2e-5 at D = 5376).
+    if metric == pkg.METRIC_L2:
+        scale = float((qn * qn).sum(1).max() + (ref._base() ** 2).sum(1).max())
+        floor = (2e-6 if (store == "f32" or algo == "simt") else 1e-4) * scale
+    else:
+        floor = 1e-6
     st = oracle.compare_topk(D, I, Dr, Ir, lambda ids: ref.exact_scores(qn, ids), metric, tol=tol, abs_floor=floor)
     assert st["recall"] >= 0.999, st
     # the stored rows come back as the oracle's rounded rows
