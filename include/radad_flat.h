@@ -136,6 +136,11 @@ int64_t rdb_launch_count(rdb_handle* h);
  * its name ("tc" / "simt"); 0 on success. */
 int rdb_last_kernel_ms(rdb_handle* h, float* ms, int* algo, int* nsplits);
 
+/* fp32 stores are searched by a split-precision tensor-core pass + exact fp32 re-rank; queries whose candidate
+ * set cannot be certified against the scorer's error bound are re-searched by the exact CUDA-core kernel.
+ * Returns how many queries of the last search took that fallback. */
+int64_t rdb_last_uncertified(rdb_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,7 @@ SIGNATURES = {
     "rdb_mem_info": (c_int, [_h, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]),
     "rdb_launch_count": (c_int64, [_h]),
     "rdb_last_kernel_ms": (c_int, [_h, POINTER(c_float), POINTER(c_int), POINTER(c_int)]),
+    "rdb_last_uncertified": (c_int64, [_h]),
 }
 
 _lib = None

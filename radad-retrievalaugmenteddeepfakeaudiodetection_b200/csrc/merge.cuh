@@ -108,41 +108,47 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
 }
 
 // Exact fp32 re-rank.  One warp per query.
-//   cand_idx [Q][kc] local ids (from the approximate pass, -1 = empty), cand_key [Q][kc] approximate keys
+//   cand_idx [Q][kc] local ids from the approximate pass (best-first, -1 = empty), cand_key [Q][kc] approximate keys
 //   qf [Q, D] fp32 (already normalised), master [N, D] fp32, ynorm [N]
-// Writes exact keys back in best-first order (key desc, id asc) into out_key/out_idx [Q][kc] and a per-query
-// certificate: cert[q] = 1 iff  exact_key[kout-1] - approx_key_worst > margin[q], i.e. no row outside the
-// candidate set can belong to the exact top-kout given the approximate scorer's error bound `eps * |q| |y|max`.
+// Writes exact keys in best-first order (key desc, id asc) into out_key/out_idx [Q][kc] and a per-query
+// certificate.  Let B = eps * |q| * max|y| (x2 for the L2 key 2 q.y - |y|^2) bound |approx - exact|.  A row outside
+// the candidate set has approx key <= the worst candidate's approx key, hence exact key <= approx_worst + B.  If the
+// exact kout-th key is strictly above that, no outside row can enter the exact top-kout:
+//   cert[q] = 1  iff  exact_key[kout-1] > approx_worst + B        (or the candidate set holds every row).
+// Uncertified queries are appended to `uncert_list` (count in uncert_count) for the exact fallback.
 template <bool L2>
-__global__ void __launch_bounds__(128) rerank_exact_kernel(const int* __restrict__ cand_idx,
+__global__ void __launch_bounds__(128) rerank_exact_kernel(const long long* __restrict__ cand_idx,
                                                            const float* __restrict__ cand_key, int Q, int kc, int kout,
                                                            const float* __restrict__ qf,
                                                            const float* __restrict__ master,
-                                                           const float* __restrict__ ynorm, int D, float eps_scale,
-                                                           const float* __restrict__ qnorm, float ynorm_max_sqrt,
-                                                           float* __restrict__ out_key, int* __restrict__ out_idx,
-                                                           int* __restrict__ cert) {
+                                                           const float* __restrict__ ynorm, int D, float eps,
+                                                           const float* __restrict__ qnorm,
+                                                           const float* __restrict__ ynorm_max, long long ntotal,
+                                                           float* __restrict__ out_key,
+                                                           long long* __restrict__ out_idx,
+                                                           int* __restrict__ uncert_list,
+                                                           int* __restrict__ uncert_count) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= Q) return;
   const float* qr = qf + (long long)q * D;
   float my_key = -CUDART_INF_F;
-  int my_id = -1;
-  float approx_worst = CUDART_INF_F;   // smallest approximate key among the candidates (the admission threshold)
+  long long my_id = -1;
+  float approx_worst = CUDART_INF_F;
   int nvalid = 0;
   for (int j = 0; j < kc; ++j) {
-    const int id = cand_idx[(long long)q * kc + j];
+    const long long id = cand_idx[(long long)q * kc + j];
     if (id < 0) continue;
     ++nvalid;
     approx_worst = fminf(approx_worst, cand_key[(long long)q * kc + j]);
-    const float* yr = master + (long long)id * D;
+    const float* yr = master + id * (long long)D;
     float s = 0.f;
     for (int c = lane; c < D; c += 32) s = fmaf(qr[c], __ldg(yr + c), s);
     s = warp_sum(s);
     const float key = L2 ? fmaf(2.0f, s, -ynorm[id]) : s;
     if (lane == j) { my_key = key; my_id = id; }
   }
-  // rank by counting (kc <= 32)
+  // rank by counting (kc <= 32): number of candidates strictly better than mine
   const uint32_t mok = (my_id >= 0) ? ordered_f32(my_key) : 0u;
   const long long mid = (my_id >= 0) ? my_id : 0x7FFFFFFFFFFFFFFFll;
   int rank = 0;
@@ -151,7 +157,6 @@ __global__ void __launch_bounds__(128) rerank_exact_kernel(const int* __restrict
     const long long oid = __shfl_sync(0xffffffffu, mid, j);
     if (j != lane && head_better(ook, oid, mok, mid)) ++rank;
   }
-  // distinct ranks for invalid slots: count invalid lanes below me
   const uint32_t invalid_mask = __ballot_sync(0xffffffffu, lane < kc && my_id < 0);
   if (lane < kc) {
     int pos = rank;
@@ -159,17 +164,48 @@ __global__ void __launch_bounds__(128) rerank_exact_kernel(const int* __restrict
     out_key[(long long)q * kc + pos] = (my_id >= 0) ? my_key : -CUDART_INF_F;
     out_idx[(long long)q * kc + pos] = my_id;
   }
-  // certificate
-  const int kth_lane_rank = kout - 1;
-  const uint32_t has = __ballot_sync(0xffffffffu, lane < kc && my_id >= 0 && rank == kth_lane_rank);
+  const uint32_t has = __ballot_sync(0xffffffffu, lane < kc && my_id >= 0 && rank == kout - 1);
   float kth_key = -CUDART_INF_F;
   if (has) kth_key = __shfl_sync(0xffffffffu, my_key, __ffs(has) - 1);
-  if (lane == 0 && cert) {
-    // |approx - exact| <= eps_scale * |q| * |y|  (x2 for the L2 key = 2 q.y - |y|^2)
-    const float bound = eps_scale * sqrtf(qnorm[q]) * ynorm_max_sqrt * (L2 ? 2.0f : 1.0f);
-    // a row outside the candidate set has approx key <= approx_worst, hence exact key <= approx_worst + bound
-    cert[q] = (nvalid < kc) ? 1 : ((kth_key > approx_worst + bound) ? 1 : 0);
+  if (lane == 0) {
+    const float bound = eps * sqrtf(qnorm[q]) * sqrtf(*ynorm_max) * (L2 ? 2.0f : 1.0f);
+    const bool ok = (nvalid >= ntotal) || (nvalid == kc && has && kth_key > approx_worst + bound);
+    if (!ok) uncert_list[atomicAdd(uncert_count, 1)] = q;
   }
+}
+
+// max over rows of |y|^2 (positive floats order like their bit patterns) -- feeds the re-rank certificate
+__global__ void ynorm_max_kernel(const float* __restrict__ ynorm, long long n, float* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, ynorm[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
+// rows list[i] of src [*, D] -> dst [m, D]   (compact the uncertified queries)
+__global__ void gather_f32_rows_kernel(const float* __restrict__ src, const int* __restrict__ list, int m, int D,
+                                       float* __restrict__ dst) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= m) return;
+  const float* s = src + (long long)list[w] * D;
+  float* d = dst + (long long)w * D;
+  for (int c = (threadIdx.x & 31); c < D; c += 32) d[c] = s[c];
+}
+
+// scatter rows of the fallback results back to their query slots
+__global__ void scatter_results_kernel(const int* __restrict__ list, int m, int k, const float* __restrict__ s_a,
+                                       const long long* __restrict__ s_i, const float* __restrict__ s_l,
+                                       float* __restrict__ d_a, long long* __restrict__ d_i,
+                                       float* __restrict__ d_l) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m * k) return;
+  const int r = t / k, j = t % k;
+  const long long o = (long long)list[r] * k + j;
+  d_a[o] = s_a[t];
+  d_i[o] = s_i[t];
+  if (d_l && s_l) d_l[o] = s_l[t];
 }
 
 // sum of neighbour labels per query over the first kvote results (the "kNN label vote" evidence)

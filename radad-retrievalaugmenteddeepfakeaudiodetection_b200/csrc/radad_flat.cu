@@ -89,6 +89,9 @@ struct rdb_handle {
   std::mutex mu;
   // scratch
   DevBuf add_stage, q_stage, qf, qhi, qlo, qnorm, cand_key, cand_idx, o_dist, o_idx, o_lbl, ids_stage, rec_stage;
+  DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l;
+  float* d_ynorm_max = nullptr;   // max |y|^2 over the shard (device scalar; feeds the re-rank certificate)
+  int64_t last_uncertified = 0;
   bool has_master() const { return store == RDB_STORE_F32 || (flags & RDB_FLAG_KEEP_F32_MASTER); }
   bool has_hi() const { return true; }
   bool has_lo() const { return store == RDB_STORE_F32; }
@@ -211,22 +214,24 @@ int launch_simt_t(rdb_handle* h, const T* Q, const T* Y, int nq, int ld, int nqt
 }
 
 template <int KT, bool L2>
-int launch_simt_k(rdb_handle* h, int nq, int nqt, int S, int rows_per_chunk, float* ck, int* ci, int kout) {
+int launch_simt_k(rdb_handle* h, const float* qf, const void* qhi, int nq, int nqt, int S, int rows_per_chunk,
+                  float* ck, int* ci, int kout) {
   if (h->store == RDB_STORE_F32) {
-    const float* Q = h->qf.as<float>();
+    const float* Q = qf;
     if (h->d % 4 == 0) return launch_simt_t<KT, L2, float, true>(h, Q, h->master, nq, h->d, nqt, S, rows_per_chunk, ck, ci, kout);
     return launch_simt_t<KT, L2, float, false>(h, Q, h->master, nq, h->d, nqt, S, rows_per_chunk, ck, ci, kout);
   }
   if (h->f16())
-    return launch_simt_t<KT, L2, __half, true>(h, h->qhi.as<__half>(), (const __half*)h->hi, nq, h->dp, nqt, S, rows_per_chunk, ck, ci, kout);
-  return launch_simt_t<KT, L2, __nv_bfloat16, true>(h, h->qhi.as<__nv_bfloat16>(), (const __nv_bfloat16*)h->hi, nq, h->dp, nqt, S, rows_per_chunk, ck, ci, kout);
+    return launch_simt_t<KT, L2, __half, true>(h, (const __half*)qhi, (const __half*)h->hi, nq, h->dp, nqt, S, rows_per_chunk, ck, ci, kout);
+  return launch_simt_t<KT, L2, __nv_bfloat16, true>(h, (const __nv_bfloat16*)qhi, (const __nv_bfloat16*)h->hi, nq, h->dp, nqt, S, rows_per_chunk, ck, ci, kout);
 }
 
-int launch_simt(rdb_handle* h, int nq, int k, int nqt, int S, int rows_per_chunk, float* ck, int* ci) {
+int launch_simt(rdb_handle* h, const float* qf, const void* qhi, int nq, int k, int nqt, int S, int rows_per_chunk,
+                float* ck, int* ci) {
   const bool l2 = h->metric == RDB_METRIC_L2;
 #define SIMT_CASE(KT)                                                                          \
-  return l2 ? launch_simt_k<KT, true>(h, nq, nqt, S, rows_per_chunk, ck, ci, k)                \
-            : launch_simt_k<KT, false>(h, nq, nqt, S, rows_per_chunk, ck, ci, k)
+  return l2 ? launch_simt_k<KT, true>(h, qf, qhi, nq, nqt, S, rows_per_chunk, ck, ci, k)       \
+            : launch_simt_k<KT, false>(h, qf, qhi, nq, nqt, S, rows_per_chunk, ck, ci, k)
   if (k <= 16) { SIMT_CASE(16); }
   if (k <= 32) { SIMT_CASE(32); }
   if (k <= 64) { SIMT_CASE(64); }
@@ -249,15 +254,15 @@ int encode_2d(rdb_handle* h, CUtensorMap* m, const void* base, int64_t rows, int
   return RDB_OK;
 }
 
-int launch_tc(rdb_handle* h, int nq, int k, int nqt, int S, int tiles_per_chunk, int ntiles, int nterms, float* ck,
-              int* ci) {
+int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, int nqt, int S, int tiles_per_chunk,
+              int ntiles, int nterms, float* ck, int* ci) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   int rc;
-  if ((rc = encode_2d(h, &p.tmap_q[0], h->qhi.p, nq, h->d, h->dp, TC_BM))) return rc;
+  if ((rc = encode_2d(h, &p.tmap_q[0], qhi, nq, h->d, h->dp, TC_BM))) return rc;
   if ((rc = encode_2d(h, &p.tmap_y[0], h->hi, h->n, h->d, h->dp, TC_BN))) return rc;
   if (nterms == 3) {
-    if ((rc = encode_2d(h, &p.tmap_q[1], h->qlo.p, nq, h->d, h->dp, TC_BM))) return rc;
+    if ((rc = encode_2d(h, &p.tmap_q[1], qlo, nq, h->d, h->dp, TC_BM))) return rc;
     if ((rc = encode_2d(h, &p.tmap_y[1], h->lo, h->n, h->d, h->dp, TC_BN))) return rc;
   } else {
     p.tmap_q[1] = p.tmap_q[0];
@@ -286,7 +291,61 @@ int launch_tc(rdb_handle* h, int nq, int k, int nqt, int S, int tiles_per_chunk,
 
 constexpr int64_t kQueryBatch = 65536;
 constexpr int kMaxK = 128;
-constexpr int kMaxKTc = 32;
+constexpr int kMaxKTc = 32;        // register-resident list of the tensor-core epilogue
+constexpr int kMaxKSplit = 24;     // split-precision path keeps kc = 16 / 32 candidates: slack >= 6
+constexpr int64_t kMinRowsTc = 1024;
+
+struct QueryView {
+  const float* qf;    // fp32 [nq, D] (fp32 stores)
+  const void* qhi;    // 16-bit [nq, Dp]
+  const void* qlo;    // 16-bit [nq, Dp] (split-precision)
+  const float* qnorm; // [nq]
+  int nq;
+};
+
+// score + select over the local shard into h->cand_key / h->cand_idx; *L_out = lists per query (width kc each)
+int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc, int* L_out, bool timed) {
+  int rc, S, tpc;
+  const int nqt = (qv.nq + 127) / 128;
+  cudaStream_t s = h->stream;
+  if (algo == RDB_ALGO_TC) {
+    const int ntiles = int((h->n + TC_BN - 1) / TC_BN);
+    S = choose_splits(nqt, ntiles, h->num_sms, 256, 4, &tpc);
+    CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * kc * 4));
+    CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * kc * 4));
+    if (timed) cudaEventRecord(h->ev0, s);
+    if ((rc = launch_tc(h, qv.qhi, qv.qlo, qv.nq, kc, nqt, S, tpc, ntiles, nterms, h->cand_key.as<float>(),
+                        h->cand_idx.as<int>()))) return rc;
+    if (timed) cudaEventRecord(h->ev1, s);
+    *L_out = S;
+  } else {
+    const int ntiles = int((h->n + SIMT_BN - 1) / SIMT_BN);
+    S = choose_splits(nqt, ntiles, 2 * h->num_sms, 256 / SIMT_LISTS, 2, &tpc);
+    CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * SIMT_LISTS * kc * 4));
+    CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * SIMT_LISTS * kc * 4));
+    if (timed) cudaEventRecord(h->ev0, s);
+    if ((rc = launch_simt(h, qv.qf, qv.qhi, qv.nq, kc, nqt, S, tpc * SIMT_BN, h->cand_key.as<float>(),
+                          h->cand_idx.as<int>()))) return rc;
+    if (timed) cudaEventRecord(h->ev1, s);
+    *L_out = S * SIMT_LISTS;
+  }
+  if (timed) { h->ev_valid = true; h->last_algo = algo; h->last_S = S; }
+  return RDB_OK;
+}
+
+// fold the local candidate lists: final form (dist or key, global id, label)
+int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float* qnorm, bool shard_mode, float* d_a,
+                    int64_t* d_i, float* d_l, long long id_offset, const float* labels, float* raw_key) {
+  const int warps = 4;
+  dim3 grid((nq + warps - 1) / warps), block(32 * warps);
+  merge_lists_kernel<int><<<grid, block, 0, h->stream>>>(
+      h->cand_key.as<float>(), h->cand_idx.as<int>(), nullptr, nq, L, kc, kout, h->metric == RDB_METRIC_L2 ? 1 : 0,
+      qnorm, id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l,
+      shard_mode ? d_a : raw_key);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return RDB_OK;
+}
 
 // One search over the local shard.  shard_mode: out_a receives merge keys instead of distances.
 int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int normalize, int algo, bool shard_mode,
@@ -302,12 +361,17 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   const bool host = mem == RDB_MEM_HOST;
   const bool l2 = h->metric == RDB_METRIC_L2;
   const bool sixteen = h->store != RDB_STORE_F32;
-  const bool tc_ok = sixteen && k <= kMaxKTc && h->n >= 1024;
-  if (algo == RDB_ALGO_AUTO) algo = tc_ok ? RDB_ALGO_TC : RDB_ALGO_SIMT;
-  if (algo == RDB_ALGO_TC && !(sixteen && k <= kMaxKTc && h->n >= TC_BN))
-    return fail(h, RDB_ERR_UNSUPPORTED, "search: tensor-core scorer needs a 16-bit store, k <= 32 and ntotal >= 256");
+  // scorer selection.  16-bit stores: tcgen05 (1 term).  fp32 stores: split-precision tcgen05 (3 terms) + exact
+  // fp32 re-rank + certificate, exact CUDA-core kernel for whatever cannot be certified (and for small cases).
+  const bool tc_ok = sixteen ? (k <= kMaxKTc && h->n >= TC_BN) : (k <= kMaxKSplit && h->n >= TC_BN);
+  if (algo == RDB_ALGO_AUTO) algo = (tc_ok && h->n >= kMinRowsTc) ? RDB_ALGO_TC : RDB_ALGO_SIMT;
+  if (algo == RDB_ALGO_TC && !tc_ok)
+    return fail(h, RDB_ERR_UNSUPPORTED,
+                "search: tensor-core scorer needs ntotal >= 256 and k <= 32 (16-bit store) / k <= 24 (fp32 store)");
+  const bool split = (algo == RDB_ALGO_TC) && !sixteen;
   const float* labels = (h->labels && h->nlabels == h->n) ? h->labels : nullptr;
   cudaStream_t s = h->stream;
+  h->last_uncertified = 0;
 
   for (int64_t b0 = 0; b0 < nq; b0 += kQueryBatch) {
     const int nb = int(std::min<int64_t>(kQueryBatch, nq - b0));
@@ -320,40 +384,22 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
     // ---- query prep: normalise, |q|^2, convert (same fused kernel as ingest)
     CUDA_TRY(h, h->qnorm.ensure(size_t(nb) * 4));
     int rc;
+    QueryView qv{nullptr, nullptr, nullptr, h->qnorm.as<float>(), nb};
     if (sixteen) {
       CUDA_TRY(h, h->qhi.ensure(size_t(nb) * Dp * 2));
       if ((rc = launch_ingest(h, qsrc, nb, normalize, 1, nullptr, h->qhi.p, nullptr, h->qnorm.as<float>()))) return rc;
+      qv.qhi = h->qhi.p;
     } else {
       CUDA_TRY(h, h->qf.ensure(size_t(nb) * D * 4));
-      if ((rc = launch_ingest(h, qsrc, nb, normalize, 0, h->qf.as<float>(), nullptr, nullptr, h->qnorm.as<float>()))) return rc;
-    }
-    // ---- score + select
-    int L = 0;
-    const int nqt = (nb + 127) / 128;
-    if (h->n > 0) {
-      int S, tpc;
-      if (algo == RDB_ALGO_TC) {
-        const int ntiles = int((h->n + TC_BN - 1) / TC_BN);
-        S = choose_splits(nqt, ntiles, h->num_sms, 256, 4, &tpc);
-        L = S;
-        CUDA_TRY(h, h->cand_key.ensure(size_t(nb) * L * k * 4));
-        CUDA_TRY(h, h->cand_idx.ensure(size_t(nb) * L * k * 4));
-        cudaEventRecord(h->ev0, s);
-        if ((rc = launch_tc(h, nb, k, nqt, S, tpc, ntiles, 1, h->cand_key.as<float>(), h->cand_idx.as<int>()))) return rc;
-        cudaEventRecord(h->ev1, s);
-      } else {
-        const int ntiles = int((h->n + SIMT_BN - 1) / SIMT_BN);
-        S = choose_splits(nqt, ntiles, 2 * h->num_sms, 256 / SIMT_LISTS, 2, &tpc);
-        L = S * SIMT_LISTS;
-        CUDA_TRY(h, h->cand_key.ensure(size_t(nb) * L * k * 4));
-        CUDA_TRY(h, h->cand_idx.ensure(size_t(nb) * L * k * 4));
-        cudaEventRecord(h->ev0, s);
-        if ((rc = launch_simt(h, nb, k, nqt, S, tpc * SIMT_BN, h->cand_key.as<float>(), h->cand_idx.as<int>()))) return rc;
-        cudaEventRecord(h->ev1, s);
+      if (split) {
+        CUDA_TRY(h, h->qhi.ensure(size_t(nb) * Dp * 2));
+        CUDA_TRY(h, h->qlo.ensure(size_t(nb) * Dp * 2));
       }
-      h->ev_valid = true; h->last_algo = algo; h->last_S = S;
+      if ((rc = launch_ingest(h, qsrc, nb, normalize, 0, h->qf.as<float>(), split ? h->qhi.p : nullptr,
+                              split ? h->qlo.p : nullptr, h->qnorm.as<float>()))) return rc;
+      qv.qf = h->qf.as<float>(); qv.qhi = h->qhi.p; qv.qlo = h->qlo.p;
     }
-    // ---- merge
+    // ---- output views (device scratch when the caller's buffers are on the host)
     float* d_a = out_a + b0 * k;
     int64_t* d_i = out_idx + b0 * k;
     float* d_l = out_lbl ? out_lbl + b0 * k : nullptr;
@@ -363,15 +409,76 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
       if (out_lbl) CUDA_TRY(h, h->o_lbl.ensure(size_t(nb) * k * 4));
       d_a = h->o_dist.as<float>(); d_i = h->o_idx.as<int64_t>(); d_l = out_lbl ? h->o_lbl.as<float>() : nullptr;
     }
-    {
-      const int warps = 4;
-      dim3 grid((nb + warps - 1) / warps), block(32 * warps);
-      merge_lists_kernel<int><<<grid, block, 0, s>>>(
-          h->cand_key.as<float>(), h->cand_idx.as<int>(), nullptr, nb, L, k, k, l2 ? 1 : 0, h->qnorm.as<float>(),
-          h->id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l,
-          shard_mode ? d_a : nullptr);
-      h->launches++;
-      CUDA_TRY(h, cudaGetLastError());
+    int L = 0;
+    if (!split) {
+      // ---- score + select, then merge
+      if (h->n > 0 && (rc = run_scorer(h, algo, 1, qv, k, &L, true))) return rc;
+      if ((rc = run_merge_local(h, nb, L, k, k, qv.qnorm, shard_mode, d_a, d_i, d_l, h->id_offset, labels, nullptr)))
+        return rc;
+    } else {
+      // ---- split-precision tensor-core pass keeping kc > k candidates
+      const int kc = (k <= 10) ? 16 : 32;
+      if ((rc = run_scorer(h, RDB_ALGO_TC, 3, qv, kc, &L, true))) return rc;
+      CUDA_TRY(h, h->rr_key.ensure(size_t(nb) * kc * 4));
+      CUDA_TRY(h, h->rr_idx.ensure(size_t(nb) * kc * 8));
+      CUDA_TRY(h, h->rr_key2.ensure(size_t(nb) * kc * 4));
+      CUDA_TRY(h, h->rr_idx2.ensure(size_t(nb) * kc * 8));
+      CUDA_TRY(h, h->uncert.ensure(size_t(nb + 1) * 4));
+      // approximate top-kc per query (local ids, raw keys)
+      if ((rc = run_merge_local(h, nb, L, kc, kc, qv.qnorm, false, nullptr, h->rr_idx.as<int64_t>(), nullptr, 0,
+                                nullptr, h->rr_key.as<float>()))) return rc;
+      // exact fp32 re-rank + certificate
+      int* ucount = h->uncert.as<int>();
+      int* ulist = ucount + 1;
+      CUDA_TRY(h, cudaMemsetAsync(ucount, 0, 4, s));
+      const int nks = (D + TC_BK - 1) / TC_BK;
+      const float n_mma = float(nks * (TC_BK / 16) * 3);
+      const float eps = 3.02f * 3.814697265625e-06f /*2^-18*/ + 2.0f * (n_mma + 16.f) * 1.1920928955078125e-07f /*2^-23*/;
+      {
+        const int warps = 4;
+        dim3 grid((nb + warps - 1) / warps), block(32 * warps);
+        if (l2) rerank_exact_kernel<true><<<grid, block, 0, s>>>(
+            h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, qv.qf, h->master, h->ynorm, D, eps, qv.qnorm,
+            h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount);
+        else rerank_exact_kernel<false><<<grid, block, 0, s>>>(
+            h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, qv.qf, h->master, h->ynorm, D, eps, qv.qnorm,
+            h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        // exact list (L = 1, already sorted) -> final form
+        merge_lists_kernel<long long><<<grid, block, 0, s>>>(
+            h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), nullptr, nb, 1, kc, k, l2 ? 1 : 0, qv.qnorm,
+            h->id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l,
+            shard_mode ? d_a : nullptr);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+      }
+      // ---- queries whose candidate set could not be certified: exact CUDA-core search
+      int m = 0;
+      CUDA_TRY(h, cudaMemcpyAsync(&m, ucount, 4, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(h, cudaStreamSynchronize(s));
+      h->last_uncertified += m;
+      if (m > 0) {
+        CUDA_TRY(h, h->fb_qf.ensure(size_t(m) * D * 4));
+        CUDA_TRY(h, h->fb_qnorm.ensure(size_t(m) * 4));
+        CUDA_TRY(h, h->fb_a.ensure(size_t(m) * k * 4));
+        CUDA_TRY(h, h->fb_i.ensure(size_t(m) * k * 8));
+        CUDA_TRY(h, h->fb_l.ensure(size_t(m) * k * 4));
+        gather_f32_rows_kernel<<<(m + 7) / 8, 256, 0, s>>>(qv.qf, ulist, m, D, h->fb_qf.as<float>());
+        h->launches++;
+        if ((rc = launch_ingest(h, h->fb_qf.as<float>(), m, 0, 0, nullptr, nullptr, nullptr, h->fb_qnorm.as<float>())))
+          return rc;
+        QueryView fv{h->fb_qf.as<float>(), nullptr, nullptr, h->fb_qnorm.as<float>(), m};
+        int Lf = 0;
+        if ((rc = run_scorer(h, RDB_ALGO_SIMT, 1, fv, k, &Lf, false))) return rc;
+        if ((rc = run_merge_local(h, m, Lf, k, k, fv.qnorm, shard_mode, h->fb_a.as<float>(), h->fb_i.as<int64_t>(),
+                                  h->fb_l.as<float>(), h->id_offset, labels, nullptr))) return rc;
+        scatter_results_kernel<<<(m * k + 255) / 256, 256, 0, s>>>(ulist, m, k, h->fb_a.as<float>(),
+                                                                   h->fb_i.as<long long>(), h->fb_l.as<float>(), d_a,
+                                                                   reinterpret_cast<long long*>(d_i), d_l);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+      }
     }
     if (out_qnorm)
       CUDA_TRY(h, cudaMemcpyAsync(out_qnorm + b0, h->qnorm.p, size_t(nb) * 4,
@@ -422,6 +529,11 @@ int rdb_create(int d, int metric, int store_dtype, int device, unsigned flags, r
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
   if (e != cudaSuccess) { delete h; cudaGetLastError(); return fail(nullptr, RDB_ERR_CUDA, std::string("rdb_create: ") + cudaGetErrorString(e)); }
   h->stream = h->own_stream;
+  if (cudaMalloc(&h->d_ynorm_max, 4) != cudaSuccess || cudaMemset(h->d_ynorm_max, 0, 4) != cudaSuccess) {
+    cudaGetLastError();
+    rdb_destroy(h);
+    return fail(nullptr, RDB_ERR_NOMEM, "rdb_create: device allocation failed");
+  }
   *out = h;
   return RDB_OK;
 }
@@ -432,8 +544,10 @@ int rdb_destroy(rdb_handle* h) {
     DeviceGuard dg(h->device);
     cudaStreamSynchronize(h->stream);
     cudaFree(h->master); cudaFree(h->hi); cudaFree(h->lo); cudaFree(h->ynorm); cudaFree(h->labels);
+    cudaFree(h->d_ynorm_max);
     for (DevBuf* b : {&h->add_stage, &h->q_stage, &h->qf, &h->qhi, &h->qlo, &h->qnorm, &h->cand_key, &h->cand_idx,
-                      &h->o_dist, &h->o_idx, &h->o_lbl, &h->ids_stage, &h->rec_stage})
+                      &h->o_dist, &h->o_idx, &h->o_lbl, &h->ids_stage, &h->rec_stage, &h->rr_key, &h->rr_idx,
+                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l})
       b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -502,6 +616,9 @@ int rdb_add(rdb_handle* h, const float* x, int64_t n, int mem, int normalize) {
     void* hi = reinterpret_cast<char*>(h->hi) + size_t(row0) * Dp * es;
     void* lo = h->has_lo() ? reinterpret_cast<char*>(h->lo) + size_t(row0) * Dp * es : nullptr;
     if ((rc = launch_ingest(h, src, m, normalize, norm_of_hi, master, hi, lo, h->ynorm + row0))) return rc;
+    ynorm_max_kernel<<<unsigned(std::min<int64_t>((m + 255) / 256, 1024)), 256, 0, h->stream>>>(h->ynorm + row0, m,
+                                                                                            h->d_ynorm_max);
+    h->launches++;
     if (mem == RDB_MEM_HOST) CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // staging buffer reuse
   }
   h->n += n;
@@ -642,6 +759,8 @@ int rdb_last_kernel_ms(rdb_handle* h, float* ms, int* algo, int* nsplits) {
   if (nsplits) *nsplits = h->last_S;
   return RDB_OK;
 }
+
+int64_t rdb_last_uncertified(rdb_handle* h) { return h ? h->last_uncertified : 0; }
 
 int rdb_mem_info(rdb_handle* h, size_t* index_bytes, size_t* free_bytes, size_t* total_bytes) {
   if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");

@@ -240,6 +240,11 @@ class FlatIndex:
         self._check(self._lib.rdb_last_kernel_ms(self._h, ctypes.byref(ms), ctypes.byref(algo), ctypes.byref(ns)))
         return float(ms.value), {ALGO_SIMT: "simt", ALGO_TC: "tc"}.get(algo.value, "?"), int(ns.value)
 
+    @property
+    def last_uncertified(self) -> int:
+        """Queries of the last search that fell back from the certified tensor-core path to the exact kernel."""
+        return int(self._lib.rdb_last_uncertified(self._h))
+
     def mem_info(self):
         a, b, c = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
         self._check(self._lib.rdb_mem_info(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))

@@ -102,6 +102,12 @@ CASES = [
     ("refD_bf16_tc",  2048,  5376, 256,  15, "L2", False, "bf16", "tc"),     # reference D = 7*768, Q, k
     ("refD_f32",      1500,  3584, 40,   15, "L2", False, "f32",  "simt"),   # Whisper D = 7*512
     ("l2_bf16_simt",  7000,  192,  70,   17, "L2", False, "bf16", "simt"),
+    # fp32 store on the tensor cores: split-precision (hi/lo bf16, 3 MMAs) + exact fp32 re-rank + certificate
+    ("cos_f32_split", 60000, 768,  300,  10, "IP", True,  "f32",  "tc"),     # C2-like, kc = 16
+    ("l2_f32_split",  30000, 768,  200,  15, "L2", False, "f32",  "tc"),     # reference k = top_k + 10, kc = 32
+    ("l2_f32_split_ragged", 5003, 200, 77, 24, "L2", False, "f32", "tc"),
+    ("ip_f32_split_q1", 20000, 256, 1,   5,  "IP", False, "f32",  "tc"),
+    ("l2_f32_auto",   20000, 768,  1000, 10, "L2", False, "f32",  "auto"),
     ("ip_bf16_simt_k100", 5000, 128, 50, 100, "IP", False, "bf16", "simt"),
 ]
 
@@ -112,7 +118,7 @@ def test_seeded_gaussian_vs_oracle(pkg, oracle, case):
     metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
     xb, xq = _gauss(N, Dm, 1234), _gauss(Q, Dm, 5678)
     xq[::7] = xb[: len(xq[::7])] + 0.05 * _gauss(len(xq[::7]), Dm, 9)      # near-duplicates of DB rows
-    xq[1] = xb[5]                                                            # exact self-match (distance 0)
+    xq[min(1, Q - 1)] = xb[5]                                                # exact self-match (distance 0)
     idx = pkg.FlatIndex(Dm, metric, store)
     for s in range(0, N, 4096):
         idx.add(xb[s:s + 4096], normalize=cos)
@@ -136,6 +142,40 @@ def test_seeded_gaussian_vs_oracle(pkg, oracle, case):
     # the stored rows come back as the oracle's rounded rows
     rec = idx.reconstruct_batch(I[0])
     np.testing.assert_allclose(rec, ref.reconstruct_batch(I[0]), rtol=2e-6 if store == "f32" else 1e-2, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["lattice_l2", "lattice_ip"])
+def test_lattice_bit_exact_f32_split(pkg, name):
+    """fp32 store, tensor-core split path: lattice values have lo == 0, all three MMA terms are exact."""
+    g = _load(os.path.join(GOLDEN, f"search_{name}.npz"))
+    metric = pkg.METRIC_IP if name.endswith("ip") else pkg.METRIC_L2
+    idx = pkg.FlatIndex(g["xb"].shape[1], metric, "f32")
+    idx.add(g["xb"])
+    D, I = idx.search(g["xq"], int(g["k"]), algo="tc")
+    np.testing.assert_array_equal(I, g["idx"])
+    np.testing.assert_array_equal(D, g["dist"])
+
+
+def test_split_path_certificate_fallback(pkg):
+    """A cluster of > kc identical rows cannot be certified (the kc-th candidate ties the k-th): those queries must
+    take the exact fallback and still return the lowest ids; well-separated queries stay on the fast path."""
+    N, Dm, k = 8000, 128, 10
+    xb = _gauss(N, Dm, 1)
+    xb[100:150] = xb[100]                      # 50 identical rows
+    xq = _gauss(64, Dm, 2)
+    xq[3] = xb[100]
+    xq[9] = xb[100] + 1e-4
+    idx = pkg.FlatIndex(Dm, pkg.METRIC_L2, "f32")
+    idx.add(xb)
+    Dt, It = idx.search(xq, k, algo="tc")
+    unc = idx.last_uncertified
+    Ds, Is = idx.search(xq, k, algo="simt")
+    assert 2 <= unc <= 8, unc
+    np.testing.assert_array_equal(It[3], np.arange(100, 110))
+    np.testing.assert_array_equal(It[[3, 9]], Is[[3, 9]])
+    np.testing.assert_array_equal(Dt[[3, 9]], Ds[[3, 9]])
+    np.testing.assert_array_equal(It, Is)
+    np.testing.assert_allclose(Dt, Ds, rtol=1e-5, atol=1e-4)
 
 
 def test_wrapper_behaviour(pkg, tmp_path):

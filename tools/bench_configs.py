@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""Measure the non-headline BASELINE.json configs (C1, C2, C4) and the ingest kernel on one B200.
+Not a bench line -- writes JSON lines for profiles/.  Usage: python tools/bench_configs.py [c1 c2 c4 ingest ...]"""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("radad-retrievalaugmenteddeepfakeaudiodetection_b200")
+orc = importlib.import_module("oracle.flat_oracle")
+import torch  # noqa: E402
+
+PEAK_HBM = 6547.8
+try:
+    PEAK_HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:  # noqa: BLE001
+    pass
+dev = torch.device("cuda", 0)
+
+
+def gen(n, d, seed, normalize=False):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    x = torch.randn((n, d), generator=g, device=dev)
+    return torch.nn.functional.normalize(x, dim=1) if normalize else x
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def timed(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps, out
+
+
+def parity(idx, xq_np, D, I, metric, store, cos, nsub, tol, k):
+    """oracle on the first nsub queries against the STORED rows (read back), tolerance comparator."""
+    n = idx.ntotal
+    xb = idx.reconstruct_batch(torch.arange(n, device=dev)).cpu().numpy()
+    ref = orc.FlatIndexOracle(idx.d, metric, store="f32")
+    ref.add(xb)
+    qn = orc.maybe_normalize(xq_np[:nsub], cos)
+    if store != "f32":
+        qn = orc.round_bf16(qn)
+    Dr, Ir = ref.search(qn, k + 8, direct=False)
+    scale = float((qn * qn).sum(1).max() + (xb * xb).sum(1).max())
+    floor = (2e-6 if store == "f32" else 1e-4) * scale if metric == pkg.METRIC_L2 else 1e-6
+    return orc.compare_topk(D[:nsub], I[:nsub], Dr, Ir, lambda ids: ref.exact_scores(qn, ids), metric, tol, floor)
+
+
+def c1():
+    N, Dm, Q, k = 20000, 768, 1000, 10
+    xb, xq = gen(N, Dm, 1234).cpu().numpy(), gen(Q, Dm, 5678).cpu().numpy()
+    for store in ("f32", "bf16"):
+        idx = pkg.FlatIndex(Dm, pkg.METRIC_IP, store)
+        idx.add(xb, normalize=True)
+        dt, (D, I) = timed(lambda: idx.search(xq, k, normalize=True), 20)
+        st = parity(idx, xq, D, I, pkg.METRIC_IP, store, True, Q, 1e-5 if store == "f32" else 1e-3, k)
+        emit(config="C1 20k x 768, 1k queries, k=10 cosine, host numpy in/out", store=store, ms=dt * 1e3,
+             qps=Q / dt, scorer=idx.last_kernel_ms()[1], kernel_ms=idx.last_kernel_ms()[0], parity=st)
+    torch.set_num_threads(os.cpu_count())
+    xbn = orc.maybe_normalize(xb, True)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        orc.torch_cpu_flat_search(xbn, orc.maybe_normalize(xq, True), k, orc.METRIC_IP)
+    dt = (time.perf_counter() - t0) / 5
+    emit(config="C1 CPU port (torch-CPU sgemm+topk)", cores=os.cpu_count(), ms=dt * 1e3, qps=Q / dt)
+
+
+def c2():
+    N, Dm, Q, k = 1_000_000, 768, 10000, 10
+    xq = gen(Q, Dm, 5678)
+    for metric, cos, name in ((pkg.METRIC_L2, False, "L2"), (pkg.METRIC_IP, True, "cosine")):
+        idx = pkg.FlatIndex(Dm, metric, "f32")
+        idx.reserve(N)
+        for c in range(4):
+            idx.add(gen(N // 4, Dm, 1234 + c), normalize=cos)
+        dt, (D, I) = timed(lambda: idx.search(xq, k, normalize=cos), 3, warm=1)
+        kms, scorer, ns = idx.last_kernel_ms()
+        st = parity(idx, xq.cpu().numpy(), D.cpu().numpy(), I.cpu().numpy(), metric, "f32", cos, 128, 1e-5, k)
+        emit(config=f"C2 1M x 768 fp32, 10k queries, k=10 {name}, device in/out", ms=dt * 1e3, qps=Q / dt,
+             scorer=scorer, kernel_ms=kms, tflops=2.0 * Q * N * Dm / (kms * 1e-3) / 1e12, parity_128q=st,
+             uncertified_queries=idx.last_uncertified)
+        dt, _ = timed(lambda: idx.search(xq, k, normalize=cos, algo="simt"), 2, warm=1)
+        emit(config=f"C2 (exact CUDA-core kernel only) {name}", ms=dt * 1e3, qps=Q / dt,
+             tflops=2.0 * Q * N * Dm / dt / 1e12)
+        idx.close()
+
+
+def c4():
+    N, Dm, k = 1_000_000, 768, 15
+    for store in ("bf16", "f32"):
+        idx = pkg.FlatIndex(Dm, pkg.METRIC_L2, store)
+        idx.reserve(N)
+        for c in range(4):
+            idx.add(gen(N // 4, Dm, 1234 + c))
+        xq = gen(2000, Dm, 5678).cpu().numpy()
+        for nq in (1, 2):
+            lat, kms = [], []
+            for i in range(0, 600, nq):
+                t0 = time.perf_counter()
+                idx.search(xq[i:i + nq], k)                      # host in, host out: H2D + kernels + D2H + sync
+                lat.append((time.perf_counter() - t0) * 1e3)
+                kms.append(idx.last_kernel_ms()[0])
+            lat, kms = np.sort(lat[20:]), np.sort(kms[20:])
+            bytes_db = N * Dm * (2 if store == "bf16" else 4)
+            emit(config=f"C4 1M x 768 {store}, batch-{nq} streaming, k=15 L2, host in/out",
+                 p50_ms=float(lat[len(lat) // 2]), p99_ms=float(lat[int(len(lat) * 0.99)]),
+                 kernel_p50_ms=float(kms[len(kms) // 2]), scorer=idx.last_kernel_ms()[1],
+                 hbm_floor_ms=bytes_db / (PEAK_HBM * 1e9) * 1e3,
+                 kernel_hbm_frac=bytes_db / (float(kms[len(kms) // 2]) * 1e-3) / 1e9 / PEAK_HBM)
+        idx.close()
+
+
+def ingest():
+    N, Dm = 2_000_000, 768
+    x = gen(N, Dm, 1)
+    for store, cos in (("bf16", True), ("bf16", False), ("f32", True)):
+        idx = pkg.FlatIndex(Dm, pkg.METRIC_IP, store)
+        idx.reserve(N)
+        idx.add(x[:1000], normalize=cos)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        idx.add(x[1000:], normalize=cos)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        rows = N - 1000
+        rd = rows * Dm * 4 * (2 if cos else 1)                   # normalise reads the row twice (2nd pass hits L2/L1)
+        wr = rows * (Dm * 2 + 4) if store == "bf16" else rows * (Dm * 4 + Dm * 2 * 2 + 4)
+        alg = rows * Dm * 4 + wr                                 # algorithmic: read once + writes
+        emit(config=f"ingest 2M x 768 fp32 -> {store}, normalize={cos}, device tensor in", ms=ms,
+             rows_per_s=rows / (ms * 1e-3), algorithmic_GBs=alg / (ms * 1e-3) / 1e9,
+             frac_of_hbm_peak=alg / (ms * 1e-3) / 1e9 / PEAK_HBM)
+        idx.close()
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c1", "ingest", "c4", "c2"]
+    for w in which:
+        globals()[w]()
