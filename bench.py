@@ -224,7 +224,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- build this rank's row shard on the device (never materialise the database on the host)
-    sidx = pkg.ShardedFlatIndex(DIM, pkg.METRIC_IP, "bf16", device=local_rank)
+    sidx = pkg.ShardedFlatIndex(DIM, pkg.METRIC_IP, "bf16", device=local_rank,
+                                exchange=os.environ.get("RDB_EXCHANGE", "peer"))
     start, end = sidx.set_shard(N_DB)
     lab_gen = torch.Generator(device=dev)
     for c in range(start // GEN_CHUNK, -(-end // GEN_CHUNK)):
@@ -313,6 +314,8 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "parallelism": f"row-shards x{world}", "scorer": algo,
+                       "exchange": ("none" if world == 1 else sidx.exchange + ("-memory fused gather+merge kernel"
+                                                                              if sidx.exchange == "peer" else " all-gather + merge")),
                        "db_chunks_per_query_tile": nsplits,
                        "l2_policy": "inputs larger than L2 (database shard >> 126 MB), no flush needed"},
             "e2e": {"value": NQ / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e,

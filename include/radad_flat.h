@@ -95,6 +95,20 @@ int rdb_merge_shards(rdb_handle* h, const float* key, const int64_t* idx, const 
                      int nlists, int k, const float* qnorm, float* out_dist, int64_t* out_idx,
                      float* out_labels);
 
+/* Fused exchange + merge over NVLink peer memory (the B200-native form of the step above): every rank leaves its
+ * candidates in a buffer obtained from rdb_ipc_alloc, peers map it with rdb_ipc_open (CUDA IPC handle, 64 bytes,
+ * exchanged once), and ONE kernel merges list g by loading it straight from GPU g's memory -- no all-gather.
+ * key_ptrs/idx_ptrs/lbl_ptrs: host arrays of `nlists` device pointers to [nq][k] planes (float32/int64/float32);
+ * the caller orders the launch after all ranks finished writing (a stream-ordered barrier).  No reference
+ * counterpart. */
+int rdb_ipc_alloc(rdb_handle* h, size_t bytes, void** dev_ptr, unsigned char* handle_out /*[64]*/);
+int rdb_ipc_open(rdb_handle* h, const unsigned char* handle /*[64]*/, void** dev_ptr);
+int rdb_ipc_close(rdb_handle* h, void* dev_ptr);
+int rdb_ipc_free(rdb_handle* h, void* dev_ptr);
+int rdb_merge_shards_peer(rdb_handle* h, const void* const* key_ptrs, const void* const* idx_ptrs,
+                          const void* const* lbl_ptrs, int nlists, int64_t nq, int k, const float* qnorm,
+                          float* out_dist, int64_t* out_idx, float* out_labels);
+
 /* Replaces index.reconstruct(i) -- pipeline.py:503.  `out` is a HOST float32[d]. */
 int rdb_reconstruct(rdb_handle* h, int64_t id, float* out);
 

@@ -40,6 +40,12 @@ SIGNATURES = {
     "rdb_search_shard": (c_int, [_h, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdb_merge_shards": (c_int, [_h, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
+    "rdb_ipc_alloc": (c_int, [_h, c_size_t, POINTER(c_void_p), c_void_p]),
+    "rdb_ipc_open": (c_int, [_h, c_void_p, POINTER(c_void_p)]),
+    "rdb_ipc_close": (c_int, [_h, c_void_p]),
+    "rdb_ipc_free": (c_int, [_h, c_void_p]),
+    "rdb_merge_shards_peer": (c_int, [_h, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int, c_int64,
+                                      c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdb_reconstruct": (c_int, [_h, c_int64, c_void_p]),
     "rdb_reconstruct_batch": (c_int, [_h, c_void_p, c_int64, c_int, c_void_p]),
     "rdb_set_labels": (c_int, [_h, c_void_p, c_int64]),

@@ -51,6 +51,96 @@ struct TopK {
   }
 };
 
+__device__ __forceinline__ float unordered_f32(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+
+// Selector policy used by the tensor-core epilogue for k <= KT (register-resident list).
+template <int KT>
+struct SelectSmall {
+  TopK<KT> top;
+  __device__ __forceinline__ void init(int) { top.init(); }
+  __device__ __forceinline__ float threshold() const { return top.worst(); }
+  __device__ __forceinline__ void offer(float v, int id) { if (v > top.worst()) top.insert(v, id); }
+  __device__ __forceinline__ void end_group(int) {}
+  __device__ __forceinline__ void finalize(int kout, float* __restrict__ ck, int* __restrict__ ci) {
+#pragma unroll
+    for (int j = 0; j < KT; ++j)
+      if (j < kout) { ck[j] = top.key[j]; ci[j] = top.idx[j]; }
+  }
+};
+
+// Selector policy for large k (k <= 128): an append-only per-thread reservoir in LOCAL memory (L1/L2-backed)
+// with a stale admission threshold, pruned warp-synchronously to the exact best k whenever any lane runs out
+// of room.  The prune finds the k-th largest key exactly by 4-way bisection over the ordered-uint key space
+// (<= 16 passes) and compacts in arrival order, so among equal keys the earliest arrivals (= lowest ids) stay.
+// Appends are ~k*ln(n/k) per thread per unit and cost one scattered local store each.
+template <int CAP>
+struct SelectReservoir {
+  uint32_t okey[CAP];   // ordered_f32(key)
+  int idx[CAP];
+  int cnt, k;
+  float thr;
+  __device__ __forceinline__ void init(int k_) { cnt = 0; k = k_; thr = -CUDART_INF_F; }
+  __device__ __forceinline__ float threshold() const { return thr; }
+  __device__ __forceinline__ void offer(float v, int id) {
+    if (v > thr) { okey[cnt] = ordered_f32(v); idx[cnt] = id; ++cnt; }
+  }
+  __device__ __forceinline__ uint32_t count_gt(uint32_t t) const {
+    uint32_t c = 0;
+    for (int i = 0; i < cnt; ++i) c += (okey[i] > t) ? 1u : 0u;
+    return c;
+  }
+  // exact prune to k entries (no-op for lanes holding <= k)
+  __device__ __noinline__ void prune() {
+    if (cnt <= k) return;
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (int i = 0; i < cnt; ++i) { const uint32_t o = okey[i]; lo = min(lo, o); hi = max(hi, o); }
+    // smallest t in [lo, hi] with count(okey > t) < k  ==  the k-th largest key
+    while (lo < hi) {
+      const uint32_t span = hi - lo;
+      const uint32_t q1 = lo + (span >> 2), q2 = lo + (span >> 1), q3 = lo + (span >> 2) + (span >> 1);
+      uint32_t c1 = 0, c2 = 0, c3 = 0;
+      for (int i = 0; i < cnt; ++i) {
+        const uint32_t o = okey[i];
+        c1 += (o > q1) ? 1u : 0u; c2 += (o > q2) ? 1u : 0u; c3 += (o > q3) ? 1u : 0u;
+      }
+      const uint32_t kk = uint32_t(k);
+      if (c1 < kk) hi = q1;
+      else if (c2 < kk) { lo = q1 + 1; hi = q2; }
+      else if (c3 < kk) { lo = q2 + 1; hi = q3; }
+      else lo = q3 + 1;
+    }
+    const uint32_t t = lo;
+    int need = k - int(count_gt(t));      // entries equal to t to keep, in arrival order
+    int j = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const uint32_t o = okey[i];
+      bool keep = o > t;
+      if (!keep && o == t && need > 0) { keep = true; --need; }
+      if (keep) { okey[j] = o; idx[j] = idx[i]; ++j; }
+    }
+    cnt = j;
+    thr = unordered_f32(t);
+  }
+  __device__ __forceinline__ void end_group(int room) {
+    if (__any_sync(0xffffffffu, cnt > CAP - room)) prune();
+  }
+  // sorted best-first output (key desc, id asc): prune to k, then k rounds of arg-best extraction
+  __device__ __noinline__ void finalize(int kout, float* __restrict__ ck, int* __restrict__ ci) {
+    prune();
+    for (int r = 0; r < kout; ++r) {
+      uint32_t bo = 0; int bid = 0x7FFFFFFF, bi = -1;
+      for (int i = 0; i < cnt; ++i) {
+        const uint32_t o = okey[i];
+        if (o > bo || (o == bo && o != 0 && idx[i] < bid)) { bo = o; bid = idx[i]; bi = i; }
+      }
+      if (bi >= 0) { ck[r] = unordered_f32(bo); ci[r] = bid; okey[bi] = 0; }
+      else { ck[r] = -CUDART_INF_F; ci[r] = -1; }
+    }
+  }
+};
+
 // ----------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA, tcgen05 (Blackwell 5th-gen tensor cores, TMEM).
 // ----------------------------------------------------------------------------------------------

@@ -208,6 +208,66 @@ __global__ void scatter_results_kernel(const int* __restrict__ list, int m, int 
   if (d_l && s_l) d_l[o] = s_l[t];
 }
 
+// Fused gather + merge over NVLink peer memory (multi-GPU row shards).  Each rank left its [Q][k] candidates
+// (key, global id, label) in a buffer that every peer has mapped (CUDA IPC); this kernel reads list g straight from
+// GPU g's memory with ordinary loads (P2P over NVLink/NVSwitch) while merging -- no all-gather, no staging copy.
+// One warp per query, lane g owns list g (G <= 32).
+struct PeerLists {
+  const float* key[32];
+  const long long* idx[32];
+  const float* lbl[32];
+};
+__global__ void __launch_bounds__(128) merge_peer_lists_kernel(const PeerLists P, int G, int Q, int k, int metric_l2,
+                                                               const float* __restrict__ qnorm,
+                                                               float* __restrict__ out_dist,
+                                                               long long* __restrict__ out_idx,
+                                                               float* __restrict__ out_lbl) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const long long base = (long long)q * k;
+  const float* pk = nullptr; const long long* pi = nullptr; const float* pl = nullptr;
+#pragma unroll
+  for (int g = 0; g < 32; ++g) if (g == lane && g < G) { pk = P.key[g]; pi = P.idx[g]; pl = P.lbl[g]; }
+  int ptr = 0;
+  uint32_t hok = 0; long long hid = 0x7FFFFFFFFFFFFFFFll; float hkey = 0.f;
+  if (pk) {
+    const long long id = pi[base];
+    if (id >= 0) { hkey = pk[base]; hok = ordered_f32(hkey); hid = id; }
+  }
+  for (int r = 0; r < k; ++r) {
+    uint32_t wok = hok; long long wid = hid; int wl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t ook = __shfl_xor_sync(0xffffffffu, wok, o);
+      const long long oid = __shfl_xor_sync(0xffffffffu, wid, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+      if (head_better(ook, oid, wok, wid) || (ook == wok && oid == wid && ol < wl)) { wok = ook; wid = oid; wl = ol; }
+    }
+    const long long o = base + r;
+    if (wok == 0) {
+      if (lane == 0) {
+        out_dist[o] = metric_l2 ? CUDART_INF_F : -CUDART_INF_F;
+        out_idx[o] = -1;
+        if (out_lbl) out_lbl[o] = 0.f;
+      }
+      continue;
+    }
+    if (lane == wl) {
+      out_dist[o] = metric_l2 ? fmaxf(0.f, qnorm[q] - hkey) : hkey;
+      out_idx[o] = hid;
+      if (out_lbl) out_lbl[o] = pl ? pl[base + ptr] : 0.f;
+      ++ptr;
+      hok = 0; hid = 0x7FFFFFFFFFFFFFFFll;
+      if (ptr < k) {
+        const long long id = pi[base + ptr];
+        if (id >= 0) { hkey = pk[base + ptr]; hok = ordered_f32(hkey); hid = id; }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // sum of neighbour labels per query over the first kvote results (the "kNN label vote" evidence)
 __global__ void label_vote_kernel(const float* __restrict__ lbl, int Q, int k, int kvote, float* __restrict__ vote) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;

@@ -182,7 +182,8 @@ int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int n
 // ---------------------------------------------------------------------------------------------- scheduling
 // Split the database into S chunks so that nqt * S work units fill the machine in whole waves.
 // cost model: waves * (tiles_per_chunk + per-unit overhead);  `slots` = concurrently resident CTAs.
-int choose_splits(int64_t nqt, int64_t ntiles, int slots, int max_lists, int min_tiles, int* tiles_per_chunk) {
+int choose_splits(int64_t nqt, int64_t ntiles, int slots, int max_lists, int min_tiles, int* tiles_per_chunk,
+                  double unit_overhead_tiles = 2.0) {
   int64_t maxS = std::min<int64_t>(std::min<int64_t>(max_lists, ntiles), std::max<int64_t>(1, ntiles / min_tiles));
   double best = 1e300;
   int bestS = 1;
@@ -193,7 +194,7 @@ int choose_splits(int64_t nqt, int64_t ntiles, int slots, int max_lists, int min
     if (S2 != S) continue;
     const int64_t units = nqt * S2;
     const int64_t waves = (units + slots - 1) / slots;
-    const double cost = double(waves) * (double(tpc) + 2.0);
+    const double cost = double(waves) * (double(tpc) + unit_overhead_tiles);
     if (cost < best * 0.999) { best = cost; bestS = int(S2); best_tpc = tpc; }
   }
   *tiles_per_chunk = int(best_tpc);
@@ -239,6 +240,8 @@ int launch_simt(rdb_handle* h, const float* qf, const void* qhi, int nq, int k, 
 #undef SIMT_CASE
 }
 
+constexpr int kReservoirCap = 320;   // large-k epilogue: room for 128 kept + >= 160 appended between prunes
+
 int encode_2d(rdb_handle* h, CUtensorMap* m, const void* base, int64_t rows, int D, int Dp, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return fail(h, RDB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -275,14 +278,15 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
   p.idesc = make_idesc_f16(TC_BM, TC_BN, h->f16() ? 0 : 1);
   const int grid = std::min(p.num_units, h->num_sms);
   const bool l2 = h->metric == RDB_METRIC_L2;
-#define TC_LAUNCH(KT, L2V)                                                                                       \
+#define TC_LAUNCH(SEL, L2V)                                                                                      \
   do {                                                                                                           \
-    auto kern = score_select_tc_kernel<KT, L2V>;                                                                 \
+    auto kern = score_select_tc_kernel<SEL, L2V>;                                                                \
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes())); \
     kern<<<dim3(grid), dim3(TC_THREADS), tc_smem_bytes(), h->stream>>>(p);                                       \
   } while (0)
-  if (k <= 16) { if (l2) TC_LAUNCH(16, true); else TC_LAUNCH(16, false); }
-  else         { if (l2) TC_LAUNCH(32, true); else TC_LAUNCH(32, false); }
+  if (k <= 16)      { if (l2) TC_LAUNCH(SelectSmall<16>, true); else TC_LAUNCH(SelectSmall<16>, false); }
+  else if (k <= 32) { if (l2) TC_LAUNCH(SelectSmall<32>, true); else TC_LAUNCH(SelectSmall<32>, false); }
+  else              { if (l2) TC_LAUNCH(SelectReservoir<kReservoirCap>, true); else TC_LAUNCH(SelectReservoir<kReservoirCap>, false); }
 #undef TC_LAUNCH
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
@@ -291,7 +295,7 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
 
 constexpr int64_t kQueryBatch = 65536;
 constexpr int kMaxK = 128;
-constexpr int kMaxKTc = 32;        // register-resident list of the tensor-core epilogue
+constexpr int kMaxKTc = 128;       // k <= 32: register-resident list; 32 < k <= 128: local-memory reservoir
 constexpr int kMaxKSplit = 24;     // split-precision path keeps kc = 16 / 32 candidates: slack >= 6
 constexpr int64_t kMinRowsTc = 1024;
 
@@ -310,7 +314,8 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
   cudaStream_t s = h->stream;
   if (algo == RDB_ALGO_TC) {
     const int ntiles = int((h->n + TC_BN - 1) / TC_BN);
-    S = choose_splits(nqt, ntiles, h->num_sms, 256, 4, &tpc);
+    // large k: per-unit selection overhead (reservoir warm-up, final sort) is worth ~64 tiles -> fewer, longer units
+    S = choose_splits(nqt, ntiles, h->num_sms, 256, kc > 32 ? 64 : 4, &tpc, kc > 32 ? 64.0 : 2.0);
     CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * kc * 4));
     CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * kc * 4));
     if (timed) cudaEventRecord(h->ev0, s);
@@ -367,7 +372,7 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   if (algo == RDB_ALGO_AUTO) algo = (tc_ok && h->n >= kMinRowsTc) ? RDB_ALGO_TC : RDB_ALGO_SIMT;
   if (algo == RDB_ALGO_TC && !tc_ok)
     return fail(h, RDB_ERR_UNSUPPORTED,
-                "search: tensor-core scorer needs ntotal >= 256 and k <= 32 (16-bit store) / k <= 24 (fp32 store)");
+                "search: tensor-core scorer needs ntotal >= 256 and k <= 128 (16-bit store) / k <= 24 (fp32 store)");
   const bool split = (algo == RDB_ALGO_TC) && !sixteen;
   const float* labels = (h->labels && h->nlabels == h->n) ? h->labels : nullptr;
   cudaStream_t s = h->stream;
@@ -655,6 +660,73 @@ int rdb_merge_shards(rdb_handle* h, const float* key, const int64_t* idx, const 
   merge_lists_kernel<long long><<<grid, block, 0, h->stream>>>(
       key, reinterpret_cast<const long long*>(idx), labels, int(nq), nlists, k, k, h->metric == RDB_METRIC_L2 ? 1 : 0,
       qnorm, 0, nullptr, out_dist, reinterpret_cast<long long*>(out_idx), out_labels, nullptr);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return RDB_OK;
+}
+
+int rdb_ipc_alloc(rdb_handle* h, size_t bytes, void** dev_ptr, unsigned char* handle_out) {
+  if (!h || !dev_ptr || !handle_out || bytes == 0) return fail(h, RDB_ERR_INVALID, "ipc_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  void* p = nullptr;
+  CUDA_TRY(h, cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t mh;
+  cudaError_t e = cudaIpcGetMemHandle(&mh, p);
+  if (e != cudaSuccess) { cudaFree(p); cudaGetLastError(); return fail(h, RDB_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+  memcpy(handle_out, &mh, 64);
+  *dev_ptr = p;
+  return RDB_OK;
+}
+
+int rdb_ipc_open(rdb_handle* h, const unsigned char* handle, void** dev_ptr) {
+  if (!h || !handle || !dev_ptr) return fail(h, RDB_ERR_INVALID, "ipc_open: bad arguments");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, handle, 64);
+  CUDA_TRY(h, cudaIpcOpenMemHandle(dev_ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+  return RDB_OK;
+}
+
+int rdb_ipc_close(rdb_handle* h, void* dev_ptr) {
+  if (!h || !dev_ptr) return fail(h, RDB_ERR_INVALID, "ipc_close: bad arguments");
+  DeviceGuard dg(h->device);
+  CUDA_TRY(h, cudaIpcCloseMemHandle(dev_ptr));
+  return RDB_OK;
+}
+
+int rdb_ipc_free(rdb_handle* h, void* dev_ptr) {
+  if (!h || !dev_ptr) return fail(h, RDB_ERR_INVALID, "ipc_free: bad arguments");
+  DeviceGuard dg(h->device);
+  cudaStreamSynchronize(h->stream);
+  CUDA_TRY(h, cudaFree(dev_ptr));
+  return RDB_OK;
+}
+
+int rdb_merge_shards_peer(rdb_handle* h, const void* const* key_ptrs, const void* const* idx_ptrs,
+                          const void* const* lbl_ptrs, int nlists, int64_t nq, int k, const float* qnorm,
+                          float* out_dist, int64_t* out_idx, float* out_labels) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  if (nq < 0 || k < 1 || nlists < 1 || nlists > 32 || !key_ptrs || !idx_ptrs || !out_dist || !out_idx)
+    return fail(h, RDB_ERR_INVALID, "merge_shards_peer: bad arguments (1 <= nlists <= 32)");
+  if (h->metric == RDB_METRIC_L2 && !qnorm) return fail(h, RDB_ERR_INVALID, "merge_shards_peer: L2 needs qnorm");
+  if (nq == 0) return RDB_OK;
+  PeerLists P;
+  memset(&P, 0, sizeof(P));
+  for (int g = 0; g < nlists; ++g) {
+    P.key[g] = reinterpret_cast<const float*>(key_ptrs[g]);
+    P.idx[g] = reinterpret_cast<const long long*>(idx_ptrs[g]);
+    P.lbl[g] = lbl_ptrs ? reinterpret_cast<const float*>(lbl_ptrs[g]) : nullptr;
+  }
+  const int warps = 4;
+  dim3 grid(unsigned((nq + warps - 1) / warps)), block(32 * warps);
+  merge_peer_lists_kernel<<<grid, block, 0, h->stream>>>(P, nlists, int(nq), k, h->metric == RDB_METRIC_L2 ? 1 : 0,
+                                                         qnorm, out_dist, reinterpret_cast<long long*>(out_idx),
+                                                         out_labels);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return RDB_OK;

@@ -70,8 +70,8 @@ __device__ __forceinline__ void tc_load_yn(float4 (&y)[8], const float* __restri
   for (int g = 0; g < 8; ++g) y[g] = __ldg(yn4 + g);
 }
 
-template <int KT, bool L2>
-__device__ __forceinline__ void tc_process32(uint32_t (&r)[32], TopK<KT>& top, const float4 (&y)[8],
+template <class Sel, bool L2>
+__device__ __forceinline__ void tc_process32(uint32_t (&r)[32], Sel& sel, const float4 (&y)[8],
                                              int col0 /*global row id of column 0 of this group*/, int nvalid) {
   float v[32];
 #pragma unroll
@@ -85,7 +85,7 @@ __device__ __forceinline__ void tc_process32(uint32_t (&r)[32], TopK<KT>& top, c
       v[4 * g + 3] = fmaf(2.0f, v[4 * g + 3], -y[g].w);
     }
   }
-  const float worst = top.worst();
+  const float worst = sel.threshold();
   uint32_t mask = 0;
 #pragma unroll
   for (int j = 0; j < 32; ++j) mask |= (v[j] > worst) ? (1u << j) : 0u;
@@ -93,13 +93,13 @@ __device__ __forceinline__ void tc_process32(uint32_t (&r)[32], TopK<KT>& top, c
   while (mask) {
     const int j = __ffs(mask) - 1;
     mask &= mask - 1;
-    const float x = sel32(v, j);
-    if (x > top.worst()) top.insert(x, col0 + j);
+    sel.offer(sel32(v, j), col0 + j);
   }
   __syncwarp();
+  sel.end_group(32);
 }
 
-template <int KT, bool L2>
+template <class Sel, bool L2>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       const int qtile = unit % p.nqt, chunk = unit / p.nqt;
       const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
-      TopK<KT> top;
-      top.init();
+      Sel sel;
+      sel.init(p.kout);
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
           if (L2) tc_load_yn(yb, p.ynorm, n0 + (c + 1) * 32);
           tmem_ld_wait_regs(ra);
           tmem_ld_32x32(taddr + (c + 1) * 32, rb);
-          tc_process32<KT, L2>(ra, top, ya, n0 + c * 32, nvalid - c * 32);
+          tc_process32<Sel, L2>(ra, sel, ya, n0 + c * 32, nvalid - c * 32);
           if (L2 && c + 2 < TC_BN / 32) tc_load_yn(ya, p.ynorm, n0 + (c + 2) * 32);
           tmem_ld_wait_regs(rb);
           if (c + 2 < TC_BN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
-          tc_process32<KT, L2>(rb, top, yb, n0 + (c + 1) * 32, nvalid - (c + 1) * 32);
+          tc_process32<Sel, L2>(rb, sel, yb, n0 + (c + 1) * 32, nvalid - (c + 1) * 32);
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -231,9 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
       const long long q = (long long)qtile * TC_BM + row;
       if (q < p.nq) {
         const long long base = (q * p.S + chunk) * (long long)p.kout;
-#pragma unroll
-        for (int j = 0; j < KT; ++j)
-          if (j < p.kout) { p.cand_key[base + j] = top.key[j]; p.cand_idx[base + j] = top.idx[j]; }
+        sel.finalize(p.kout, p.cand_key + base, p.cand_idx + base);
       }
     }
   }

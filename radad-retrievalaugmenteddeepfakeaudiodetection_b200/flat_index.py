@@ -214,6 +214,50 @@ class FlatIndex:
                                                ctypes.c_void_p(L.data_ptr())))
         return D, I, L
 
+    # ---- peer-memory exchange (CUDA IPC): buffers every rank of the node can map
+    def ipc_alloc(self, nbytes: int):
+        """Device buffer + its 64-byte CUDA IPC handle (bytes)."""
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        self._check(self._lib.rdb_ipc_alloc(self._h, int(nbytes), ctypes.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def ipc_open(self, handle: bytes) -> int:
+        ptr = ctypes.c_void_p()
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self._lib.rdb_ipc_open(self._h, buf, ctypes.byref(ptr)))
+        return int(ptr.value)
+
+    def ipc_close(self, ptr: int) -> None:
+        self._check(self._lib.rdb_ipc_close(self._h, ctypes.c_void_p(ptr)))
+
+    def ipc_free(self, ptr: int) -> None:
+        self._check(self._lib.rdb_ipc_free(self._h, ctypes.c_void_p(ptr)))
+
+    def search_shard_into(self, q, k: int, normalize: bool, key_ptr: int, gid_ptr: int, lab_ptr: int, qnorm):
+        """search_shard writing the candidates to raw device pointers (the IPC-exported buffer)."""
+        import torch
+        q = q.detach().to(torch.float32).contiguous()
+        self._use_torch_stream(torch)
+        self._check(self._lib.rdb_search_shard(self._h, ctypes.c_void_p(q.data_ptr()), q.shape[0], int(k),
+                                               int(bool(normalize)), ctypes.c_void_p(key_ptr),
+                                               ctypes.c_void_p(gid_ptr), ctypes.c_void_p(lab_ptr),
+                                               ctypes.c_void_p(qnorm.data_ptr())))
+
+    def merge_shards_peer(self, key_ptrs, gid_ptrs, lab_ptrs, nq: int, k: int, qnorm):
+        """ONE kernel: gather list g from GPU g's memory over NVLink (P2P loads) while merging."""
+        import torch
+        G = len(key_ptrs)
+        arr = lambda v: (ctypes.c_void_p * G)(*[ctypes.c_void_p(int(x)) for x in v])   # noqa: E731
+        D = torch.empty((nq, k), dtype=torch.float32, device=qnorm.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=qnorm.device)
+        L = torch.empty((nq, k), dtype=torch.float32, device=qnorm.device)
+        self._use_torch_stream(torch)
+        self._check(self._lib.rdb_merge_shards_peer(self._h, arr(key_ptrs), arr(gid_ptrs), arr(lab_ptrs), G, nq, k,
+                                                    ctypes.c_void_p(qnorm.data_ptr()), ctypes.c_void_p(D.data_ptr()),
+                                                    ctypes.c_void_p(I.data_ptr()), ctypes.c_void_p(L.data_ptr())))
+        return D, I, L
+
     def label_vote(self, labels_nq_k, kvote: int):
         if _is_cuda_tensor(labels_nq_k):
             import torch

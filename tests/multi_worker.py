@@ -24,13 +24,16 @@ def main():
     xq = np.random.default_rng(5678).standard_normal((Q, Dm)).astype(np.float32)
     xq[0] = xb[3]
     labels = (np.arange(N) % 2).astype(np.float32)
-    for metric, cos, store in ((pkg.METRIC_L2, False, "bf16"), (pkg.METRIC_IP, True, "bf16"), (pkg.METRIC_L2, False, "f32")):
-        sh = pkg.ShardedFlatIndex(Dm, metric, store, device=local)
+    for metric, cos, store, exch in ((pkg.METRIC_L2, False, "bf16", "peer"), (pkg.METRIC_IP, True, "bf16", "peer"),
+                                     (pkg.METRIC_L2, False, "f32", "peer"), (pkg.METRIC_L2, False, "bf16", "nccl"),
+                                     (pkg.METRIC_IP, True, "bf16", "nccl")):
+        sh = pkg.ShardedFlatIndex(Dm, metric, store, device=local, exchange=exch)
         s, e = sh.set_shard(N)
         sh.add_local(xb[s:e], normalize=cos)
         sh.set_labels_local(labels[s:e])
         q = torch.from_numpy(xq).to(dev)
-        D, I, L = sh.search(q, k, normalize=cos)
+        for rep in range(3):                                # repeated calls alternate the two peer half-buffers
+            D, I, L = sh.search(q, k, normalize=cos)
         torch.cuda.synchronize()
         full = pkg.FlatIndex(Dm, metric, store, device=local)
         full.add(xb, normalize=cos)

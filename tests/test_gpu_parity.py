@@ -109,6 +109,11 @@ CASES = [
     ("ip_f32_split_q1", 20000, 256, 1,   5,  "IP", False, "f32",  "tc"),
     ("l2_f32_auto",   20000, 768,  1000, 10, "L2", False, "f32",  "auto"),
     ("ip_bf16_simt_k100", 5000, 128, 50, 100, "IP", False, "bf16", "simt"),
+    # large k on the tensor cores: local-memory reservoir + exact bisection prune (C5: k = 100, D = 256)
+    ("ip_bf16_tc_k100", 60000, 256, 300, 100, "IP", True,  "bf16", "tc"),
+    ("l2_bf16_tc_k64",  20000, 128, 130, 64,  "L2", False, "bf16", "tc"),
+    ("l2_bf16_tc_k128", 9000,  96,  40,  128, "L2", False, "bf16", "tc"),
+    ("ip_f16_tc_k33",   5000,  64,  33,  33,  "IP", False, "f16",  "tc"),
 ]
 
 
@@ -142,6 +147,27 @@ def test_seeded_gaussian_vs_oracle(pkg, oracle, case):
     # the stored rows come back as the oracle's rounded rows
     rec = idx.reconstruct_batch(I[0])
     np.testing.assert_allclose(rec, ref.reconstruct_batch(I[0]), rtol=2e-6 if store == "f32" else 1e-2, atol=1e-7)
+
+
+@pytest.mark.parametrize("metric_s", ["L2", "IP"])
+@pytest.mark.parametrize("k", [40, 100])
+def test_lattice_bit_exact_large_k(pkg, oracle, metric_s, k):
+    """Large-k tensor-core path on lattice data: heavy ties (few distinct scores) stress the reservoir prune's
+    'earliest arrival wins' rule; result must equal the oracle bit-for-bit (ids and distances)."""
+    rng = np.random.default_rng(7)
+    xb = rng.integers(-2, 3, size=(6000, 64)).astype(np.float32)
+    xb[3000:3200] = xb[10]                                    # 200 identical rows: ties far beyond k
+    xq = rng.integers(-2, 3, size=(70, 64)).astype(np.float32)
+    xq[0] = xb[10]
+    metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
+    idx = pkg.FlatIndex(64, metric, "bf16")
+    idx.add(xb)
+    D, I = idx.search(xq, k, algo="tc")
+    ref = oracle.FlatIndexOracle(64, metric)
+    ref.add(xb)
+    Dr, Ir = ref.search(xq, k, direct=False)
+    np.testing.assert_array_equal(I, Ir)
+    np.testing.assert_array_equal(D, Dr)
 
 
 @pytest.mark.parametrize("name", ["lattice_l2", "lattice_ip"])
