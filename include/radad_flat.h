@@ -35,7 +35,7 @@ typedef struct rdb_handle rdb_handle;
 enum { RDB_METRIC_L2 = 0, RDB_METRIC_IP = 1 };                       /* faiss.IndexFlatL2 / IndexFlatIP   */
 enum { RDB_STORE_F32 = 0, RDB_STORE_BF16 = 1, RDB_STORE_F16 = 2 };   /* GpuIndexFlatConfig.useFloat16 -> 2 */
 enum { RDB_MEM_HOST = 0, RDB_MEM_DEVICE = 1 };
-enum { RDB_ALGO_AUTO = 0, RDB_ALGO_SIMT = 1, RDB_ALGO_TC = 2 };      /* scorer selection (tests / bench)   */
+enum { RDB_ALGO_AUTO = 0, RDB_ALGO_SIMT = 1, RDB_ALGO_TC = 2, RDB_ALGO_STREAM = 3 }; /* scorer (tests / bench) */
 enum {
   RDB_OK = 0, RDB_ERR_INVALID = 1, RDB_ERR_CUDA = 2, RDB_ERR_NOMEM = 3, RDB_ERR_IO = 4, RDB_ERR_UNSUPPORTED = 5
 };
@@ -78,7 +78,8 @@ int rdb_add(rdb_handle* h, const float* x, int64_t n, int mem, int normalize);
 int rdb_search(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int normalize, float* out_dist,
                int64_t* out_idx, float* out_labels);
 
-/* Same, with an explicit scorer (RDB_ALGO_*): SIMT = exact fp32 CUDA-core kernel, TC = tcgen05 kernel. */
+/* Same, with an explicit scorer (RDB_ALGO_*): SIMT = exact fp32 CUDA-core kernel, TC = tcgen05 kernel (16-bit
+ * stores; fp32 stores: split-precision + exact re-rank + certificate), STREAM = small-batch HBM-streaming kernel. */
 int rdb_search_algo(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int normalize, int algo,
                     float* out_dist, int64_t* out_idx, float* out_labels);
 

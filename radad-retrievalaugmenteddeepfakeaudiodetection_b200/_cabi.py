@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libradad_flat.so")
 METRIC_L2, METRIC_IP = 0, 1
 STORE_F32, STORE_BF16, STORE_F16 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
-ALGO_AUTO, ALGO_SIMT, ALGO_TC = 0, 1, 2
+ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_STREAM = 0, 1, 2, 3
 FLAG_KEEP_F32_MASTER = 1
 ABI_VERSION = 1
 

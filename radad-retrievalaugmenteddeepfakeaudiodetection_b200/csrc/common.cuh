@@ -58,6 +58,7 @@ __device__ __forceinline__ float unordered_f32(uint32_t o) {
 // Selector policy used by the tensor-core epilogue for k <= KT (register-resident list).
 template <int KT>
 struct SelectSmall {
+  static constexpr bool kDirect = false;
   TopK<KT> top;
   __device__ __forceinline__ void init(int) { top.init(); }
   __device__ __forceinline__ float threshold() const { return top.worst(); }
@@ -77,7 +78,9 @@ struct SelectSmall {
 // Appends are ~k*ln(n/k) per thread per unit and cost one scattered local store each.
 template <int CAP>
 struct SelectReservoir {
-  uint32_t okey[CAP];   // ordered_f32(key)
+  static constexpr bool kDirect = true;
+  static constexpr int B = 16;   // entries loaded per batch: independent local-memory loads in flight per thread
+  uint32_t okey[CAP];   // ordered_f32(key); 0 = never a valid key of a finite score
   int idx[CAP];
   int cnt, k;
   float thr;
@@ -86,57 +89,87 @@ struct SelectReservoir {
   __device__ __forceinline__ void offer(float v, int id) {
     if (v > thr) { okey[cnt] = ordered_f32(v); idx[cnt] = id; ++cnt; }
   }
-  __device__ __forceinline__ uint32_t count_gt(uint32_t t) const {
-    uint32_t c = 0;
-    for (int i = 0; i < cnt; ++i) c += (okey[i] > t) ? 1u : 0u;
-    return c;
+  __device__ __forceinline__ void load_keys(int i, uint32_t (&o)[B]) const {
+#pragma unroll
+    for (int j = 0; j < B; ++j) o[j] = (i + j < cnt) ? okey[i + j] : 0u;   // 0 is below every real key
   }
-  // exact prune to k entries (no-op for lanes holding <= k)
+  // exact prune to the best k entries (no-op for lanes holding <= k); all loops are warp-convergent
   __device__ __noinline__ void prune() {
     if (cnt <= k) return;
     uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-    for (int i = 0; i < cnt; ++i) { const uint32_t o = okey[i]; lo = min(lo, o); hi = max(hi, o); }
-    // smallest t in [lo, hi] with count(okey > t) < k  ==  the k-th largest key
+    for (int i = 0; i < cnt; i += B) {
+      uint32_t o[B];
+      load_keys(i, o);
+#pragma unroll
+      for (int j = 0; j < B; ++j) { hi = max(hi, o[j]); lo = min(lo, (i + j < cnt) ? o[j] : 0xFFFFFFFFu); }
+    }
+    // smallest t in [lo, hi] with count(okey > t) < k  ==  the k-th largest key.  8-way bisection: 3 bits per pass.
+    const uint32_t kk = uint32_t(k);
     while (lo < hi) {
       const uint32_t span = hi - lo;
-      const uint32_t q1 = lo + (span >> 2), q2 = lo + (span >> 1), q3 = lo + (span >> 2) + (span >> 1);
-      uint32_t c1 = 0, c2 = 0, c3 = 0;
-      for (int i = 0; i < cnt; ++i) {
-        const uint32_t o = okey[i];
-        c1 += (o > q1) ? 1u : 0u; c2 += (o > q2) ? 1u : 0u; c3 += (o > q3) ? 1u : 0u;
+      uint32_t qv[7], c[7];
+#pragma unroll
+      for (int m = 0; m < 7; ++m) { qv[m] = lo + uint32_t((uint64_t(span) * uint32_t(m + 1)) >> 3); c[m] = 0; }
+      for (int i = 0; i < cnt; i += B) {
+        uint32_t o[B];
+        load_keys(i, o);
+#pragma unroll
+        for (int j = 0; j < B; ++j)
+#pragma unroll
+          for (int m = 0; m < 7; ++m) c[m] += (o[j] > qv[m]) ? 1u : 0u;
       }
-      const uint32_t kk = uint32_t(k);
-      if (c1 < kk) hi = q1;
-      else if (c2 < kk) { lo = q1 + 1; hi = q2; }
-      else if (c3 < kk) { lo = q2 + 1; hi = q3; }
-      else lo = q3 + 1;
+      // c[] is non-increasing in m; pick the first sub-interval whose upper end already has < k above it
+      uint32_t nlo = qv[6] + 1, nhi = hi;
+#pragma unroll
+      for (int m = 6; m >= 0; --m)
+        if (c[m] < kk) { nhi = qv[m]; nlo = (m == 0) ? lo : qv[m - 1] + 1; }
+      lo = nlo; hi = nhi;
     }
     const uint32_t t = lo;
-    int need = k - int(count_gt(t));      // entries equal to t to keep, in arrival order
-    int j = 0;
-    for (int i = 0; i < cnt; ++i) {
-      const uint32_t o = okey[i];
-      bool keep = o > t;
-      if (!keep && o == t && need > 0) { keep = true; --need; }
-      if (keep) { okey[j] = o; idx[j] = idx[i]; ++j; }
+    uint32_t gt = 0;
+    for (int i = 0; i < cnt; i += B) {
+      uint32_t o[B];
+      load_keys(i, o);
+#pragma unroll
+      for (int j = 0; j < B; ++j) gt += (o[j] > t) ? 1u : 0u;
     }
-    cnt = j;
+    int need = k - int(gt);                // entries equal to t to keep, in arrival (= ascending id) order
+    int w = 0;
+    for (int i = 0; i < cnt; i += B) {
+      uint32_t o[B]; int id[B];
+      load_keys(i, o);
+#pragma unroll
+      for (int j = 0; j < B; ++j) id[j] = (i + j < cnt) ? idx[i + j] : 0;
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        bool keep = o[j] > t;
+        if (!keep && o[j] == t && i + j < cnt && need > 0) { keep = true; --need; }
+        if (keep) { okey[w] = o[j]; idx[w] = id[j]; ++w; }     // w <= i + j: never overtakes the reads
+      }
+    }
+    cnt = w;
     thr = unordered_f32(t);
   }
   __device__ __forceinline__ void end_group(int room) {
     if (__any_sync(0xffffffffu, cnt > CAP - room)) prune();
   }
-  // sorted best-first output (key desc, id asc): prune to k, then k rounds of arg-best extraction
+  // sorted best-first output (key desc, id asc): prune to <= k entries, then rank each entry by counting
   __device__ __noinline__ void finalize(int kout, float* __restrict__ ck, int* __restrict__ ci) {
     prune();
-    for (int r = 0; r < kout; ++r) {
-      uint32_t bo = 0; int bid = 0x7FFFFFFF, bi = -1;
-      for (int i = 0; i < cnt; ++i) {
-        const uint32_t o = okey[i];
-        if (o > bo || (o == bo && o != 0 && idx[i] < bid)) { bo = o; bid = idx[i]; bi = i; }
+    for (int r = cnt; r < kout; ++r) { ck[r] = -CUDART_INF_F; ci[r] = -1; }
+    for (int a = 0; a < cnt; ++a) {
+      const uint32_t oa = okey[a];
+      const int ia = idx[a];
+      int rank = 0;
+      for (int i = 0; i < cnt; i += B) {
+        uint32_t o[B]; int id[B];
+        load_keys(i, o);
+#pragma unroll
+        for (int j = 0; j < B; ++j) id[j] = (i + j < cnt) ? idx[i + j] : 0x7FFFFFFF;
+#pragma unroll
+        for (int j = 0; j < B; ++j) rank += (o[j] > oa || (o[j] == oa && id[j] < ia)) ? 1 : 0;
       }
-      if (bi >= 0) { ck[r] = unordered_f32(bo); ci[r] = bid; okey[bi] = 0; }
-      else { ck[r] = -CUDART_INF_F; ci[r] = -1; }
+      if (rank < kout) { ck[rank] = unordered_f32(oa); ci[rank] = ia; }
     }
   }
 };

@@ -24,6 +24,7 @@
 #include "ingest.cuh"
 #include "merge.cuh"
 #include "score_simt.cuh"
+#include "score_stream.cuh"
 #include "score_tc.cuh"
 
 using namespace rdb;
@@ -89,7 +90,7 @@ struct rdb_handle {
   std::mutex mu;
   // scratch
   DevBuf add_stage, q_stage, qf, qhi, qlo, qnorm, cand_key, cand_idx, o_dist, o_idx, o_lbl, ids_stage, rec_stage;
-  DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l;
+  DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l, qs16;
   float* d_ynorm_max = nullptr;   // max |y|^2 over the shard (device scalar; feeds the re-rank certificate)
   int64_t last_uncertified = 0;
   bool has_master() const { return store == RDB_STORE_F32 || (flags & RDB_FLAG_KEEP_F32_MASTER); }
@@ -305,7 +306,39 @@ struct QueryView {
   const void* qlo;    // 16-bit [nq, Dp] (split-precision)
   const float* qnorm; // [nq]
   int nq;
+  const float* qs16 = nullptr;  // fp32 [nq, Dp] copy of the ROUNDED 16-bit queries (stream scorer, 16-bit stores)
 };
+
+template <typename T, bool L2>
+int launch_stream_t(rdb_handle* h, const T* Y, int ld, const float* Qs, int nq, int blocks, int rpb, float* ck, int* ci,
+                    int kout) {
+  const int nqt = nq <= 1 ? 1 : (nq <= 2 ? 2 : 4);
+  const size_t smem = stream_smem_bytes(nqt, ld);
+#define STREAM_LAUNCH(NQ)                                                                                    \
+  do {                                                                                                       \
+    auto kern = score_select_stream_kernel<T, NQ, L2>;                                                       \
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    kern<<<dim3(blocks), dim3(STREAM_THREADS), smem, h->stream>>>(Y, ld, h->ynorm, int(h->n), Qs, nq, rpb, ck, ci, \
+                                                                  kout);                                     \
+  } while (0)
+  if (nqt == 1) STREAM_LAUNCH(1); else if (nqt == 2) STREAM_LAUNCH(2); else STREAM_LAUNCH(4);
+#undef STREAM_LAUNCH
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return RDB_OK;
+}
+
+int launch_stream(rdb_handle* h, const QueryView& qv, int k, int blocks, int rpb, float* ck, int* ci) {
+  const bool l2 = h->metric == RDB_METRIC_L2;
+  if (h->store == RDB_STORE_F32)
+    return l2 ? launch_stream_t<float, true>(h, h->master, h->d, qv.qf, qv.nq, blocks, rpb, ck, ci, k)
+              : launch_stream_t<float, false>(h, h->master, h->d, qv.qf, qv.nq, blocks, rpb, ck, ci, k);
+  if (h->f16())
+    return l2 ? launch_stream_t<__half, true>(h, (const __half*)h->hi, h->dp, qv.qs16, qv.nq, blocks, rpb, ck, ci, k)
+              : launch_stream_t<__half, false>(h, (const __half*)h->hi, h->dp, qv.qs16, qv.nq, blocks, rpb, ck, ci, k);
+  return l2 ? launch_stream_t<__nv_bfloat16, true>(h, (const __nv_bfloat16*)h->hi, h->dp, qv.qs16, qv.nq, blocks, rpb, ck, ci, k)
+            : launch_stream_t<__nv_bfloat16, false>(h, (const __nv_bfloat16*)h->hi, h->dp, qv.qs16, qv.nq, blocks, rpb, ck, ci, k);
+}
 
 // score + select over the local shard into h->cand_key / h->cand_idx; *L_out = lists per query (width kc each)
 int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc, int* L_out, bool timed) {
@@ -315,12 +348,23 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
   if (algo == RDB_ALGO_TC) {
     const int ntiles = int((h->n + TC_BN - 1) / TC_BN);
     // large k: per-unit selection overhead (reservoir warm-up, final sort) is worth ~64 tiles -> fewer, longer units
-    S = choose_splits(nqt, ntiles, h->num_sms, 256, kc > 32 ? 64 : 4, &tpc, kc > 32 ? 64.0 : 2.0);
-    CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * kc * 4));
-    CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * kc * 4));
+    S = choose_splits(nqt, ntiles, h->num_sms, 256 / TC_LISTS, kc > 32 ? 64 : 4, &tpc, kc > 32 ? 64.0 : 2.0);
+    CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * TC_LISTS * kc * 4));
+    CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * TC_LISTS * kc * 4));
     if (timed) cudaEventRecord(h->ev0, s);
     if ((rc = launch_tc(h, qv.qhi, qv.qlo, qv.nq, kc, nqt, S, tpc, ntiles, nterms, h->cand_key.as<float>(),
                         h->cand_idx.as<int>()))) return rc;
+    if (timed) cudaEventRecord(h->ev1, s);
+    *L_out = S * TC_LISTS;
+  } else if (algo == RDB_ALGO_STREAM) {
+    // small batch: one block per SM streams a contiguous slice of the stored rows; one list per block
+    const int blocks = int(std::min<int64_t>(h->num_sms, (h->n + 31) / 32));
+    const int rpb = int(round_up((h->n + blocks - 1) / blocks, 8));
+    S = int((h->n + rpb - 1) / rpb);
+    CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * kc * 4));
+    CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * kc * 4));
+    if (timed) cudaEventRecord(h->ev0, s);
+    if ((rc = launch_stream(h, qv, kc, S, rpb, h->cand_key.as<float>(), h->cand_idx.as<int>()))) return rc;
     if (timed) cudaEventRecord(h->ev1, s);
     *L_out = S;
   } else {
@@ -369,7 +413,12 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   // scorer selection.  16-bit stores: tcgen05 (1 term).  fp32 stores: split-precision tcgen05 (3 terms) + exact
   // fp32 re-rank + certificate, exact CUDA-core kernel for whatever cannot be certified (and for small cases).
   const bool tc_ok = sixteen ? (k <= kMaxKTc && h->n >= TC_BN) : (k <= kMaxKSplit && h->n >= TC_BN);
-  if (algo == RDB_ALGO_AUTO) algo = (tc_ok && h->n >= kMinRowsTc) ? RDB_ALGO_TC : RDB_ALGO_SIMT;
+  // small batches are a pure HBM stream of the stored rows: dedicated streaming scorer (exact fp32 for fp32 stores)
+  const bool stream_ok = nq <= 4 && k <= 32 && h->n >= 1 && (sixteen || D % 4 == 0);
+  if (algo == RDB_ALGO_AUTO)
+    algo = (stream_ok && h->n >= 4096) ? RDB_ALGO_STREAM : ((tc_ok && h->n >= kMinRowsTc) ? RDB_ALGO_TC : RDB_ALGO_SIMT);
+  if (algo == RDB_ALGO_STREAM && !stream_ok)
+    return fail(h, RDB_ERR_UNSUPPORTED, "search: streaming scorer needs nq <= 4, k <= 32 (and D % 4 == 0 for fp32 stores)");
   if (algo == RDB_ALGO_TC && !tc_ok)
     return fail(h, RDB_ERR_UNSUPPORTED,
                 "search: tensor-core scorer needs ntotal >= 256 and k <= 128 (16-bit store) / k <= 24 (fp32 store)");
@@ -394,6 +443,15 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
       CUDA_TRY(h, h->qhi.ensure(size_t(nb) * Dp * 2));
       if ((rc = launch_ingest(h, qsrc, nb, normalize, 1, nullptr, h->qhi.p, nullptr, h->qnorm.as<float>()))) return rc;
       qv.qhi = h->qhi.p;
+      if (algo == RDB_ALGO_STREAM) {
+        // fp32 copy of the rounded queries, pitch Dp (what the streaming scorer keeps in shared memory)
+        CUDA_TRY(h, h->qs16.ensure(size_t(nb) * Dp * 4));
+        if (h->f16()) gather_rows_kernel<__half><<<(nb + 7) / 8, 256, 0, s>>>(nullptr, nb, nb, Dp, Dp, nullptr, (const __half*)h->qhi.p, 0, 0, h->qs16.as<float>());
+        else gather_rows_kernel<__nv_bfloat16><<<(nb + 7) / 8, 256, 0, s>>>(nullptr, nb, nb, Dp, Dp, nullptr, (const __nv_bfloat16*)h->qhi.p, 0, 0, h->qs16.as<float>());
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        qv.qs16 = h->qs16.as<float>();
+      }
     } else {
       CUDA_TRY(h, h->qf.ensure(size_t(nb) * D * 4));
       if (split) {
@@ -552,7 +610,7 @@ int rdb_destroy(rdb_handle* h) {
     cudaFree(h->d_ynorm_max);
     for (DevBuf* b : {&h->add_stage, &h->q_stage, &h->qf, &h->qhi, &h->qlo, &h->qnorm, &h->cand_key, &h->cand_idx,
                       &h->o_dist, &h->o_idx, &h->o_lbl, &h->ids_stage, &h->rec_stage, &h->rr_key, &h->rr_idx,
-                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l})
+                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l, &h->qs16})
       b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

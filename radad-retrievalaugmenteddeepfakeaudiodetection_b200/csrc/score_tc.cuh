@@ -7,7 +7,7 @@
 //                           into a 4-stage shared-memory ring (mbarrier full/empty).
 //   warp 1   MMA issuer   : one elected thread issues tcgen05.mma.kind::f16 (M=128, N=256, K=16), fp32
 //                           accumulators double-buffered in TMEM (2 x 256 of 512 columns).
-//   warps 2-5 epilogue    : tcgen05.ld 32x32b -> each thread owns ONE query row, applies the L2 fix-up
+//   warps 2-9 epilogue    : tcgen05.ld 32x32b -> each thread owns ONE query row x one 128-column half, applies the L2 fix-up
 //                           (key = 2 q.y - |y|^2), threshold-filters against its running k-th best and inserts
 //                           the rare survivors into a register-resident sorted list.  MMA of tile t+1
 //                           overlaps selection of tile t.
@@ -33,7 +33,9 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;        // two per TMEM lane quarter: each takes one half of the 256 columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_LISTS = 2;            // candidate lists per (query, chunk): one per column half
 constexpr int TC_TMEM_COLS = 512;
 constexpr size_t tc_smem_bytes() { return size_t(TC_STAGES) * TC_STAGE_BYTES + 256 + 1024; }
 
@@ -41,8 +43,8 @@ struct TcParams {
   CUtensorMap tmap_q[2];  // [0] = hi, [1] = lo   bf16/f16 [nq, D], box {64, 128}, SWIZZLE_128B
   CUtensorMap tmap_y[2];  // [0] = hi, [1] = lo   bf16/f16 [N,  D], box {64, 256}, SWIZZLE_128B
   const float* ynorm;     // [N] |y|^2 (L2 only)
-  float* cand_key;        // [nq][S][kout]
-  int* cand_idx;          // [nq][S][kout]  local row ids, -1 = empty
+  float* cand_key;        // [nq][S * TC_LISTS][kout]
+  int* cand_idx;          // [nq][S * TC_LISTS][kout]  local row ids, -1 = empty
   int nq, N, D;
   int nqt, S, tiles_per_chunk, ntiles, kout, num_units, nterms;
   uint32_t idesc;
@@ -86,14 +88,41 @@ __device__ __forceinline__ void tc_process32(uint32_t (&r)[32], Sel& sel, const 
     }
   }
   const float worst = sel.threshold();
-  uint32_t mask = 0;
+  // fast path: a depth-5 max tree (31 independent FMNMX) decides whether ANY of the 32 columns can survive;
+  // in steady state almost no group does, so the per-element compare/mask work below is skipped entirely.
+  float m[16];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) mask |= (v[j] > worst) ? (1u << j) : 0u;
-  if (nvalid < 32) mask &= (nvalid <= 0) ? 0u : (0xFFFFFFFFu >> (32 - nvalid));
-  while (mask) {
-    const int j = __ffs(mask) - 1;
-    mask &= mask - 1;
-    sel.offer(sel32(v, j), col0 + j);
+  for (int j = 0; j < 16; ++j) m[j] = fmaxf(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[2 * j], m[2 * j + 1]);
+  float oct[4];                                   // maxima of columns [8o, 8o + 8)
+#pragma unroll
+  for (int o = 0; o < 4; ++o) oct[o] = fmaxf(m[2 * o], m[2 * o + 1]);
+  const float mx = fmaxf(fmaxf(oct[0], oct[1]), fmaxf(oct[2], oct[3]));
+  if (mx > worst || nvalid < 32) {
+    if (Sel::kDirect) {
+      // frequent, cheap hits (large-k reservoir): visit only the octets that hold a survivor and append directly
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        if (oct[o] > worst) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (8 * o + j < nvalid) sel.offer(v[8 * o + j], col0 + 8 * o + j);
+        }
+      }
+    } else {
+      // rare, expensive hits (register-resident sorted list): bit mask + select tree keeps the insert code single
+      uint32_t mk[4] = {0u, 0u, 0u, 0u};          // 4 independent chains instead of one 32-deep OR chain
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mk[j & 3] |= (v[j] > worst) ? (1u << j) : 0u;
+      uint32_t mask = (mk[0] | mk[1]) | (mk[2] | mk[3]);
+      if (nvalid < 32) mask &= (nvalid <= 0) ? 0u : (0xFFFFFFFFu >> (32 - nvalid));
+      while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        sel.offer(sel32(v, j), col0 + j);
+      }
+    }
   }
   __syncwarp();
   sel.end_group(32);
@@ -118,7 +147,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
     tma_prefetch_desc(&p.tmap_q[0]);
     tma_prefetch_desc(&p.tmap_y[0]);
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_ptr);
@@ -189,7 +218,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
     }
   } else {
     // ------------------------------------------------------------------ epilogue: fused top-k
-    const int ew = warp & 3;                 // TMEM lane group this warp may access
+    const int ew = warp & 3;                 // TMEM lane quarter this warp may access (hardware rule: warp_id % 4)
+    const int half = (warp - 2) >> 2;        // which 128-column half of the tile this warp selects from
     const int row = ew * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -201,22 +231,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * TC_BN);
-        const int n0 = t * TC_BN;
-        const int nvalid = p.N - n0;         // >= 256 for full tiles
+        const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * TC_BN + half * (TC_BN / 2));
+        const int n0 = t * TC_BN + half * (TC_BN / 2);
+        const int nvalid = p.N - n0;         // >= 128 for full tiles
         uint32_t ra[32], rb[32];
         float4 ya[8], yb[8];
         if (L2) tc_load_yn(ya, p.ynorm, n0);
         tmem_ld_32x32(taddr, ra);
 #pragma unroll
-        for (int c = 0; c < TC_BN / 32; c += 2) {
+        for (int c = 0; c < TC_BN / 64; c += 2) {
           if (L2) tc_load_yn(yb, p.ynorm, n0 + (c + 1) * 32);
           tmem_ld_wait_regs(ra);
           tmem_ld_32x32(taddr + (c + 1) * 32, rb);
           tc_process32<Sel, L2>(ra, sel, ya, n0 + c * 32, nvalid - c * 32);
-          if (L2 && c + 2 < TC_BN / 32) tc_load_yn(ya, p.ynorm, n0 + (c + 2) * 32);
+          if (L2 && c + 2 < TC_BN / 64) tc_load_yn(ya, p.ynorm, n0 + (c + 2) * 32);
           tmem_ld_wait_regs(rb);
-          if (c + 2 < TC_BN / 32) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+          if (c + 2 < TC_BN / 64) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
           else {
             // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
             tc_fence_before();
@@ -230,7 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
       }
       const long long q = (long long)qtile * TC_BM + row;
       if (q < p.nq) {
-        const long long base = (q * p.S + chunk) * (long long)p.kout;
+        const long long base = ((q * p.S + chunk) * TC_LISTS + half) * (long long)p.kout;
         sel.finalize(p.kout, p.cand_key + base, p.cand_idx + base);
       }
     }

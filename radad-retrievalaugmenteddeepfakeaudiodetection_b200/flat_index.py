@@ -15,14 +15,14 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _cabi
-from ._cabi import (ALGO_AUTO, ALGO_SIMT, ALGO_TC, FLAG_KEEP_F32_MASTER, MEM_DEVICE, MEM_HOST, METRIC_IP,
+from ._cabi import (ALGO_AUTO, ALGO_SIMT, ALGO_STREAM, ALGO_TC, FLAG_KEEP_F32_MASTER, MEM_DEVICE, MEM_HOST, METRIC_IP,
                     METRIC_L2, STORE_BF16, STORE_F16, STORE_F32)
 
 _STORE_BY_NAME = {"f32": STORE_F32, "fp32": STORE_F32, "float32": STORE_F32,
                   "bf16": STORE_BF16, "bfloat16": STORE_BF16,
                   "f16": STORE_F16, "fp16": STORE_F16, "float16": STORE_F16}
 _STORE_NAME = {STORE_F32: "f32", STORE_BF16: "bf16", STORE_F16: "f16"}
-ALGO_BY_NAME = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC}
+ALGO_BY_NAME = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC, "stream": ALGO_STREAM}
 
 
 def _is_cuda_tensor(x) -> bool:
@@ -282,7 +282,7 @@ class FlatIndex:
     def last_kernel_ms(self) -> Tuple[float, str, int]:
         ms, algo, ns = ctypes.c_float(), ctypes.c_int(), ctypes.c_int()
         self._check(self._lib.rdb_last_kernel_ms(self._h, ctypes.byref(ms), ctypes.byref(algo), ctypes.byref(ns)))
-        return float(ms.value), {ALGO_SIMT: "simt", ALGO_TC: "tc"}.get(algo.value, "?"), int(ns.value)
+        return float(ms.value), {ALGO_SIMT: "simt", ALGO_TC: "tc", ALGO_STREAM: "stream"}.get(algo.value, "?"), int(ns.value)
 
     @property
     def last_uncertified(self) -> int:

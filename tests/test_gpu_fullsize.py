@@ -1,0 +1,122 @@
+"""GPU, BASELINE.json full sizes: size-independent properties of the search (the CPU oracle cannot hold these).
+
+C3: 10M x 768 bf16, 65 536 queries, k = 10, cosine.   C2: 1M x 768 fp32, 10 000 queries, k = 10, L2.
+Properties: planted exact copies are found at rank 0 with the self-distance; results are sorted best-first with
+no duplicate ids; every returned distance equals the score recomputed from the stored rows; searching the two
+halves of the database separately and merging gives the identical result (shard invariance); a sampled subset
+of queries matches a torch fp32 brute force over the stored rows (checker only)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _gen(torch, n, d, seed, dev):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    return torch.randn((n, d), generator=g, device=dev)
+
+
+def _bruteforce(torch, idx, qs, k, metric_ip, chunk=500_000):
+    dev = qs.device
+    bv = torch.full((qs.shape[0], k), float("-inf"), device=dev)
+    bi = torch.full((qs.shape[0], k), -1, dtype=torch.int64, device=dev)
+    for s in range(0, idx.ntotal, chunk):
+        e = min(idx.ntotal, s + chunk)
+        rows = idx.reconstruct_batch(torch.arange(s, e, device=dev))
+        sc = qs @ rows.T
+        if not metric_ip:
+            sc = 2 * sc - (rows * rows).sum(1)[None, :]
+        v, i = torch.topk(sc, k, dim=1)
+        cv, ci = torch.cat([bv, v], 1), torch.cat([bi, i + s], 1)
+        bv, sel = torch.topk(cv, k, dim=1)
+        bi = torch.gather(ci, 1, sel)
+    return bv, bi
+
+
+def test_c3_full_size_properties(pkg):
+    import torch
+    dev = torch.device("cuda", 0)
+    N, D, Q, k = 10_000_000, 768, 65536, 10
+    idx = pkg.FlatIndex(D, pkg.METRIC_IP, "bf16")
+    idx.reserve(N)
+    for c in range(40):
+        idx.add(_gen(torch, N // 40, D, 1234 + c, dev), normalize=True)
+    assert idx.ntotal == N
+    q = _gen(torch, Q, D, 5678, dev)
+    planted = torch.randint(0, N, (512,), generator=torch.Generator().manual_seed(3)).to(dev)
+    q[:512] = idx.reconstruct_batch(planted)                    # exact copies of stored rows
+    Dv, Iv = idx.search(q, k, normalize=True)
+    torch.cuda.synchronize()
+    # planted rows come back first with cosine ~ 1 (ties with an identical stored row are impossible here)
+    assert torch.equal(Iv[:512, 0], planted)
+    assert float((Dv[:512, 0] - 1.0).abs().max()) < 4e-3         # bf16-rounded unit vectors: |y|^2 = 1 +- 2^-8
+    # sorted best-first, ids valid and distinct
+    assert bool((Dv[:, :-1] >= Dv[:, 1:]).all())
+    assert int(Iv.min()) >= 0 and int(Iv.max()) < N
+    srt = Iv.sort(dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())
+    # distances are the scores of the returned rows (recomputed from the stored rows, fp32)
+    sub = torch.arange(0, Q, 257, device=dev)
+    qs = torch.nn.functional.normalize(q[sub], dim=1, eps=1e-12).to(torch.bfloat16).float()
+    rows = idx.reconstruct_batch(Iv[sub])                        # [s, k, D]
+    rec = torch.einsum("sd,skd->sk", qs, rows)
+    assert float((rec - Dv[sub]).abs().max()) < 1e-3 * float(Dv[sub].abs().max()) + 1e-5
+    # brute force on the sample: identical neighbour sets (ties within 1e-3 relative tolerated)
+    bv, bi = _bruteforce(torch, idx, qs, k, True)
+    same = (Iv[sub].unsqueeze(2) == bi.unsqueeze(1)).any(2)
+    if not bool(same.all()):
+        miss = ~same
+        assert float(((Dv[sub] - bv[:, -1:]).abs() / bv[:, -1:].abs())[miss].max()) < 1e-3
+    assert float(same.float().mean()) > 0.9995
+    idx.close()
+
+
+def test_c3_shard_invariance_2m(pkg):
+    """top-k(union of shards) == merge of per-shard top-k, bit for bit (2M rows, 3 uneven shards)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    N, D, Q, k = 2_000_000, 768, 4096, 10
+    x = [_gen(torch, 250_000, D, 1234 + c, dev) for c in range(8)]
+    full = pkg.FlatIndex(D, pkg.METRIC_IP, "bf16")
+    for c in x:
+        full.add(c, normalize=True)
+    q = _gen(torch, Q, D, 5678, dev)
+    Df, If = full.search(q, k, normalize=True)
+    bounds = [(0, 3), (3, 4), (4, 8)]
+    keys, gids, labs, shards = [], [], [], []
+    for a, b in bounds:
+        sh = pkg.FlatIndex(D, pkg.METRIC_IP, "bf16")
+        sh.set_id_offset(a * 250_000)
+        for c in x[a:b]:
+            sh.add(c, normalize=True)
+        kk, gg, ll, qn = sh.search_shard(q, k, normalize=True)
+        keys.append(kk), gids.append(gg), labs.append(ll), shards.append(sh)
+    Dm, Im, _ = shards[0].merge_shards(torch.stack(keys, 1), torch.stack(gids, 1), torch.stack(labs, 1), qn)
+    torch.cuda.synchronize()
+    assert torch.equal(Im, If) and torch.equal(Dm, Df)
+
+
+def test_c2_full_size_fp32_certified(pkg):
+    """C2: fp32 store through the certified tensor-core path == the exact CUDA-core kernel on a query sample."""
+    import torch
+    dev = torch.device("cuda", 0)
+    N, D, Q, k = 1_000_000, 768, 10000, 10
+    idx = pkg.FlatIndex(D, pkg.METRIC_L2, "f32")
+    idx.reserve(N)
+    for c in range(4):
+        idx.add(_gen(torch, N // 4, D, 1234 + c, dev))
+    q = _gen(torch, Q, D, 5678, dev)
+    q[:64] = idx.reconstruct_batch(torch.arange(1000, 1064, device=dev))
+    Dt, It = idx.search(q, k)                                     # auto -> split tcgen05 + re-rank + certificate
+    assert idx.last_kernel_ms()[1] == "tc"
+    unc = idx.last_uncertified
+    torch.cuda.synchronize()
+    assert torch.equal(It[:64, 0], torch.arange(1000, 1064, device=dev))
+    assert float(Dt[:64, 0].abs().max()) < 2e-2                   # |q|^2 + |y|^2 - 2 q.y cancels at scale 1536
+    assert bool((Dt[:, :-1] <= Dt[:, 1:]).all())
+    De, Ie = idx.search(q[:512], k, algo="simt")                  # exact fp32 kernel on a sample
+    assert torch.equal(It[:512], Ie)
+    assert float((Dt[:512] - De).abs().max()) <= 1e-5 * float(De.abs().max()) + 2e-3
+    assert unc <= Q // 100
+    idx.close()

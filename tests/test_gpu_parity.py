@@ -109,6 +109,13 @@ CASES = [
     ("ip_f32_split_q1", 20000, 256, 1,   5,  "IP", False, "f32",  "tc"),
     ("l2_f32_auto",   20000, 768,  1000, 10, "L2", False, "f32",  "auto"),
     ("ip_bf16_simt_k100", 5000, 128, 50, 100, "IP", False, "bf16", "simt"),
+    # small-batch HBM-streaming scorer (batch-1 latency path; exact fp32 for fp32 stores)
+    ("stream_l2_f32_q1",   30000, 768, 1, 15, "L2", False, "f32",  "stream"),
+    ("stream_cos_f32_q2",  30000, 768, 2, 15, "IP", True,  "f32",  "stream"),
+    ("stream_l2_bf16_q1",  50001, 768, 1, 15, "L2", False, "bf16", "stream"),
+    ("stream_ip_bf16_q3",  7003,  100, 3, 32, "IP", False, "bf16", "stream"),   # Dp = 104, ragged N
+    ("stream_l2_f16_q4",   9000,  256, 4, 5,  "L2", False, "f16",  "stream"),
+    ("auto_l2_f32_q1",     30000, 768, 1, 15, "L2", False, "f32",  "auto"),
     # large k on the tensor cores: local-memory reservoir + exact bisection prune (C5: k = 100, D = 256)
     ("ip_bf16_tc_k100", 60000, 256, 300, 100, "IP", True,  "bf16", "tc"),
     ("l2_bf16_tc_k64",  20000, 128, 130, 64,  "L2", False, "bf16", "tc"),
@@ -147,6 +154,21 @@ def test_seeded_gaussian_vs_oracle(pkg, oracle, case):
     # the stored rows come back as the oracle's rounded rows
     rec = idx.reconstruct_batch(I[0])
     np.testing.assert_allclose(rec, ref.reconstruct_batch(I[0]), rtol=2e-6 if store == "f32" else 1e-2, atol=1e-7)
+
+
+@pytest.mark.parametrize("store", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("name", ["lattice_l2", "lattice_ip"])
+def test_lattice_bit_exact_stream(pkg, name, store):
+    """Streaming scorer on lattice data, 1..4 queries per call: bit-exact ids and distances, lowest id on ties."""
+    g = _load(os.path.join(GOLDEN, f"search_{name}.npz"))
+    metric = pkg.METRIC_IP if name.endswith("ip") else pkg.METRIC_L2
+    idx = pkg.FlatIndex(g["xb"].shape[1], metric, store)
+    idx.add(g["xb"])
+    k = int(g["k"])
+    for q0, nq in ((0, 1), (1, 2), (3, 3), (6, 4)):
+        D, I = idx.search(g["xq"][q0:q0 + nq], k, algo="stream")
+        np.testing.assert_array_equal(I, g["idx"][q0:q0 + nq])
+        np.testing.assert_array_equal(D, g["dist"][q0:q0 + nq])
 
 
 @pytest.mark.parametrize("metric_s", ["L2", "IP"])
