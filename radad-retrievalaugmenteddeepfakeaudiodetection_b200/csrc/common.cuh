@@ -58,7 +58,6 @@ __device__ __forceinline__ float unordered_f32(uint32_t o) {
 // Selector policy used by the tensor-core epilogue for k <= KT (register-resident list).
 template <int KT>
 struct SelectSmall {
-  static constexpr bool kDirect = false;
   TopK<KT> top;
   __device__ __forceinline__ void init(int) { top.init(); }
   __device__ __forceinline__ float threshold() const { return top.worst(); }
@@ -78,7 +77,6 @@ struct SelectSmall {
 // Appends are ~k*ln(n/k) per thread per unit and cost one scattered local store each.
 template <int CAP>
 struct SelectReservoir {
-  static constexpr bool kDirect = true;
   static constexpr int B = 16;   // entries loaded per batch: independent local-memory loads in flight per thread
   uint32_t okey[CAP];   // ordered_f32(key); 0 = never a valid key of a finite score
   int idx[CAP];

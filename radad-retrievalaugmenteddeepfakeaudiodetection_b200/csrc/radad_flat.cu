@@ -313,15 +313,17 @@ template <typename T, bool L2>
 int launch_stream_t(rdb_handle* h, const T* Y, int ld, const float* Qs, int nq, int blocks, int rpb, float* ck, int* ci,
                     int kout) {
   const int nqt = nq <= 1 ? 1 : (nq <= 2 ? 2 : 4);
-  const size_t smem = stream_smem_bytes(nqt, ld);
-#define STREAM_LAUNCH(NQ)                                                                                    \
+  const int kl = kout <= 32 ? 1 : 4;
+  const size_t smem = stream_smem_bytes(nqt, ld, kl);
+#define STREAM_LAUNCH(NQ, KL)                                                                                \
   do {                                                                                                       \
-    auto kern = score_select_stream_kernel<T, NQ, L2>;                                                       \
+    auto kern = score_select_stream_kernel<T, NQ, L2, KL>;                                                   \
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     kern<<<dim3(blocks), dim3(STREAM_THREADS), smem, h->stream>>>(Y, ld, h->ynorm, int(h->n), Qs, nq, rpb, ck, ci, \
                                                                   kout);                                     \
   } while (0)
-  if (nqt == 1) STREAM_LAUNCH(1); else if (nqt == 2) STREAM_LAUNCH(2); else STREAM_LAUNCH(4);
+  if (kl == 1) { if (nqt == 1) STREAM_LAUNCH(1, 1); else if (nqt == 2) STREAM_LAUNCH(2, 1); else STREAM_LAUNCH(4, 1); }
+  else         { if (nqt == 1) STREAM_LAUNCH(1, 4); else if (nqt == 2) STREAM_LAUNCH(2, 4); else STREAM_LAUNCH(4, 4); }
 #undef STREAM_LAUNCH
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
@@ -414,11 +416,11 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   // fp32 re-rank + certificate, exact CUDA-core kernel for whatever cannot be certified (and for small cases).
   const bool tc_ok = sixteen ? (k <= kMaxKTc && h->n >= TC_BN) : (k <= kMaxKSplit && h->n >= TC_BN);
   // small batches are a pure HBM stream of the stored rows: dedicated streaming scorer (exact fp32 for fp32 stores)
-  const bool stream_ok = nq <= 4 && k <= 32 && h->n >= 1 && (sixteen || D % 4 == 0);
+  const bool stream_ok = nq <= 4 && k <= 128 && h->n >= 1 && (sixteen || D % 4 == 0);
   if (algo == RDB_ALGO_AUTO)
     algo = (stream_ok && h->n >= 4096) ? RDB_ALGO_STREAM : ((tc_ok && h->n >= kMinRowsTc) ? RDB_ALGO_TC : RDB_ALGO_SIMT);
   if (algo == RDB_ALGO_STREAM && !stream_ok)
-    return fail(h, RDB_ERR_UNSUPPORTED, "search: streaming scorer needs nq <= 4, k <= 32 (and D % 4 == 0 for fp32 stores)");
+    return fail(h, RDB_ERR_UNSUPPORTED, "search: streaming scorer needs nq <= 4, k <= 128 (and D % 4 == 0 for fp32 stores)");
   if (algo == RDB_ALGO_TC && !tc_ok)
     return fail(h, RDB_ERR_UNSUPPORTED,
                 "search: tensor-core scorer needs ntotal >= 256 and k <= 128 (16-bit store) / k <= 24 (fp32 store)");

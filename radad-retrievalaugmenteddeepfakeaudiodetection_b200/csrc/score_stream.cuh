@@ -3,7 +3,7 @@
 // through HBM (2*D flops per 2*D or 4*D bytes), so this kernel is built around the memory system instead of the
 // tensor cores: every warp reads whole rows with 128-bit coalesced loads (rows are contiguous -> full DRAM
 // pages, unlike 128-byte TMA box slices), 4 rows in flight per warp, fp32 FMA against the queries held in
-// shared memory, butterfly reduction, and a warp-distributed sorted top-k (lane j holds the j-th best; insertion
+// shared memory, butterfly reduction, and a warp-distributed sorted top-k (lane j holds ranks [KL*j, KL*j+KL); insertion
 // is a ballot + shuffle-shift).  The 16 warps of a block merge their lists in shared memory so each block emits
 // ONE sorted list per query; merge.cuh folds the gridDim.x lists.  Arithmetic is exact fp32 for fp32 stores
 // (no split / re-rank needed) and fp32-accumulated products of the stored 16-bit values otherwise.
@@ -47,18 +47,42 @@ template <> struct StreamVec<__half> {
   }
 };
 
-// warp-distributed sorted list: lane j holds the j-th best (key desc; equal keys in arrival = ascending-id order)
+// Warp-distributed sorted list, KL entries per lane: lane j holds ranks [KL*j, KL*j + KL) (key desc; equal keys in
+// arrival = ascending-id order).  KL = 1 serves k <= 32, KL = 4 serves k <= 128 -- registers only, no shared memory.
+template <int KL>
 struct WarpList {
-  float key; int idx;
-  __device__ __forceinline__ void init() { key = -CUDART_INF_F; idx = -1; }
-  __device__ __forceinline__ float threshold(int k) const { return __shfl_sync(0xffffffffu, key, k - 1); }
+  float key[KL]; int idx[KL];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int s = 0; s < KL; ++s) { key[s] = -CUDART_INF_F; idx[s] = -1; }
+  }
+  __device__ __forceinline__ float threshold(int k) const {
+    const int r = k - 1;
+    float v = key[0];
+#pragma unroll
+    for (int s = 1; s < KL; ++s) v = ((r % KL) == s) ? key[s] : v;
+    return __shfl_sync(0xffffffffu, v, r / KL);
+  }
   // all lanes call with the same (v, id); v > threshold(k)
   __device__ __forceinline__ void insert(float v, int id, int lane) {
-    const int pos = __popc(__ballot_sync(0xffffffffu, key >= v));   // keys >= v stay in front (stable)
-    const float uk = __shfl_up_sync(0xffffffffu, key, 1);
-    const int ui = __shfl_up_sync(0xffffffffu, idx, 1);
-    if (lane > pos) { key = uk; idx = ui; }
-    if (lane == pos) { key = v; idx = id; }
+    int pos = 0;                                          // entries >= v stay in front (stable)
+#pragma unroll
+    for (int s = 0; s < KL; ++s) pos += __popc(__ballot_sync(0xffffffffu, key[s] >= v));
+    const int L = pos / KL, sl = pos % KL;
+    const float ck = __shfl_up_sync(0xffffffffu, key[KL - 1], 1);   // previous lane's last entry
+    const int ci = __shfl_up_sync(0xffffffffu, idx[KL - 1], 1);
+    if (lane > L) {
+#pragma unroll
+      for (int s = KL - 1; s > 0; --s) { key[s] = key[s - 1]; idx[s] = idx[s - 1]; }
+      key[0] = ck; idx[0] = ci;
+    } else if (lane == L) {
+#pragma unroll
+      for (int s = KL - 1; s > 0; --s)
+        if (s > sl) { key[s] = key[s - 1]; idx[s] = idx[s - 1]; }
+#pragma unroll
+      for (int s = 0; s < KL; ++s)
+        if (s == sl) { key[s] = v; idx[s] = id; }
+    }
   }
 };
 
@@ -66,7 +90,7 @@ struct WarpList {
 // D itself must be a multiple of EPV for fp32 (checked by the host; otherwise another scorer is used).
 // Qs: queries as fp32 [NQ][ld] in global memory (already normalised / rounded to the store dtype).
 // cand_* [nq][gridDim.x][kout].
-template <typename T, int NQ, bool L2>
+template <typename T, int NQ, bool L2, int KL>
 __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
     const T* __restrict__ Y, int ld, const float* __restrict__ ynorm, int N, const float* __restrict__ Qs, int nq,
     int rows_per_block, float* __restrict__ cand_key, int* __restrict__ cand_idx, int kout) {
@@ -81,7 +105,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
   const int row_begin = blockIdx.x * rows_per_block;
   const int row_end = min(N, row_begin + rows_per_block);
 
-  WarpList top[NQ];
+  WarpList<KL> top[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) top[q].init();
   float thr[NQ];
@@ -140,24 +164,27 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
 
   // ---- in-block merge: 16 warp lists -> 1 list per query
   __syncthreads();                                       // queries no longer needed: reuse smem
-  float* lk = sm;                                        // [NQ][STREAM_WARPS][32]
-  int* li = reinterpret_cast<int*>(sm + NQ * STREAM_WARPS * 32);
+  constexpr int LW = 32 * KL;                            // entries per warp list
+  float* lk = sm;                                        // [NQ][STREAM_WARPS][LW]
+  int* li = reinterpret_cast<int*>(sm + NQ * STREAM_WARPS * LW);
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    lk[(q * STREAM_WARPS + warp) * 32 + lane] = top[q].key;
-    li[(q * STREAM_WARPS + warp) * 32 + lane] = top[q].idx;
-  }
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int sl = 0; sl < KL; ++sl) {
+      lk[(q * STREAM_WARPS + warp) * LW + lane * KL + sl] = top[q].key[sl];
+      li[(q * STREAM_WARPS + warp) * LW + lane * KL + sl] = top[q].idx[sl];
+    }
   __syncthreads();
   if (warp < nq) {
     const int q = warp;
     // lane w < STREAM_WARPS owns list w; k rounds of warp arg-best over the heads (key desc, id asc)
     int ptr = 0;
     const bool own = lane < STREAM_WARPS;
-    const float* mk = lk + (q * STREAM_WARPS + (own ? lane : 0)) * 32;
-    const int* mi = li + (q * STREAM_WARPS + (own ? lane : 0)) * 32;
+    const float* mk = lk + (q * STREAM_WARPS + (own ? lane : 0)) * LW;
+    const int* mi = li + (q * STREAM_WARPS + (own ? lane : 0)) * LW;
     for (int r = 0; r < kout; ++r) {
       uint32_t ok = 0; int id = 0x7FFFFFFF; float kv = 0.f;
-      if (own && ptr < 32 && mi[ptr] >= 0) { kv = mk[ptr]; ok = ordered_f32(kv); id = mi[ptr]; }
+      if (own && ptr < LW && mi[ptr] >= 0) { kv = mk[ptr]; ok = ordered_f32(kv); id = mi[ptr]; }
       uint32_t wok = ok; int wid = id; int wl = lane;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -178,8 +205,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
   }
 }
 
-constexpr size_t stream_smem_bytes(int nq_t, int ld) {
-  const size_t a = size_t(nq_t) * ld * 4, b = size_t(nq_t) * STREAM_WARPS * 32 * 8;
+constexpr size_t stream_smem_bytes(int nq_t, int ld, int kl) {
+  const size_t a = size_t(nq_t) * ld * 4, b = size_t(nq_t) * STREAM_WARPS * 32 * kl * 8;
   return a > b ? a : b;
 }
 

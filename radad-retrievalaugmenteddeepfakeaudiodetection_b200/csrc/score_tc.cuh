@@ -99,28 +99,43 @@ __device__ __forceinline__ void tc_process32(uint32_t (&r)[32], Sel& sel, const 
 #pragma unroll
   for (int o = 0; o < 4; ++o) oct[o] = fmaxf(m[2 * o], m[2 * o + 1]);
   const float mx = fmaxf(fmaxf(oct[0], oct[1]), fmaxf(oct[2], oct[3]));
-  if (mx > worst || nvalid < 32) {
-    if (Sel::kDirect) {
-      // frequent, cheap hits (large-k reservoir): visit only the octets that hold a survivor and append directly
+  if (nvalid < 32) {
+    // ragged last tile (rare): generic 32-wide mask
+    uint32_t mask = 0;
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        if (oct[o] > worst) {
+    for (int j = 0; j < 32; ++j) mask |= (v[j] > worst) ? (1u << j) : 0u;
+    mask &= (nvalid <= 0) ? 0u : (0xFFFFFFFFu >> (32 - nvalid));
+    while (mask) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      sel.offer(sel32(v, j), col0 + j);
+    }
+  } else if (mx > worst) {
+    // slow path, kept warp-convergent and narrow: lanes walk their hot octets (usually one); the octet's 8 values
+    // are fetched with a 2-level select, reduced to an 8-bit mask, and survivors go through ONE offer site.
+    uint32_t hot = (oct[0] > worst ? 1u : 0u) | (oct[1] > worst ? 2u : 0u) | (oct[2] > worst ? 4u : 0u) |
+                   (oct[3] > worst ? 8u : 0u);
+    while (hot) {
+      const int o = __ffs(hot) - 1;
+      hot &= hot - 1;
+      float w[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (8 * o + j < nvalid) sel.offer(v[8 * o + j], col0 + 8 * o + j);
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float a = (o & 1) ? v[8 + j] : v[j];
+        const float b = (o & 1) ? v[24 + j] : v[16 + j];
+        w[j] = (o & 2) ? b : a;
       }
-    } else {
-      // rare, expensive hits (register-resident sorted list): bit mask + select tree keeps the insert code single
-      uint32_t mk[4] = {0u, 0u, 0u, 0u};          // 4 independent chains instead of one 32-deep OR chain
+      const float th = sel.threshold();
+      uint32_t m8 = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mk[j & 3] |= (v[j] > worst) ? (1u << j) : 0u;
-      uint32_t mask = (mk[0] | mk[1]) | (mk[2] | mk[3]);
-      if (nvalid < 32) mask &= (nvalid <= 0) ? 0u : (0xFFFFFFFFu >> (32 - nvalid));
-      while (mask) {
-        const int j = __ffs(mask) - 1;
-        mask &= mask - 1;
-        sel.offer(sel32(v, j), col0 + j);
+      for (int j = 0; j < 8; ++j) m8 |= (w[j] > th) ? (1u << j) : 0u;
+      while (m8) {
+        const int j = __ffs(m8) - 1;
+        m8 &= m8 - 1;
+        const float x01 = (j & 1) ? w[1] : w[0], x23 = (j & 1) ? w[3] : w[2];
+        const float x45 = (j & 1) ? w[5] : w[4], x67 = (j & 1) ? w[7] : w[6];
+        const float xa = (j & 2) ? x23 : x01, xb = (j & 2) ? x67 : x45;
+        sel.offer((j & 4) ? xb : xa, col0 + 8 * o + j);
       }
     }
   }

@@ -116,6 +116,9 @@ CASES = [
     ("stream_ip_bf16_q3",  7003,  100, 3, 32, "IP", False, "bf16", "stream"),   # Dp = 104, ragged N
     ("stream_l2_f16_q4",   9000,  256, 4, 5,  "L2", False, "f16",  "stream"),
     ("auto_l2_f32_q1",     30000, 768, 1, 15, "L2", False, "f32",  "auto"),
+    ("stream_ip_bf16_q1_k100", 40000, 256, 1, 100, "IP", True, "bf16", "stream"),   # C5, Q = 1
+    ("stream_l2_f32_q4_k128",  9000,  128, 4, 128, "L2", False, "f32", "stream"),
+    ("stream_l2_bf16_q2_k33",  5001,  64,  2, 33,  "L2", False, "bf16", "stream"),
     # large k on the tensor cores: local-memory reservoir + exact bisection prune (C5: k = 100, D = 256)
     ("ip_bf16_tc_k100", 60000, 256, 300, 100, "IP", True,  "bf16", "tc"),
     ("l2_bf16_tc_k64",  20000, 128, 130, 64,  "L2", False, "bf16", "tc"),
