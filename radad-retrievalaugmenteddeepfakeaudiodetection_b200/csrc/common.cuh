@@ -56,17 +56,36 @@ __device__ __forceinline__ float unordered_f32(uint32_t o) {
 }
 
 // Selector policy used by the tensor-core epilogue for k <= KT (register-resident list).
+// Cross-unit threshold sharing.  gthr[q] holds (as an ordered uint, 0 = none) a lower bound of the GLOBAL k-th best
+// key of query q over everything any work unit has seen so far: a unit's local k-th best can only be <= the global
+// one, so publishing it with atomicMax is always safe.  Units run chunk-major, so a unit usually starts with the
+// bound left by the previous chunks and admits ~k/j new elements instead of k*ln(n/k).  Elements EQUAL to the bound
+// must still be admitted (the bound may come from rows with higher ids), hence floor = the next float below it.
+__device__ __forceinline__ float floor_from_gthr(uint32_t g) {
+  return (g >= 2u) ? unordered_f32(g - 1u) : -CUDART_INF_F;
+}
+
 template <int KT>
 struct SelectSmall {
   TopK<KT> top;
-  __device__ __forceinline__ void init(int) { top.init(); }
-  __device__ __forceinline__ float threshold() const { return top.worst(); }
-  __device__ __forceinline__ void offer(float v, int id) { if (v > top.worst()) top.insert(v, id); }
+  float floor_;
+  uint32_t* gq;
+  __device__ __forceinline__ void init(int, uint32_t* gthr_q) {
+    top.init();
+    gq = gthr_q;
+    floor_ = gq ? floor_from_gthr(__ldcg(gq)) : -CUDART_INF_F;
+  }
+  __device__ __forceinline__ float threshold() const { return fmaxf(top.worst(), floor_); }
+  __device__ __forceinline__ void offer(float v, int id) { if (v > threshold()) top.insert(v, id); }
   __device__ __forceinline__ void end_group(int) {}
   __device__ __forceinline__ void finalize(int kout, float* __restrict__ ck, int* __restrict__ ci) {
+    float kth = -CUDART_INF_F;
 #pragma unroll
-    for (int j = 0; j < KT; ++j)
+    for (int j = 0; j < KT; ++j) {
       if (j < kout) { ck[j] = top.key[j]; ci[j] = top.idx[j]; }
+      if (j == kout - 1) kth = top.key[j];
+    }
+    if (gq && kth > -CUDART_INF_F) atomicMax(gq, ordered_f32(kth));
   }
 };
 
@@ -82,7 +101,13 @@ struct SelectReservoir {
   int idx[CAP];
   int cnt, k;
   float thr;
-  __device__ __forceinline__ void init(int k_) { cnt = 0; k = k_; thr = -CUDART_INF_F; }
+  uint32_t* gq;
+  __device__ __forceinline__ void init(int k_, uint32_t* gthr_q) {
+    cnt = 0; k = k_; gq = gthr_q;
+    thr = gq ? floor_from_gthr(__ldcg(gq)) : -CUDART_INF_F;
+  }
+  // tighten the admission threshold with what other units (and the other column half) have published
+  __device__ __forceinline__ void refresh() { if (gq) thr = fmaxf(thr, floor_from_gthr(__ldcg(gq))); }
   __device__ __forceinline__ float threshold() const { return thr; }
   __device__ __forceinline__ void offer(float v, int id) {
     if (v > thr) { okey[cnt] = ordered_f32(v); idx[cnt] = id; ++cnt; }
@@ -93,7 +118,7 @@ struct SelectReservoir {
   }
   // exact prune to the best k entries (no-op for lanes holding <= k); all loops are warp-convergent
   __device__ __noinline__ void prune() {
-    if (cnt <= k) return;
+    if (cnt <= k) { refresh(); return; }
     uint32_t lo = 0xFFFFFFFFu, hi = 0u;
     for (int i = 0; i < cnt; i += B) {
       uint32_t o[B];
@@ -146,7 +171,9 @@ struct SelectReservoir {
       }
     }
     cnt = w;
-    thr = unordered_f32(t);
+    thr = fmaxf(thr, unordered_f32(t));
+    if (gq) atomicMax(gq, t);            // t = exact k-th best of everything this thread has seen: a global lower bound
+    refresh();
   }
   __device__ __forceinline__ void end_group(int room) {
     if (__any_sync(0xffffffffu, cnt > CAP - room)) prune();

@@ -90,7 +90,7 @@ struct rdb_handle {
   std::mutex mu;
   // scratch
   DevBuf add_stage, q_stage, qf, qhi, qlo, qnorm, cand_key, cand_idx, o_dist, o_idx, o_lbl, ids_stage, rec_stage;
-  DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l, qs16;
+  DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l, qs16, gthr;
   float* d_ynorm_max = nullptr;   // max |y|^2 over the shard (device scalar; feeds the re-rank certificate)
   int64_t last_uncertified = 0;
   bool has_master() const { return store == RDB_STORE_F32 || (flags & RDB_FLAG_KEEP_F32_MASTER); }
@@ -273,6 +273,9 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
     p.tmap_y[1] = p.tmap_y[0];
   }
   p.ynorm = h->ynorm; p.cand_key = ck; p.cand_idx = ci;
+  CUDA_TRY(h, h->gthr.ensure(size_t(nq) * 4));
+  CUDA_TRY(h, cudaMemsetAsync(h->gthr.p, 0, size_t(nq) * 4, h->stream));
+  p.gthr = (S > 1 || TC_LISTS > 1) ? h->gthr.as<uint32_t>() : nullptr;
   p.nq = nq; p.N = int(h->n); p.D = h->d;
   p.nqt = nqt; p.S = S; p.tiles_per_chunk = tiles_per_chunk; p.ntiles = ntiles; p.kout = k;
   p.num_units = nqt * S; p.nterms = nterms;
@@ -315,12 +318,15 @@ int launch_stream_t(rdb_handle* h, const T* Y, int ld, const float* Qs, int nq, 
   const int nqt = nq <= 1 ? 1 : (nq <= 2 ? 2 : 4);
   const int kl = kout <= 32 ? 1 : 4;
   const size_t smem = stream_smem_bytes(nqt, ld, kl);
+  // lanes per row: whole warp for long rows, 16 / 8 lanes when a row is only a few 128-bit vectors
+  const int nvec = ld / StreamVec<T>::EPV;
+  const int lpr_log2 = nvec >= 96 ? 5 : (nvec >= 48 ? 4 : 3);
 #define STREAM_LAUNCH(NQ, KL)                                                                                \
   do {                                                                                                       \
     auto kern = score_select_stream_kernel<T, NQ, L2, KL>;                                                   \
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     kern<<<dim3(blocks), dim3(STREAM_THREADS), smem, h->stream>>>(Y, ld, h->ynorm, int(h->n), Qs, nq, rpb, ck, ci, \
-                                                                  kout);                                     \
+                                                                  kout, lpr_log2);                           \
   } while (0)
   if (kl == 1) { if (nqt == 1) STREAM_LAUNCH(1, 1); else if (nqt == 2) STREAM_LAUNCH(2, 1); else STREAM_LAUNCH(4, 1); }
   else         { if (nqt == 1) STREAM_LAUNCH(1, 4); else if (nqt == 2) STREAM_LAUNCH(2, 4); else STREAM_LAUNCH(4, 4); }
@@ -361,7 +367,7 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
   } else if (algo == RDB_ALGO_STREAM) {
     // small batch: one block per SM streams a contiguous slice of the stored rows; one list per block
     const int blocks = int(std::min<int64_t>(h->num_sms, (h->n + 31) / 32));
-    const int rpb = int(round_up((h->n + blocks - 1) / blocks, 8));
+    const int rpb = int(round_up((h->n + blocks - 1) / blocks, 32));
     S = int((h->n + rpb - 1) / rpb);
     CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * kc * 4));
     CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * kc * 4));
@@ -612,7 +618,7 @@ int rdb_destroy(rdb_handle* h) {
     cudaFree(h->d_ynorm_max);
     for (DevBuf* b : {&h->add_stage, &h->q_stage, &h->qf, &h->qhi, &h->qlo, &h->qnorm, &h->cand_key, &h->cand_idx,
                       &h->o_dist, &h->o_idx, &h->o_lbl, &h->ids_stage, &h->rec_stage, &h->rr_key, &h->rr_idx,
-                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l, &h->qs16})
+                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l, &h->qs16, &h->gthr})
       b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

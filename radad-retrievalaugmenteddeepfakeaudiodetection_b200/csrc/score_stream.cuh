@@ -93,7 +93,7 @@ struct WarpList {
 template <typename T, int NQ, bool L2, int KL>
 __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
     const T* __restrict__ Y, int ld, const float* __restrict__ ynorm, int N, const float* __restrict__ Qs, int nq,
-    int rows_per_block, float* __restrict__ cand_key, int* __restrict__ cand_idx, int kout) {
+    int rows_per_block, float* __restrict__ cand_key, int* __restrict__ cand_idx, int kout, int lpr_log2) {
   extern __shared__ __align__(16) float sm[];
   float* qs = sm;                                        // [NQ][ld]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -112,19 +112,23 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
 #pragma unroll
   for (int q = 0; q < NQ; ++q) thr[q] = -CUDART_INF_F;
 
-  // warp w takes rows row_begin + (g * STREAM_WARPS + w) * R .. + R   (R rows in flight), g = 0, 1, ...
+  // Lane groups of `lpr` lanes own rows (short rows: 8 or 16 lanes per row, so the shuffle reduction is amortised over
+  // several rows per warp step).  Per step a warp takes RW = R * G consecutive rows: group g rows r0 + g*R .. + R.
   constexpr int R = StreamVec<T>::R;
-  for (int r0 = row_begin + warp * R; r0 < row_end; r0 += STREAM_WARPS * R) {
+  const int lpr = 1 << lpr_log2, G = 32 >> lpr_log2;
+  const int grp = lane >> lpr_log2, l = lane & (lpr - 1);
+  const int RW = R * G;
+  for (int r0 = row_begin + warp * RW; r0 < row_end; r0 += STREAM_WARPS * RW) {
     float acc[R][NQ];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int q = 0; q < NQ; ++q) acc[r][q] = 0.f;
-    for (int c = lane; c < nvec; c += 32) {
+    for (int c = l; c < nvec; c += lpr) {
       float y[R][EPV];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int row = min(r0 + r, row_end - 1);        // clamp: duplicates are discarded below
+        const int row = min(r0 + grp * R + r, row_end - 1);   // clamp: duplicates are discarded below
         StreamVec<T>::load(Y + (long long)row * ld + c * EPV, y[r]);
       }
 #pragma unroll
@@ -141,21 +145,27 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
           for (int e = 0; e < EPV; ++e) acc[r][q] = fmaf(qv[e], y[r][e], acc[r][q]);
       }
     }
+    for (int o = lpr >> 1; o > 0; o >>= 1)
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int row = r0 + r;
-      if (row < row_end) {                               // warp-uniform
-        float yn = 0.f;
-        if (L2) yn = __ldg(ynorm + row);
+      for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          float s = acc[r][q];
+        for (int q = 0; q < NQ; ++q) acc[r][q] += __shfl_xor_sync(0xffffffffu, acc[r][q], o);
+    // offer the RW scores in ascending row order (warp-uniform control flow)
+    for (int gg = 0; gg < G; ++gg) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          const float key = L2 ? fmaf(2.0f, s, -yn) : s;
-          if (q < nq && key > thr[q]) {                  // warp-uniform
-            top[q].insert(key, row, lane);
-            thr[q] = top[q].threshold(kout);
+      for (int r = 0; r < R; ++r) {
+        const int row = r0 + gg * R + r;
+        if (row < row_end) {
+          float yn = 0.f;
+          if (L2) yn = __ldg(ynorm + row);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const float sc = __shfl_sync(0xffffffffu, acc[r][q], gg << lpr_log2);
+            const float key = L2 ? fmaf(2.0f, sc, -yn) : sc;
+            if (q < nq && key > thr[q]) {
+              top[q].insert(key, row, lane);
+              thr[q] = top[q].threshold(kout);
+            }
           }
         }
       }

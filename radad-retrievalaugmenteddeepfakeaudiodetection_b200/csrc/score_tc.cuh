@@ -45,6 +45,7 @@ struct TcParams {
   const float* ynorm;     // [N] |y|^2 (L2 only)
   float* cand_key;        // [nq][S * TC_LISTS][kout]
   int* cand_idx;          // [nq][S * TC_LISTS][kout]  local row ids, -1 = empty
+  uint32_t* gthr;         // [nq] shared lower bound of the global k-th best key (ordered uint, 0 = none), or null
   int nq, N, D;
   int nqt, S, tiles_per_chunk, ntiles, kout, num_units, nterms;
   uint32_t idesc;
@@ -241,8 +242,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       const int qtile = unit % p.nqt, chunk = unit / p.nqt;
       const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
+      const long long q = (long long)qtile * TC_BM + row;
       Sel sel;
-      sel.init(p.kout);
+      sel.init(p.kout, (p.gthr && q < p.nq) ? p.gthr + q : nullptr);
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
@@ -273,7 +275,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      const long long q = (long long)qtile * TC_BM + row;
       if (q < p.nq) {
         const long long base = ((q * p.S + chunk) * TC_LISTS + half) * (long long)p.kout;
         sel.finalize(p.kout, p.cand_key + base, p.cand_idx + base);
