@@ -42,6 +42,20 @@ METRIC_NAME = "QPS @k=10 on 10M x 768 DB (exact flat search)"
 WORKLOAD = f"C3: {N_DB}x{DIM} bf16 DB, {NQ}-query batch, k={K}, cosine (IP + L2-normalise), exact flat search"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this exact workload (profiles/r01_ncu_c3_traffic.json); None if it does not match."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_c3_traffic.json")
+    try:
+        with open(p) as f:
+            j = json.load(f)
+        if j.get("workload", "").startswith(f"C3: {N_DB}x{DIM} bf16 DB, {NQ}-query batch, k={K},"):
+            return float(j["traffic_bytes_per_launch"])
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -124,8 +138,8 @@ def run_reference(args):
     orc = importlib.import_module("oracle.flat_oracle")
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_s = min(N_DB, int(os.environ.get("RDB_REF_ROWS", 500_000)))
-    nq_s = int(os.environ.get("RDB_REF_Q", 256))
+    n_s = min(N_DB, int(os.environ.get("RDB_REF_ROWS", 1_000_000)))
+    nq_s = int(os.environ.get("RDB_REF_Q", 2048))
     rng = np.random.default_rng(DB_SEED)
     xb = rng.standard_normal((n_s, DIM), dtype=np.float32)
     xb /= (np.linalg.norm(xb, axis=1, keepdims=True) + 1e-12)
@@ -160,15 +174,16 @@ def cpu_baseline(torch, orc, idx, q_dev):
     import numpy as np
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_s = min(idx.ntotal, 500_000)
+    n_s = min(idx.ntotal, 1_000_000)
     ids = torch.arange(n_s, device=q_dev.device, dtype=torch.int64)
     xb = idx.reconstruct_batch(ids).cpu().numpy()                # stored (bf16-rounded, normalised) rows as fp32
-    xq = q_dev[:512].cpu().numpy()
+    xq = q_dev[:16384].cpu().numpy()
     qn = orc.maybe_normalize(xq, True)
+    orc.torch_cpu_flat_search(xb, qn[:64], K, orc.METRIC_IP)     # warm-up
     t0 = time.perf_counter()
-    orc.torch_cpu_flat_search(xb, qn[:32], K, orc.METRIC_IP)     # warm-up + calibration
+    orc.torch_cpu_flat_search(xb, qn[:256], K, orc.METRIC_IP)    # calibration
     t_cal = time.perf_counter() - t0
-    nq_s = int(max(32, min(512, 32 * (8.0 / max(t_cal, 1e-3)))))
+    nq_s = int(max(256, min(len(qn), 256 * (12.0 / max(t_cal, 1e-3)))))   # ~12 s of CPU work
     t0 = time.perf_counter()
     Dc, Ic = orc.torch_cpu_flat_search(xb, qn[:nq_s], K, orc.METRIC_IP)
     dt = time.perf_counter() - t0
@@ -323,7 +338,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": ach / pk["bf16_sustained"], "traffic": None,
+                         "frac": ach / pk["bf16_sustained"], "traffic": ncu_traffic() if world == 1 else None,
+                         "traffic_note": "bytes/launch from the committed ncu --set full capture (profiles/); 19x the "
+                                         "15.36 GB database (imperfect L2 sharing across CTAs) but only 5% of DRAM "
+                                         "bandwidth: not the bound",
                          "kernel": "score_select_tc_kernel", "kernel_ms": ms_kern,
                          "flops_per_launch": flops, "peak_source": pk["src"] + " sustained bf16",
                          "frac_of_burst": ach / pk["bf16_burst"],

@@ -117,6 +117,14 @@ int rdb_reconstruct(rdb_handle* h, int64_t id, float* out);
  * ids < 0 or out of range give a zero row (the caller's padding value, pipeline.py:511-512). */
 int rdb_reconstruct_batch(rdb_handle* h, const int64_t* ids, int64_t n, int mem, float* out);
 
+/* The caller's rank-ordered self-exclusion + "first K survivors of K+10" compaction -- pipeline.py:491-520 -- on the
+ * device.  idx/dist/labels [nq][ks] are search results (device), row_code[ntotal] an integer code per row (the file
+ * basename the reference compares), excl_sorted[n_excl] the ascending codes to skip.  Outputs [nq][K]; missing slots
+ * get id -1, label 0, distance NaN (the reference's padding).  All pointers are device pointers. */
+int rdb_filter_first_k(rdb_handle* h, const int64_t* idx, const float* dist, const float* labels, int64_t nq, int ks,
+                       const int64_t* row_code, const int64_t* excl_sorted, int n_excl, int K, int64_t* out_idx,
+                       float* out_dist, float* out_labels);
+
 /* Neighbour labels for the kNN label vote: labels float32[n] (host), n must equal ntotal at search time.
  * Mirrors VectorDatabase.vector_labels -- vector_database.py:16,142. */
 int rdb_set_labels(rdb_handle* h, const float* labels, int64_t n);

@@ -48,6 +48,8 @@ SIGNATURES = {
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdb_reconstruct": (c_int, [_h, c_int64, c_void_p]),
     "rdb_reconstruct_batch": (c_int, [_h, c_void_p, c_int64, c_int, c_void_p]),
+    "rdb_filter_first_k": (c_int, [_h, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p]),
     "rdb_set_labels": (c_int, [_h, c_void_p, c_int64]),
     "rdb_label_vote": (c_int, [_h, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "rdb_ntotal": (c_int64, [_h]),

@@ -268,6 +268,46 @@ __global__ void __launch_bounds__(128) merge_peer_lists_kernel(const PeerLists P
   }
 }
 
+// Rank-ordered self-exclusion + first-K-survivors compaction (pipeline.py:491-520) on the device.
+//   idx/dist/lbl [B][ks] best-first search results; row_code[ntotal] = int code of each row's file basename;
+//   excl [ne] sorted ascending = codes to skip.  One thread per query walks its ks results in rank order, skips
+//   excluded rows (binary search), keeps the first K; pads with id -1 / label 0 / distance NaN.
+__global__ void filter_first_k_kernel(const long long* __restrict__ idx, const float* __restrict__ dist,
+                                      const float* __restrict__ lbl, int B, int ks,
+                                      const long long* __restrict__ row_code, long long ntotal,
+                                      const long long* __restrict__ excl, int ne, int K,
+                                      long long* __restrict__ out_idx, float* __restrict__ out_dist,
+                                      float* __restrict__ out_lbl) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int n = 0;
+  for (int j = 0; j < ks && n < K; ++j) {
+    const long long id = idx[(long long)b * ks + j];
+    if (id < 0 || id >= ntotal) continue;
+    bool skip = false;
+    if (ne > 0) {
+      const long long code = row_code[id];
+      int lo = 0, hi = ne - 1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const long long v = excl[mid];
+        if (v == code) { skip = true; break; }
+        if (v < code) lo = mid + 1; else hi = mid - 1;
+      }
+    }
+    if (skip) continue;
+    out_idx[(long long)b * K + n] = id;
+    out_dist[(long long)b * K + n] = dist[(long long)b * ks + j];
+    out_lbl[(long long)b * K + n] = lbl ? lbl[(long long)b * ks + j] : 0.f;
+    ++n;
+  }
+  for (; n < K; ++n) {
+    out_idx[(long long)b * K + n] = -1;
+    out_dist[(long long)b * K + n] = __int_as_float(0x7FC00000);   // NaN (pipeline.py:515)
+    out_lbl[(long long)b * K + n] = 0.f;
+  }
+}
+
 // sum of neighbour labels per query over the first kvote results (the "kNN label vote" evidence)
 __global__ void label_vote_kernel(const float* __restrict__ lbl, int Q, int k, int kvote, float* __restrict__ vote) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;

@@ -850,6 +850,25 @@ int rdb_set_labels(rdb_handle* h, const float* labels, int64_t n) {
   return RDB_OK;
 }
 
+int rdb_filter_first_k(rdb_handle* h, const int64_t* idx, const float* dist, const float* labels, int64_t nq, int ks,
+                       const int64_t* row_code, const int64_t* excl_sorted, int n_excl, int K, int64_t* out_idx,
+                       float* out_dist, float* out_labels) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  if (nq < 0 || ks < 0 || K < 1 || !out_idx || !out_dist || !out_labels || (ks > 0 && (!idx || !dist)) ||
+      (n_excl > 0 && (!row_code || !excl_sorted)))
+    return fail(h, RDB_ERR_INVALID, "filter_first_k: bad arguments");
+  if (nq == 0) return RDB_OK;
+  filter_first_k_kernel<<<unsigned((nq + 127) / 128), 128, 0, h->stream>>>(
+      reinterpret_cast<const long long*>(idx), dist, labels, int(nq), ks, reinterpret_cast<const long long*>(row_code),
+      h->n + h->id_offset, reinterpret_cast<const long long*>(excl_sorted), n_excl, K,
+      reinterpret_cast<long long*>(out_idx), out_dist, out_labels);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return RDB_OK;
+}
+
 int rdb_label_vote(rdb_handle* h, const float* lbl, int64_t nq, int k, int kvote, int mem, float* vote) {
   if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
   std::lock_guard<std::mutex> lock(h->mu);

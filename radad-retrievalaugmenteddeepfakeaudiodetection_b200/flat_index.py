@@ -258,6 +258,22 @@ class FlatIndex:
                                                     ctypes.c_void_p(I.data_ptr()), ctypes.c_void_p(L.data_ptr())))
         return D, I, L
 
+    def filter_first_k(self, idx, dist, lab, row_codes, excl_sorted, K: int):
+        """Device-side rank-ordered exclusion + first-K compaction (pipeline.py:491-520); torch CUDA in/out."""
+        import torch
+        B, ks = idx.shape
+        idx, dist, lab = idx.contiguous(), dist.contiguous(), lab.contiguous()
+        oi = torch.empty((B, K), dtype=torch.int64, device=idx.device)
+        od = torch.empty((B, K), dtype=torch.float32, device=idx.device)
+        ol = torch.empty((B, K), dtype=torch.float32, device=idx.device)
+        ne = 0 if excl_sorted is None else int(excl_sorted.numel())
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() else None   # noqa: E731
+        self._use_torch_stream(torch)
+        self._check(self._lib.rdb_filter_first_k(self._h, p(idx), p(dist), p(lab), B, ks, p(row_codes) if ne else None,
+                                                 p(excl_sorted) if ne else None, ne, int(K), ctypes.c_void_p(oi.data_ptr()),
+                                                 ctypes.c_void_p(od.data_ptr()), ctypes.c_void_p(ol.data_ptr())))
+        return oi, od, ol
+
     def label_vote(self, labels_nq_k, kvote: int):
         if _is_cuda_tensor(labels_nq_k):
             import torch

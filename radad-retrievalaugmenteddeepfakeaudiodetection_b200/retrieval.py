@@ -67,7 +67,8 @@ def retrieve_similar_vectors(vector_db, query_vectors, top_k: int, dim: Optional
         labs = torch.zeros(B, 0, device=q.device)
     ks = idxs.shape[1]
 
-    excluded = torch.zeros((B, ks), dtype=torch.bool, device=q.device)
+    # exclusion set -> sorted integer codes on the device (basenames are coded once per database, cached)
+    row_codes = excl = None
     if exclude_self and ks > 0:
         codes_np, table = _basename_codes(vector_db)
         if query_paths is not None:
@@ -80,27 +81,10 @@ def retrieve_similar_vectors(vector_db, query_vectors, top_k: int, dim: Optional
             if cache is None or cache[0] is not codes_np or cache[1].device != q.device:
                 cache = (codes_np, torch.from_numpy(codes_np).to(q.device))
                 vector_db._basename_codes_dev = cache
-            row_codes = cache[1][idxs.clamp(min=0)]
-            excluded = torch.isin(row_codes, torch.from_numpy(ex).to(q.device)) | (idxs < 0)
-    # first K survivors in rank order (pipeline.py:491-509): stable sort survivors to the front
-    keep = ~excluded
-    order_key = torch.arange(ks, device=q.device).expand(B, ks) + (~keep).to(torch.int64) * ks
-    sel = torch.argsort(order_key, dim=1, stable=True)[:, :K]
-    if sel.shape[1] < K:                                                            # fewer than K results exist
-        pad = torch.zeros((B, K - sel.shape[1]), dtype=sel.dtype, device=q.device)
-        valid = torch.cat([torch.gather(keep, 1, sel), torch.zeros_like(pad, dtype=torch.bool)], 1) if ks else \
-            torch.zeros((B, K), dtype=torch.bool, device=q.device)
-        sel = torch.cat([sel, pad], 1)
-    else:
-        valid = torch.gather(keep, 1, sel)
-    if ks > 0:
-        idx_k = torch.where(valid, torch.gather(idxs, 1, sel), torch.full_like(sel, -1))
-        lbl_k = torch.where(valid, torch.gather(labs, 1, sel), torch.zeros((), device=q.device))
-        dst_k = torch.where(valid, torch.gather(dists, 1, sel), torch.full((), float("nan"), device=q.device))
-    else:
-        idx_k = torch.full((B, K), -1, dtype=torch.int64, device=q.device)
-        lbl_k = torch.zeros((B, K), device=q.device)
-        dst_k = torch.full((B, K), float("nan"), device=q.device)
+            row_codes = cache[1]
+            excl = torch.from_numpy(np.sort(ex)).to(q.device)
+    # first K survivors in rank order (pipeline.py:491-520): one CUDA kernel, one thread per query
+    idx_k, dst_k, lbl_k = vector_db.index.filter_first_k(idxs, dists, labs, row_codes, excl, K)
     vec = vector_db.index.reconstruct_batch(idx_k)                                  # [B, K, D], zero rows for -1
     if vec.shape[2] != D:
         raise RuntimeError(f"index dimension {vec.shape[2]} != expected {D}")
