@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -241,6 +242,16 @@ int launch_simt(rdb_handle* h, const float* qf, const void* qhi, int nq, int k, 
 #undef SIMT_CASE
 }
 
+// tuning knob (profiling only): RDB_TC_HINT_{Q,Y} = first | normal | last
+uint64_t l2_hint_from_env(const char* name, uint64_t dflt) {
+  const char* v = getenv(name);
+  if (!v) return dflt;
+  if (!strcmp(v, "first")) return kEvictFirst;
+  if (!strcmp(v, "last")) return kEvictLast;
+  if (!strcmp(v, "normal")) return kEvictNormal;
+  return dflt;
+}
+
 constexpr int kReservoirCap = 320;   // large-k epilogue: room for 128 kept + >= 160 appended between prunes
 
 int encode_2d(rdb_handle* h, CUtensorMap* m, const void* base, int64_t rows, int D, int Dp, int box_rows) {
@@ -280,6 +291,8 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
   p.nqt = nqt; p.S = S; p.tiles_per_chunk = tiles_per_chunk; p.ntiles = ntiles; p.kout = k;
   p.num_units = nqt * S; p.nterms = nterms;
   p.idesc = make_idesc_f16(TC_BM, TC_BN, h->f16() ? 0 : 1);
+  p.hint_q = l2_hint_from_env("RDB_TC_HINT_Q", kEvictLast);     // queries: re-read for every DB tile -> keep
+  p.hint_y = l2_hint_from_env("RDB_TC_HINT_Y", kEvictNormal);   // database tiles: shared by the CTAs of a wave
   const int grid = std::min(p.num_units, h->num_sms);
   const bool l2 = h->metric == RDB_METRIC_L2;
 #define TC_LAUNCH(SEL, L2V)                                                                                      \

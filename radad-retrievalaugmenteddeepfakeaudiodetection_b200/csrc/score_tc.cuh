@@ -49,6 +49,7 @@ struct TcParams {
   int nq, N, D;
   int nqt, S, tiles_per_chunk, ntiles, kout, num_units, nterms;
   uint32_t idesc;
+  uint64_t hint_q, hint_y;  // TMA L2 eviction-priority hints for the query / database operand
 };
 
 // value of element j (dynamic) of a register array, as a 31-select tree (keeps the array in registers)
@@ -191,8 +192,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = smem + stage * TC_STAGE_BYTES;
               mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-              tma_load_2d(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, kEvictLast);
-              tma_load_2d(sa + TC_A_BYTES, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK, t * TC_BN, kEvictNormal);
+              tma_load_2d(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
+              tma_load_2d(sa + TC_A_BYTES, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK, t * TC_BN, p.hint_y);
               if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             }
           }
