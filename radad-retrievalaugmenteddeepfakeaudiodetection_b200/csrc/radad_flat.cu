@@ -91,7 +91,7 @@ struct rdb_handle {
   std::mutex mu;
   // scratch
   DevBuf add_stage, q_stage, qf, qhi, qlo, qnorm, cand_key, cand_idx, o_dist, o_idx, o_lbl, ids_stage, rec_stage;
-  DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l, qs16, gthr;
+  DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l, qs16, gthr, tcsync;
   float* d_ynorm_max = nullptr;   // max |y|^2 over the shard (device scalar; feeds the re-rank certificate)
   int64_t last_uncertified = 0;
   bool has_master() const { return store == RDB_STORE_F32 || (flags & RDB_FLAG_KEEP_F32_MASTER); }
@@ -269,42 +269,85 @@ int encode_2d(rdb_handle* h, CUtensorMap* m, const void* base, int64_t rows, int
   return RDB_OK;
 }
 
-int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, int nqt, int S, int tiles_per_chunk,
+// CTAs per MMA group.  Both forms are built and parity-tested: cta_group::1 (one CTA = one 128-query tile, M = 128)
+// and cta_group::2 (a CTA pair runs M = 256 MMAs, each SM staging half of the database tile).  Measured on B200 at
+// the C3 size (profiles/r01_tc_cta_pair_ab.md) the kernel is POWER-bound: the pair form reaches a higher tensor-pipe
+// utilisation per clock (94 % vs 80 %) but the power cap then holds the SM clock lower (1.04 vs 1.38 GHz) and it
+// ends ~4-11 % slower, so the single-CTA form is the default.  RDB_TC_CG=2 selects the pair form.
+int tc_cta_group(int nq) {
+  const char* v = getenv("RDB_TC_CG");
+  return (v && atoi(v) == 2 && nq > TC_BM) ? 2 : 1;
+}
+
+template <class SEL, bool L2V, int CG>
+int launch_tc_kernel(rdb_handle* h, const TcParams& p, int groups) {
+  auto kern = score_select_tc_kernel<SEL, L2V, CG>;
+  CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<CG>()));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(groups * CG));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = tc_smem_bytes<CG>();
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(h, cudaLaunchKernelEx(&cfg, kern, p));
+  return RDB_OK;
+}
+
+template <int CG>
+int launch_tc_cg(rdb_handle* h, TcParams& p, int k) {
+  int rc;
+  if ((rc = encode_2d(h, &p.tmap_y[0], h->hi, h->n, h->d, h->dp, TC_BN / CG))) return rc;
+  if (p.nterms == 3) { if ((rc = encode_2d(h, &p.tmap_y[1], h->lo, h->n, h->d, h->dp, TC_BN / CG))) return rc; }
+  else p.tmap_y[1] = p.tmap_y[0];
+  p.idesc = make_idesc_f16(TC_BM * CG, TC_BN, h->f16() ? 0 : 1);
+  const int groups = std::min(p.num_units, h->num_sms / CG);
+  const bool l2 = h->metric == RDB_METRIC_L2;
+  if (k <= 16)      return l2 ? launch_tc_kernel<SelectSmall<16>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<16>, false, CG>(h, p, groups);
+  else if (k <= 32) return l2 ? launch_tc_kernel<SelectSmall<32>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<32>, false, CG>(h, p, groups);
+  return l2 ? launch_tc_kernel<SelectReservoir<kReservoirCap>, true, CG>(h, p, groups)
+            : launch_tc_kernel<SelectReservoir<kReservoirCap>, false, CG>(h, p, groups);
+}
+
+// nqg = query-tile GROUPS (128 * cg queries each); S chunks of tiles_per_chunk 256-row database tiles
+int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, int cg, int nqg, int S, int tiles_per_chunk,
               int ntiles, int nterms, float* ck, int* ci) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   int rc;
   if ((rc = encode_2d(h, &p.tmap_q[0], qhi, nq, h->d, h->dp, TC_BM))) return rc;
-  if ((rc = encode_2d(h, &p.tmap_y[0], h->hi, h->n, h->d, h->dp, TC_BN))) return rc;
-  if (nterms == 3) {
-    if ((rc = encode_2d(h, &p.tmap_q[1], qlo, nq, h->d, h->dp, TC_BM))) return rc;
-    if ((rc = encode_2d(h, &p.tmap_y[1], h->lo, h->n, h->d, h->dp, TC_BN))) return rc;
-  } else {
-    p.tmap_q[1] = p.tmap_q[0];
-    p.tmap_y[1] = p.tmap_y[0];
-  }
+  if (nterms == 3) { if ((rc = encode_2d(h, &p.tmap_q[1], qlo, nq, h->d, h->dp, TC_BM))) return rc; }
+  else p.tmap_q[1] = p.tmap_q[0];
   p.ynorm = h->ynorm; p.cand_key = ck; p.cand_idx = ci;
   CUDA_TRY(h, h->gthr.ensure(size_t(nq) * 4));
   CUDA_TRY(h, cudaMemsetAsync(h->gthr.p, 0, size_t(nq) * 4, h->stream));
   p.gthr = (S > 1 || TC_LISTS > 1) ? h->gthr.as<uint32_t>() : nullptr;
   p.nq = nq; p.N = int(h->n); p.D = h->d;
-  p.nqt = nqt; p.S = S; p.tiles_per_chunk = tiles_per_chunk; p.ntiles = ntiles; p.kout = k;
-  p.num_units = nqt * S; p.nterms = nterms;
-  p.idesc = make_idesc_f16(TC_BM, TC_BN, h->f16() ? 0 : 1);
+  p.nqt = nqg; p.S = S; p.tiles_per_chunk = tiles_per_chunk; p.ntiles = ntiles; p.kout = k;
+  p.num_units = nqg * S; p.nterms = nterms;
+  { const char* v = getenv("RDB_TC_DEBUG"); p.dbg = v ? atoi(v) : 0; }
   p.hint_q = l2_hint_from_env("RDB_TC_HINT_Q", kEvictLast);     // queries: re-read for every DB tile -> keep
   p.hint_y = l2_hint_from_env("RDB_TC_HINT_Y", kEvictNormal);   // database tiles: shared by the CTAs of a wave
-  const int grid = std::min(p.num_units, h->num_sms);
-  const bool l2 = h->metric == RDB_METRIC_L2;
-#define TC_LAUNCH(SEL, L2V)                                                                                      \
-  do {                                                                                                           \
-    auto kern = score_select_tc_kernel<SEL, L2V>;                                                                \
-    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes())); \
-    kern<<<dim3(grid), dim3(TC_THREADS), tc_smem_bytes(), h->stream>>>(p);                                       \
-  } while (0)
-  if (k <= 16)      { if (l2) TC_LAUNCH(SelectSmall<16>, true); else TC_LAUNCH(SelectSmall<16>, false); }
-  else if (k <= 32) { if (l2) TC_LAUNCH(SelectSmall<32>, true); else TC_LAUNCH(SelectSmall<32>, false); }
-  else              { if (l2) TC_LAUNCH(SelectReservoir<kReservoirCap>, true); else TC_LAUNCH(SelectReservoir<kReservoirCap>, false); }
-#undef TC_LAUNCH
+  // lock-step window of the TMA producers (score_tc.cuh): on when every slot of the persistent grid stays inside two
+  // chunks and units are long enough to drift; RDB_TC_LOCKSTEP=<window in groups of 8 tiles> (0 = off) overrides.
+  {
+    const int ngroups = std::min(p.num_units, h->num_sms / cg);
+    int window = 8;
+    if (const char* v = getenv("RDB_TC_LOCKSTEP")) window = atoi(v);
+    const int sync_groups = (tiles_per_chunk + TC_SYNC_GS - 1) / TC_SYNC_GS;
+    if (window > 0 && nqg >= ngroups && sync_groups > 2 * window) {
+      const size_t slots = size_t((p.num_units + ngroups - 1) / ngroups);
+      const size_t bytes = slots * 2 * size_t(sync_groups) * 4;
+      CUDA_TRY(h, h->tcsync.ensure(bytes));
+      CUDA_TRY(h, cudaMemsetAsync(h->tcsync.p, 0, bytes, h->stream));
+      p.sync = h->tcsync.as<uint32_t>(); p.sync_groups = sync_groups; p.sync_window = window;
+    }
+  }
+  rc = (cg == 2) ? launch_tc_cg<2>(h, p, k) : launch_tc_cg<1>(h, p, k);
+  if (rc) return rc;
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return RDB_OK;
@@ -368,12 +411,14 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
   cudaStream_t s = h->stream;
   if (algo == RDB_ALGO_TC) {
     const int ntiles = int((h->n + TC_BN - 1) / TC_BN);
+    const int cg = tc_cta_group(qv.nq);
+    const int nqg = (qv.nq + TC_BM * cg - 1) / (TC_BM * cg);
     // large k: per-unit selection overhead (reservoir warm-up, final sort) is worth ~64 tiles -> fewer, longer units
-    S = choose_splits(nqt, ntiles, h->num_sms, 256 / TC_LISTS, kc > 32 ? 64 : 4, &tpc, kc > 32 ? 64.0 : 2.0);
+    S = choose_splits(nqg, ntiles, h->num_sms / cg, 256 / TC_LISTS, kc > 32 ? 64 : 4, &tpc, kc > 32 ? 64.0 : 2.0);
     CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * TC_LISTS * kc * 4));
     CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * TC_LISTS * kc * 4));
     if (timed) cudaEventRecord(h->ev0, s);
-    if ((rc = launch_tc(h, qv.qhi, qv.qlo, qv.nq, kc, nqt, S, tpc, ntiles, nterms, h->cand_key.as<float>(),
+    if ((rc = launch_tc(h, qv.qhi, qv.qlo, qv.nq, kc, cg, nqg, S, tpc, ntiles, nterms, h->cand_key.as<float>(),
                         h->cand_idx.as<int>()))) return rc;
     if (timed) cudaEventRecord(h->ev1, s);
     *L_out = S * TC_LISTS;
@@ -631,7 +676,7 @@ int rdb_destroy(rdb_handle* h) {
     cudaFree(h->d_ynorm_max);
     for (DevBuf* b : {&h->add_stage, &h->q_stage, &h->qf, &h->qhi, &h->qlo, &h->qnorm, &h->cand_key, &h->cand_idx,
                       &h->o_dist, &h->o_idx, &h->o_lbl, &h->ids_stage, &h->rec_stage, &h->rr_key, &h->rr_idx,
-                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l, &h->qs16, &h->gthr})
+                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l, &h->qs16, &h->gthr, &h->tcsync})
       b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

@@ -29,28 +29,59 @@ namespace rdb {
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 256;
 constexpr int TC_BK = 64;
-constexpr int TC_STAGES = 4;
+// CG = CTAs per MMA (tcgen05 cta_group): 1 = one CTA owns a 128-query tile and stages whole 256-row DB tiles;
+// 2 = a CTA pair (the two SMs of a TPC) runs M = 256 MMAs: each CTA stages its own 128 queries plus HALF of the DB
+// tile (the tensor cores read the other half from the peer SM), i.e. 32 KB instead of 48 KB per K-slice per SM:
+// a third less L2->SM operand traffic and a 6-deep instead of 4-deep ring in the same shared memory.
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
-constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+template <int CG> struct TcCfg {
+  static constexpr int STAGES = (CG == 2) ? 6 : 4;
+  static constexpr int B_ROWS = TC_BN / CG;
+  static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + 256 + 1024;
+};
 constexpr int TC_EPI_WARPS = 8;        // two per TMEM lane quarter: each takes one half of the 256 columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_LISTS = 2;            // candidate lists per (query, chunk): one per column half
 constexpr int TC_TMEM_COLS = 512;
-constexpr size_t tc_smem_bytes() { return size_t(TC_STAGES) * TC_STAGE_BYTES + 256 + 1024; }
+template <int CG> constexpr size_t tc_smem_bytes() { return TcCfg<CG>::SMEM; }
 
 struct TcParams {
   CUtensorMap tmap_q[2];  // [0] = hi, [1] = lo   bf16/f16 [nq, D], box {64, 128}, SWIZZLE_128B
-  CUtensorMap tmap_y[2];  // [0] = hi, [1] = lo   bf16/f16 [N,  D], box {64, 256}, SWIZZLE_128B
+  CUtensorMap tmap_y[2];  // [0] = hi, [1] = lo   bf16/f16 [N,  D], box {64, 256 / CG}, SWIZZLE_128B
   const float* ynorm;     // [N] |y|^2 (L2 only)
   float* cand_key;        // [nq][S * TC_LISTS][kout]
   int* cand_idx;          // [nq][S * TC_LISTS][kout]  local row ids, -1 = empty
   uint32_t* gthr;         // [nq] shared lower bound of the global k-th best key (ordered uint, 0 = none), or null
   int nq, N, D;
-  int nqt, S, tiles_per_chunk, ntiles, kout, num_units, nterms;
+  int nqt /* query-tile groups of 128 * CG queries */, S, tiles_per_chunk, ntiles, kout, num_units, nterms;
   uint32_t idesc;
+  int dbg;                  // profiling only (RDB_TC_DEBUG): 1 = skip the selection work (results invalid)
   uint64_t hint_q, hint_y;  // TMA L2 eviction-priority hints for the query / database operand
+  // Lock-step window (see tc_lockstep_* below): progress counters [slot][2][sync_groups], or null = off
+  uint32_t* sync;
+  int sync_groups, sync_window;
 };
+
+// ---- lock-step window ----------------------------------------------------------------------------------------------
+// The CTAs that run the same DB chunk in the same scheduling slot (the j-th unit of every CTA) stream the SAME tiles
+// against different query tiles; one HBM fetch serves all of them only while they stay within an L2-sized window of
+// each other.  Left alone they drift apart (ncu, C3: 19.5 database volumes of DRAM reads per launch instead of the
+// 3.5 the schedule needs).  The TMA producers therefore keep a sliding window: a producer bumps counter[g] after
+// issuing group g (TC_SYNC_GS tiles) and does not start group g + W before all members of its (slot, chunk) bumped
+// counter[g].  It is a performance hint only -- relaxed atomics, the counter for the next check is prefetched one
+// group ahead (no stall for CTAs that are not ahead), and the wait is bounded (a member that is not resident, e.g.
+// on a GPU shared with another kernel, cannot deadlock the others: the waiter gives up lock-step for that unit).
+constexpr int TC_SYNC_GS = 8;
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_u32(uint32_t* p) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
 
 // value of element j (dynamic) of a register array, as a 31-select tree (keeps the array in registers)
 __device__ __forceinline__ float sel32(const float (&v)[32], int j) {
@@ -145,31 +176,41 @@ __device__ __forceinline__ void tc_process32(uint32_t (&r)[32], Sel& sel, const 
   sel.end_group(32);
 }
 
-template <class Sel, bool L2>
+template <class Sel, bool L2, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<CG>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + TC_STAGES;
-  uint64_t* tfull_bar = empty_bar + TC_STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CG == 2: the two CTAs of a cluster form one MMA group; `group` walks the work units, `rank` picks the query
+  // tile (A half) and the database half (B half) this CTA stages.  Rank 0 is the leader (issues MMA, owns full_bar).
+  const int rank = (CG == 2) ? int(cluster_ctarank()) : 0;
+  const int group = int(blockIdx.x) / CG;
+  const int ngroups = int(gridDim.x) / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_q[0]);
     tma_prefetch_desc(&p.tmap_y[0]);
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS * CG); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_ptr);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_pair<TC_TMEM_COLS>(tmem_ptr);
+    else tmem_alloc<TC_TMEM_COLS>(tmem_ptr);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -180,32 +221,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-        const int qtile = unit % p.nqt, chunk = unit / p.nqt;
+      int slot = 0;
+      for (int unit = group; unit < p.num_units; unit += ngroups, ++slot) {
+        const int qtile = (unit % p.nqt) * CG + rank, chunk = unit / p.nqt;
         const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
+        // lock-step window: members = units of this slot that run this chunk (host enables it only when nqt >= ngroups,
+        // so a slot touches at most two chunks)
+        const int u_lo = max(slot * ngroups, chunk * p.nqt);
+        const int u_hi = min(min((slot + 1) * ngroups, (chunk + 1) * p.nqt), p.num_units);
+        const uint32_t members = uint32_t(u_hi - u_lo);
+        const bool counted = p.sync != nullptr && rank == 0 && members > 1;
+        bool waiting = counted;
+        uint32_t* ctr = p.sync + (size_t(slot) * 2 + size_t(chunk - (slot * ngroups) / p.nqt)) * p.sync_groups;
+        uint32_t seen = 0;
         for (int t = t0; t < t1; ++t) {
+          if (counted) {
+            const int tau = t - t0, g = tau / TC_SYNC_GS;
+            if (tau % TC_SYNC_GS == 0) {
+              if (waiting && g >= p.sync_window && seen < members) {
+                int spins = 0;
+                while ((seen = ld_relaxed_u32(ctr + g - p.sync_window)) < members) {
+                  if (++spins > 256) { waiting = false; break; }
+                  __nanosleep(200);
+                }
+              }
+              if (g + 1 >= p.sync_window) seen = ld_relaxed_u32(ctr + g + 1 - p.sync_window);   // for the next check
+            }
+          }
           for (int term = 0; term < p.nterms; ++term) {
             // nterms == 1: (hi, hi).  nterms == 3: (lo, hi), (hi, lo), (hi, hi) -- small terms first.
             const int qsel = (p.nterms == 3 && term == 0) ? 1 : 0;
             const int ysel = (p.nterms == 3 && term == 1) ? 1 : 0;
             for (int ks = 0; ks < nks; ++ks) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* sa = smem + stage * TC_STAGE_BYTES;
-              mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-              tma_load_2d(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
-              tma_load_2d(sa + TC_A_BYTES, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK, t * TC_BN, p.hint_y);
-              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              if (CG == 2) {
+                // both CTAs' bytes complete on the leader's barrier; the leader posts the expectation for both
+                if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                tma_load_2d_pair(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
+                tma_load_2d_pair(sa + TC_A_BYTES, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK,
+                                 t * TC_BN + rank * Cfg::B_ROWS, p.hint_y);
+              } else {
+                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                tma_load_2d(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
+                tma_load_2d(sa + TC_A_BYTES, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK, t * TC_BN, p.hint_y);
+              }
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
+          if (counted && (t - t0) % TC_SYNC_GS == TC_SYNC_GS - 1) red_add_u32(ctr + (t - t0) / TC_SYNC_GS);
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (single thread; leader CTA only)
+    if (lane == 0 && rank == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      for (int unit = group; unit < p.num_units; unit += ngroups) {
         const int chunk = unit / p.nqt;
         const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
         for (int t = t0; t < t1; ++t) {
@@ -216,18 +289,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
           for (int ks = 0; ks < nslices; ++ks) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
             const uint64_t da = make_sw128_kmajor_desc(sa);
             const uint64_t db = make_sw128_kmajor_desc(sa + TC_A_BYTES);
 #pragma unroll
             for (int kk = 0; kk < TC_BK / 16; ++kk) {
               // +32 bytes per K=16 step inside the 128-byte swizzle atom (descriptor address unit = 16 B)
-              umma_f16_ss(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), p.idesc, (ks | kk) != 0);
+              if (CG == 2) umma_f16_ss_pair(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), p.idesc, (ks | kk) != 0);
+              else umma_f16_ss(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), p.idesc, (ks | kk) != 0);
             }
-            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+            if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+          // accumulator complete -> epilogue (of both CTAs of a pair)
+          if (CG == 2) umma_commit_pair(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
@@ -240,8 +316,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
     const int row = ew * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-      const int qtile = unit % p.nqt, chunk = unit / p.nqt;
+    for (int unit = group; unit < p.num_units; unit += ngroups) {
+      const int qtile = (unit % p.nqt) * CG + rank, chunk = unit / p.nqt;
       const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
       const long long q = (long long)qtile * TC_BM + row;
       Sel sel;
@@ -252,6 +328,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
         const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * TC_BN + half * (TC_BN / 2));
         const int n0 = t * TC_BN + half * (TC_BN / 2);
         const int nvalid = p.N - n0;         // >= 128 for full tiles
+        if (p.dbg & 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+          continue;
+        }
         uint32_t ra[32], rb[32];
         float4 ya[8], yb[8];
         if (L2) tc_load_yn(ya, p.ynorm, n0);
@@ -269,7 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
             // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
           }
           tc_process32<Sel, L2>(rb, sel, yb, n0 + (c + 1) * 32, nvalid - (c + 1) * 32);
         }
@@ -284,8 +368,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: the peer's smem/TMEM/barriers stay alive until both are done
+  if (warp == 1) {
+    if (CG == 2) tmem_dealloc_pair<TC_TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+  }
 }
 
 }  // namespace rdb

@@ -195,6 +195,37 @@ def test_lattice_bit_exact_large_k(pkg, oracle, metric_s, k):
     np.testing.assert_array_equal(D, Dr)
 
 
+@pytest.mark.parametrize("store", ["bf16", "f32"])
+@pytest.mark.parametrize("metric_s", ["L2", "IP"])
+@pytest.mark.parametrize("k", [10, 24, 100])
+def test_cta_pair_kernel_bit_exact(pkg, oracle, monkeypatch, metric_s, k, store):
+    """The cta_group::2 form of the tensor-core scorer (a CTA pair runs M = 256 MMAs, RDB_TC_CG=2): lattice data, ragged
+    query count (an odd number of 128-query tiles, last tile partly empty) and ragged N -- ids and distances must equal
+    the oracle bit-for-bit, and the single-CTA form must agree."""
+    if store == "f32" and k > 24:
+        pytest.skip("split-precision path serves k <= 24")
+    rng = np.random.default_rng(11)
+    N, Dm, nq = 7013, 200, 300
+    xb = rng.integers(-2, 3, size=(N, Dm)).astype(np.float32)
+    xb[4000:4150] = xb[5]
+    xq = rng.integers(-2, 3, size=(nq, Dm)).astype(np.float32)
+    xq[299] = xb[5]
+    metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
+    idx = pkg.FlatIndex(Dm, metric, store)
+    idx.add(xb)
+    ref = oracle.FlatIndexOracle(Dm, metric)
+    ref.add(xb)
+    Dr, Ir = ref.search(xq, k, direct=False)
+    monkeypatch.setenv("RDB_TC_CG", "2")
+    D2, I2 = idx.search(xq, k, algo="tc")
+    monkeypatch.setenv("RDB_TC_CG", "1")
+    D1, I1 = idx.search(xq, k, algo="tc")
+    np.testing.assert_array_equal(I2, Ir)
+    np.testing.assert_array_equal(D2, Dr)
+    np.testing.assert_array_equal(I1, Ir)
+    np.testing.assert_array_equal(D1, Dr)
+
+
 @pytest.mark.parametrize("name", ["lattice_l2", "lattice_ip"])
 def test_lattice_bit_exact_f32_split(pkg, name):
     """fp32 store, tensor-core split path: lattice values have lo == 0, all three MMA terms are exact."""
