@@ -110,6 +110,12 @@ int rdb_merge_shards_peer(rdb_handle* h, const void* const* key_ptrs, const void
                           const void* const* lbl_ptrs, int nlists, int64_t nq, int k, const float* qnorm,
                           float* out_dist, int64_t* out_idx, float* out_labels);
 
+/* Single-process multi-GPU (one host thread drives every shard, as pipeline.py:90 constructs ONE VectorDatabase):
+ * let kernels of this handle's device dereference memory of `peer_device` (cudaDeviceEnablePeerAccess; already
+ * enabled / same device = success), so rdb_merge_shards_peer can take plain pointers of the other shards' buffers.
+ * No reference counterpart. */
+int rdb_enable_peer_access(rdb_handle* h, int peer_device);
+
 /* Replaces index.reconstruct(i) -- pipeline.py:503.  `out` is a HOST float32[d]. */
 int rdb_reconstruct(rdb_handle* h, int64_t id, float* out);
 

@@ -996,6 +996,21 @@ int rdb_mem_info(rdb_handle* h, size_t* index_bytes, size_t* free_bytes, size_t*
 //      i64 dummy, i64 dummy, u8 is_trained, i32 metric_type (0 = IP, 1 = L2), u64 count (= ntotal * d floats), data.
 static uint32_t fourcc(const char* s) { return uint32_t(uint8_t(s[0])) | uint32_t(uint8_t(s[1])) << 8 | uint32_t(uint8_t(s[2])) << 16 | uint32_t(uint8_t(s[3])) << 24; }
 
+int rdb_enable_peer_access(rdb_handle* h, int peer_device) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (peer_device == h->device) return RDB_OK;
+  DeviceGuard dg(h->device);
+  int can = 0;
+  CUDA_TRY(h, cudaDeviceCanAccessPeer(&can, h->device, peer_device));
+  if (!can) return fail(h, RDB_ERR_UNSUPPORTED, "device " + std::to_string(h->device) + " cannot access device " +
+                                                    std::to_string(peer_device) + " (no NVLink/PCIe peer path)");
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+  CUDA_TRY(h, e);
+  return RDB_OK;
+}
+
 int rdb_serialize(rdb_handle* h, const char* path) {
   if (!h || !path) return fail(h, RDB_ERR_INVALID, "serialize: bad arguments");
   std::lock_guard<std::mutex> lock(h->mu);

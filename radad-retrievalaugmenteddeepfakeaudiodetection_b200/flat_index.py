@@ -258,6 +258,10 @@ class FlatIndex:
                                                     ctypes.c_void_p(I.data_ptr()), ctypes.c_void_p(L.data_ptr())))
         return D, I, L
 
+    def enable_peer_access(self, peer_device: int) -> None:
+        """Let this index's kernels read device memory of ``peer_device`` (single-process multi-GPU merge)."""
+        self._check(self._lib.rdb_enable_peer_access(self._h, int(peer_device)))
+
     def filter_first_k(self, idx, dist, lab, row_codes, excl_sorted, K: int):
         """Device-side rank-ordered exclusion + first-K compaction (pipeline.py:491-520); torch CUDA in/out."""
         import torch

@@ -1,0 +1,358 @@
+"""``MultiGpuFlatIndex`` -- one process, one host thread, G GPUs: the row-sharded index behind a single
+``VectorDatabase``.
+
+The reference constructs ONE ``VectorDatabase`` in ONE process (``pipeline.py:90``) and is single-GPU
+(``vector_database.py:23``).  ``ShardedFlatIndex`` (sharded.py) scales the search out with one process per GPU under
+``torchrun``; this class gives the same row-sharded search to an unmodified single-process caller: it has the faiss
+flat-index duck type of ``FlatIndex`` (``add / search / reconstruct / ntotal / d / is_trained / train / nprobe``), so
+``VectorDatabase`` and ``retrieve_similar_vectors`` work on top of it unchanged.
+
+  add      every call is water-filled over the shards in contiguous pieces (global id = insertion order, exactly as
+           faiss); each shard remembers its pieces as (local start, global start, count) segments.
+  search   queries are copied to every GPU (P2P over NVLink), each GPU runs the fused score+select kernels on its own
+           stream concurrently, local ids are mapped to global ids on the device, and ONE kernel on the primary GPU
+           merges the G candidate lists while loading list g straight from GPU g's memory (P2P loads; the same fused
+           gather+merge kernel the torchrun path uses) -- no all-gather, no host round trip.
+  save     the faiss IndexFlat file layout with the rows in global id order (what ``FlatIndex.save`` writes), so a
+           database written by G GPUs loads on one GPU and vice versa.
+
+All arithmetic runs in ``libradad_flat.so``; torch is plumbing (device tensors, streams, events).  No CPU fallback.
+"""
+from __future__ import annotations
+
+import bisect
+import struct
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._cabi import ALGO_AUTO, METRIC_IP, METRIC_L2
+from .flat_index import FlatIndex, _is_cuda_tensor
+
+_MIN_SPLIT_ROWS = 4096          # smaller add() calls go whole to the least-loaded shard (fewer segments)
+
+
+class MultiGpuFlatIndex:
+    """Exact flat search over a database row-sharded across the GPUs of one box, driven by one process."""
+
+    is_trained = True
+
+    def __init__(self, d: int, metric: int = METRIC_L2, store="f32", devices: Optional[Sequence[int]] = None,
+                 keep_f32_master: bool = False):
+        import torch
+        if devices is None or (isinstance(devices, str) and devices == "all"):
+            devices = list(range(torch.cuda.device_count()))
+        self.devices = [int(v) for v in devices]
+        if not self.devices:
+            raise RuntimeError("MultiGpuFlatIndex needs at least one CUDA device (no CPU fallback)")
+        self._d, self._metric = int(d), int(metric)
+        self.shards: List[FlatIndex] = [FlatIndex(d, metric, store, device=g, keep_f32_master=keep_f32_master)
+                                        for g in self.devices]
+        for g in self.devices[1:]:
+            self.shards[0].enable_peer_access(g)        # the merge kernel on the primary reads every shard's lists
+        self.nprobe = 1
+        self._ntotal = 0
+        # per shard: parallel lists of segment (local_start, global_start, count), ascending in both
+        self._seg: List[List[Tuple[int, int, int]]] = [[] for _ in self.devices]
+        self._seg_dev = [None] * len(self.devices)      # device copies (local_starts, deltas), rebuilt lazily
+        self._glob = None                               # global routing table (starts, shard, delta), rebuilt lazily
+
+    # ------------------------------------------------------------------ properties (FlatIndex duck type)
+    @property
+    def ntotal(self) -> int:
+        return self._ntotal
+
+    @property
+    def d(self) -> int:
+        return self._d
+
+    @property
+    def metric(self) -> int:
+        return self._metric
+
+    @property
+    def metric_type(self) -> int:
+        return 0 if self._metric == METRIC_IP else 1
+
+    @property
+    def store(self) -> str:
+        return self.shards[0].store
+
+    @property
+    def launch_count(self) -> int:
+        return sum(s.launch_count for s in self.shards)
+
+    @property
+    def last_uncertified(self) -> int:
+        return sum(s.last_uncertified for s in self.shards)
+
+    @property
+    def shard_sizes(self) -> List[int]:
+        return [s.ntotal for s in self.shards]
+
+    def train(self, x) -> None:
+        return None
+
+    def reserve(self, n_total: int) -> None:
+        per = -(-int(n_total) // len(self.shards))
+        for s in self.shards:
+            s.reserve(max(per, 1))
+
+    # ------------------------------------------------------------------ ingest
+    def _plan(self, n: int) -> List[Tuple[int, int]]:
+        """Water-filling: how many rows of an n-row add() go to each shard, as (shard, count) in shard order."""
+        sizes = self.shard_sizes
+        if n < _MIN_SPLIT_ROWS:
+            return [(int(np.argmin(sizes)), n)]
+        target = -(-(sum(sizes) + n) // len(sizes))
+        plan, left = [], n
+        for g, sz in enumerate(sizes):
+            take = min(left, max(0, target - sz))
+            if take:
+                plan.append((g, take))
+                left -= take
+        if left:                                        # rounding leftovers
+            plan.append((int(np.argmin(sizes)), left))
+        return plan
+
+    def add(self, x, normalize: bool = False) -> None:
+        """index.add(x) (vector_database.py:138): rows get global ids ntotal .. ntotal + n - 1."""
+        import torch
+        n = int(x.shape[0])
+        if x.ndim != 2 or int(x.shape[1]) != self._d:
+            raise RuntimeError(f"expected float32 [n, {self._d}], got {tuple(x.shape)}")
+        r0 = 0
+        for g, cnt in self._plan(n):
+            piece = x[r0:r0 + cnt]
+            shard = self.shards[g]
+            if _is_cuda_tensor(piece):
+                with torch.cuda.device(self.devices[g]):
+                    shard.add(piece.to(torch.device("cuda", self.devices[g]), non_blocking=True), normalize=normalize)
+            else:
+                shard.add(piece, normalize=normalize)
+            local0 = shard.ntotal - cnt
+            seg = self._seg[g]
+            if seg and seg[-1][0] + seg[-1][2] == local0 and seg[-1][1] + seg[-1][2] == self._ntotal + r0:
+                seg[-1] = (seg[-1][0], seg[-1][1], seg[-1][2] + cnt)
+            else:
+                seg.append((local0, self._ntotal + r0, cnt))
+            self._seg_dev[g] = None
+            r0 += cnt
+        self._ntotal += n
+        self._glob = None
+
+    def set_labels(self, labels) -> None:
+        lab = np.ascontiguousarray(labels, dtype=np.float32).reshape(-1)
+        if lab.size != self._ntotal:
+            raise RuntimeError(f"set_labels: {lab.size} labels for {self._ntotal} rows")
+        for g, shard in enumerate(self.shards):
+            if shard.ntotal:
+                shard.set_labels(np.concatenate([lab[gs:gs + c] for (_, gs, c) in self._seg[g]]))
+
+    # ------------------------------------------------------------------ id maps
+    def _local_to_global(self, g: int, local_ids):
+        """int64 local row ids (device tensor on shard g's GPU; -1 = empty slot) -> global ids."""
+        import torch
+        seg = self._seg[g]
+        if len(seg) == 1:
+            return torch.where(local_ids >= 0, local_ids + (seg[0][1] - seg[0][0]), local_ids)
+        if self._seg_dev[g] is None:
+            dev = local_ids.device
+            self._seg_dev[g] = (torch.tensor([s[0] for s in seg], dtype=torch.int64, device=dev),
+                                torch.tensor([s[1] - s[0] for s in seg], dtype=torch.int64, device=dev))
+        starts, deltas = self._seg_dev[g]
+        which = torch.bucketize(local_ids.clamp_min(0), starts, right=True) - 1
+        return torch.where(local_ids >= 0, local_ids + deltas[which], local_ids)
+
+    def _routing(self):
+        if self._glob is None:
+            rows = sorted((gs, g, ls - gs, c) for g, seg in enumerate(self._seg) for (ls, gs, c) in seg)
+            self._glob = ([r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows], [r[3] for r in rows], {})
+        return self._glob
+
+    def _locate(self, gid: int) -> Tuple[int, int]:
+        starts, shard, delta, cnt, _ = self._routing()
+        j = bisect.bisect_right(starts, gid) - 1
+        if gid < 0 or j < 0 or gid >= starts[j] + cnt[j]:
+            raise RuntimeError(f"reconstruct: id {gid} out of range [0, {self._ntotal})")
+        return shard[j], gid + delta[j]
+
+    # ------------------------------------------------------------------ search
+    def search(self, q, k: int, normalize: bool = False, algo=ALGO_AUTO, return_labels: bool = False):
+        """index.search(q, k) -> (distances float32[nq,k], ids int64[nq,k]) best-first (vector_database.py:181);
+        numpy in -> numpy out, torch CUDA in -> torch CUDA out (on the queries' device)."""
+        import torch
+        k = int(k)
+        cuda_in = _is_cuda_tensor(q)
+        prim = torch.device("cuda", self.devices[0])
+        if cuda_in:
+            out_dev = q.device
+            qp = q.detach().to(prim, torch.float32, non_blocking=True).contiguous()
+        else:
+            qh = np.ascontiguousarray(q, dtype=np.float32)
+            if qh.ndim != 2 or qh.shape[1] != self._d:
+                raise RuntimeError(f"expected float32 [nq, {self._d}], got {qh.shape}")
+            qp = torch.from_numpy(qh).to(prim, non_blocking=True)
+        if qp.dim() != 2 or qp.shape[1] != self._d:
+            raise RuntimeError(f"expected float32 [nq, {self._d}], got {tuple(qp.shape)}")
+        nq = qp.shape[0]
+        live = [g for g, s in enumerate(self.shards) if s.ntotal > 0]
+        if not live:
+            raise RuntimeError("search on an empty index")
+        # 1) broadcast the queries first: torch runs a cross-device copy on the SOURCE device's stream, so a copy issued
+        #    after the primary's own search had been enqueued would wait for it and serialise the GPUs
+        qs = {}
+        for g in live:
+            dev = torch.device("cuda", self.devices[g])
+            qs[g] = qp if dev == prim else qp.to(dev, non_blocking=True)        # P2P over NVLink
+        # 2) every GPU searches its shard concurrently (asynchronous launches on each device's current stream)
+        keys, gids, labs, events, qn_first = [], [], [], [], None
+        for g in live:
+            with torch.cuda.device(self.devices[g]):
+                key, lid, lab, qn = self.shards[g].search_shard(qs[g], k, normalize=normalize)
+                gid = self._local_to_global(g, lid)
+                ev = torch.cuda.Event()
+                ev.record()
+            keys.append(key); gids.append(gid); labs.append(lab); events.append(ev)
+            if qn_first is None:
+                qn_first = qn
+        with torch.cuda.device(prim):
+            ps = torch.cuda.current_stream()
+            for ev in events:
+                ps.wait_event(ev)
+            for t in keys + gids + labs:
+                t.record_stream(ps)                 # read by the merge kernel on the primary's stream
+            qn0 = qn_first if qn_first.device == prim else qn_first.to(prim, non_blocking=True)
+            # ONE kernel: list g is loaded straight from GPU g's memory (P2P over NVLink) while merging
+            D, I, L = self.shards[0].merge_shards_peer([t.data_ptr() for t in keys], [t.data_ptr() for t in gids],
+                                                       [t.data_ptr() for t in labs], nq, k, qn0)
+        if cuda_in:
+            D, I, L = D.to(out_dev), I.to(out_dev), L.to(out_dev)
+            return (D, I, L) if return_labels else (D, I)
+        Dn, In, Ln = D.cpu().numpy(), I.cpu().numpy(), L.cpu().numpy()
+        return (Dn, In, Ln) if return_labels else (Dn, In)
+
+    # ------------------------------------------------------------------ reconstruct
+    def reconstruct(self, i: int) -> np.ndarray:
+        g, local = self._locate(int(i))
+        return self.shards[g].reconstruct(local)
+
+    def reconstruct_batch(self, ids):
+        """Rows ``ids`` (global); ids < 0 / out of range give zero rows (pipeline.py:511-512)."""
+        import torch
+        cuda_in = _is_cuda_tensor(ids)
+        prim = torch.device("cuda", self.devices[0])
+        t = ids.detach().to(torch.int64) if cuda_in else torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64))
+        shape = tuple(t.shape)
+        out_dev = t.device if cuda_in else None
+        t = t.reshape(-1).to(prim)
+        starts, shard, delta, cnt, cache = self._routing()
+        if "dev" not in cache:
+            mk = lambda v: torch.tensor(v, dtype=torch.int64, device=prim)     # noqa: E731
+            cache["dev"] = (mk(starts), mk(shard), mk(delta), mk(cnt))
+        st, sh, de, cn = cache["dev"]
+        j = (torch.bucketize(t.clamp_min(0), st, right=True) - 1).clamp_min(0)
+        valid = (t >= 0) & (t < st[j] + cn[j])
+        which = torch.where(valid, sh[j], torch.full_like(t, -1))
+        local = t + de[j]
+        out = torch.zeros((t.numel(), self._d), dtype=torch.float32, device=prim)
+        for g, s in enumerate(self.shards):
+            if s.ntotal == 0:
+                continue
+            dev = torch.device("cuda", self.devices[g])
+            lg = torch.where(which == g, local, torch.full_like(local, -1))
+            with torch.cuda.device(dev):
+                rows = s.reconstruct_batch(lg.to(dev, non_blocking=True))      # zero rows where lg == -1
+            out += rows.to(prim, non_blocking=True)
+        out = out.reshape(shape + (self._d,))
+        if cuda_in:
+            return out.to(out_dev)
+        return out.cpu().numpy()
+
+    # ------------------------------------------------------------------ pass-throughs (elementwise on given tensors)
+    def filter_first_k(self, idx, dist, lab, row_codes, excl_sorted, K: int):
+        import torch
+        with torch.cuda.device(idx.device):
+            own = [s for g, s in enumerate(self.shards) if self.devices[g] == idx.device.index]
+            return (own[0] if own else self.shards[0]).filter_first_k(idx, dist, lab, row_codes, excl_sorted, K)
+
+    def label_vote(self, labels_nq_k, kvote: int):
+        return self.shards[0].label_vote(labels_nq_k, kvote)
+
+    def sync(self) -> None:
+        for s in self.shards:
+            s.sync()
+
+    def last_kernel_ms(self):
+        r = [s.last_kernel_ms() for s in self.shards if s.ntotal]
+        return max(v[0] for v in r), r[0][1], r[0][2]
+
+    def mem_info(self):
+        infos = [s.mem_info() for s in self.shards]
+        return {"index_bytes": sum(i["index_bytes"] for i in infos), "free": sum(i["free"] for i in infos),
+                "total": sum(i["total"] for i in infos), "per_device": infos}
+
+    # ------------------------------------------------------------------ persistence (faiss IndexFlat layout)
+    def save(self, path: str) -> None:
+        """fourcc IxF2 / IxFI, d, ntotal, 2 dummies, is_trained, metric, count, fp32 rows in GLOBAL id order."""
+        cc = b"IxFI" if self._metric == METRIC_IP else b"IxF2"
+        with open(path, "wb") as f:
+            f.write(cc + struct.pack("<iqqqBiQ", self._d, self._ntotal, 1 << 20, 1 << 20, 1, self.metric_type,
+                                     self._ntotal * self._d))
+            chunk = max(1, (64 << 20) // (self._d * 4))
+            for r0 in range(0, self._ntotal, chunk):
+                ids = np.arange(r0, min(self._ntotal, r0 + chunk), dtype=np.int64)
+                f.write(np.ascontiguousarray(self.reconstruct_batch(ids), dtype="<f4").tobytes())
+
+    @classmethod
+    def load(cls, path: str, store="f32", devices: Optional[Sequence[int]] = None, keep_f32_master: bool = False):
+        with open(path, "rb") as f:
+            head = f.read(37)
+            if len(head) < 37 or head[:4] not in (b"IxF2", b"IxFI", b"IxFl"):
+                raise RuntimeError(f"deserialize: {path} is not a faiss IndexFlat file")
+            d, n, _, _, _, mt = struct.unpack("<iqqqBi", head[4:37])
+            if mt > 1:
+                f.read(4)                                   # metric_arg
+            (count,) = struct.unpack("<Q", f.read(8))
+            if d < 1 or n < 0 or count != n * d or mt not in (0, 1):
+                raise RuntimeError(f"deserialize: {path} is not a faiss IndexFlat (L2 / IP) file")
+            idx = cls(d, METRIC_IP if mt == 0 else METRIC_L2, store, devices, keep_f32_master)
+            idx.reserve(n)
+            per = -(-n // len(idx.shards)) if n else 0
+            r0 = 0
+            while r0 < n:                                   # shard-sized pieces: one segment per shard
+                m = min(per, n - r0)
+                step = max(1, (64 << 20) // (d * 4))
+                g = int(np.argmin(idx.shard_sizes)) if idx._ntotal else 0
+                for c0 in range(0, m, step):
+                    c = min(step, m - c0)
+                    rows = np.frombuffer(f.read(c * d * 4), dtype="<f4")
+                    if rows.size != c * d:
+                        raise RuntimeError(f"deserialize: {path} is truncated")
+                    idx._add_to_shard(g, rows.reshape(c, d))
+                r0 += m
+        return idx
+
+    def _add_to_shard(self, g: int, rows: np.ndarray) -> None:
+        shard, cnt = self.shards[g], rows.shape[0]
+        shard.add(rows)
+        local0 = shard.ntotal - cnt
+        seg = self._seg[g]
+        if seg and seg[-1][0] + seg[-1][2] == local0 and seg[-1][1] + seg[-1][2] == self._ntotal:
+            seg[-1] = (seg[-1][0], seg[-1][1], seg[-1][2] + cnt)
+        else:
+            seg.append((local0, self._ntotal, cnt))
+        self._seg_dev[g] = None
+        self._ntotal += cnt
+        self._glob = None
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        for s in self.shards:
+            s.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass

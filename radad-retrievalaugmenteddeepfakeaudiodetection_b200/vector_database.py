@@ -15,7 +15,8 @@ Config keys read (all via ``getattr`` so an unmodified reference ``Config`` work
 ``vector_db_path``, ``vector_db_index_type`` (L2 | IP | IVF), ``use_float16``, ``normalize_for_ip``,
 ``vector_add_batch_size``, ``top_k``, ``vector_db_nprobe``.  New optional keys: ``db_dtype``
 ("f32" | "bf16" | "f16"; default f32, or f16 when ``use_float16``), ``db_keep_f32_master`` (bool),
-``db_device`` (int), ``restore_cosine_on_load`` (bool, opt-in fix of the ``load()`` quirk).
+``db_device`` (int), ``db_devices`` (list of ints or "all": row-shard the database over several GPUs of the box from
+this one process -- ``MultiGpuFlatIndex``), ``restore_cosine_on_load`` (bool, opt-in fix of the ``load()`` quirk).
 """
 from __future__ import annotations
 
@@ -28,6 +29,7 @@ import numpy as np
 
 from . import _cabi
 from .flat_index import FlatIndex, _is_cuda_tensor
+from .multi_gpu import MultiGpuFlatIndex
 from ._cabi import METRIC_IP, METRIC_L2
 
 
@@ -63,6 +65,14 @@ class VectorDatabase:
             except Exception:  # noqa: BLE001
                 dev = None
         self.device_id = int(dev) if dev is not None else 0
+        self._devices = None
+        devs = getattr(self.config, "db_devices", None)
+        if devs is not None:
+            if isinstance(devs, str):
+                import torch
+                devs = list(range(torch.cuda.device_count())) if devs == "all" else [int(v) for v in devs.split(",")]
+            self._devices = [int(v) for v in devs]
+            self.device_id = self._devices[0]
         # probe the device through the library itself (torch is plumbing, not a requirement)
         probe = FlatIndex(1, METRIC_L2, "f32", device=self.device_id)
         probe.close()
@@ -89,9 +99,12 @@ class VectorDatabase:
             metric = METRIC_L2
         else:
             raise ValueError(f"Unsupported index type: {index_type}")
-        self.index = FlatIndex(dimension, metric, self._store_dtype(), device=self.device_id,
-                               keep_f32_master=bool(getattr(self.config, "db_keep_f32_master", False)))
-        logging.info(f"Created radad_flat index on GPU (FlatIndex/{self.index.store}) dim={dimension}")
+        keep = bool(getattr(self.config, "db_keep_f32_master", False))
+        if self._devices is not None and len(self._devices) > 1:
+            self.index = MultiGpuFlatIndex(dimension, metric, self._store_dtype(), self._devices, keep_f32_master=keep)
+        else:
+            self.index = FlatIndex(dimension, metric, self._store_dtype(), device=self.device_id, keep_f32_master=keep)
+        logging.info(f"Created radad_flat index on GPU ({type(self.index).__name__}/{self.index.store}) dim={dimension}")
         self._cosine = (index_type == "IP") and bool(getattr(self.config, "normalize_for_ip", True))
 
     # ---- reference :100-105 (kept for API parity; the hot path fuses this into the ingest kernel) -----
@@ -243,8 +256,11 @@ class VectorDatabase:
             self.vector_labels = meta['labels']
             self.vector_metadata = meta['metadata']
 
-            self.index = FlatIndex.load(self.db_path, self._store_dtype(), device=self.device_id,
-                                        keep_f32_master=bool(getattr(self.config, "db_keep_f32_master", False)))
+            keep = bool(getattr(self.config, "db_keep_f32_master", False))
+            if self._devices is not None and len(self._devices) > 1:
+                self.index = MultiGpuFlatIndex.load(self.db_path, self._store_dtype(), self._devices, keep_f32_master=keep)
+            else:
+                self.index = FlatIndex.load(self.db_path, self._store_dtype(), device=self.device_id, keep_f32_master=keep)
             self._labels_synced = -1
             if bool(getattr(self.config, "restore_cosine_on_load", False)):
                 self._cosine = (str(meta.get('index_type', '')).upper() == "IP") and \

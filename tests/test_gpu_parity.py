@@ -433,3 +433,84 @@ def test_sharded_single_process_equals_unsharded(pkg):
     np.testing.assert_array_equal(D.cpu().numpy(), Df)
     np.testing.assert_array_equal(L.cpu().numpy(), Lf)
     assert If[0, 0] == 3 and If[0, 1] == 5000
+
+
+def _multi_devices():
+    import torch
+    n = torch.cuda.device_count()
+    return list(range(min(n, 4))) if n >= 2 else [0, 0, 0]       # one GPU: three shards on the same device
+
+
+@pytest.mark.parametrize("store", ["bf16", "f32"])
+def test_multi_gpu_single_process_equals_one_gpu(pkg, store, tmp_path):
+    """MultiGpuFlatIndex (one process drives every shard; water-filled incremental adds; peer-memory merge kernel) must
+    return exactly what one FlatIndex returns: ids, distances, labels, reconstruct, and the saved faiss file."""
+    import torch
+    N, Dm, Q, k = 30011, 96, 70, 15
+    rng = np.random.default_rng(3)
+    xb = rng.integers(-2, 3, size=(N, Dm)).astype(np.float32)     # lattice: exact in every store dtype
+    xb[20000] = xb[7]
+    xq = rng.integers(-2, 3, size=(Q, Dm)).astype(np.float32)
+    xq[0] = xb[7]                                                 # tie across shards -> lowest global id first
+    labels = (np.arange(N) % 3 == 0).astype(np.float32)
+    one = pkg.FlatIndex(Dm, pkg.METRIC_L2, store)
+    multi = pkg.MultiGpuFlatIndex(Dm, pkg.METRIC_L2, store, devices=_multi_devices())
+    for a, b in ((0, 9000), (9000, 9100), (9100, 22000), (22000, N)):      # big, tiny, big, big adds
+        one.add(xb[a:b])
+        multi.add(xb[a:b])
+    one.set_labels(labels)
+    multi.set_labels(labels)
+    assert multi.ntotal == N and sum(multi.shard_sizes) == N
+    assert max(multi.shard_sizes) - min(multi.shard_sizes) <= 4096 + 100   # water-filling keeps the shards balanced
+    D1, I1, L1 = one.search(xq, k, return_labels=True)
+    Dm_, Im_, Lm_ = multi.search(xq, k, return_labels=True)
+    np.testing.assert_array_equal(Im_, I1)
+    np.testing.assert_array_equal(Dm_, D1)
+    np.testing.assert_array_equal(Lm_, L1)
+    assert I1[0, 0] == 7 and I1[0, 1] == 20000
+    Dd, Id = multi.search(torch.from_numpy(xq).cuda(), k)                  # device tensors in -> device tensors out
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(Id.cpu().numpy(), I1)
+    np.testing.assert_array_equal(Dd.cpu().numpy(), D1)
+    ids = np.array([[0, 8999, 9000], [9050, 29999, -1]], dtype=np.int64)
+    np.testing.assert_array_equal(multi.reconstruct_batch(ids), one.reconstruct_batch(ids))
+    np.testing.assert_array_equal(multi.reconstruct(21999), one.reconstruct(21999))
+    with pytest.raises(RuntimeError):
+        multi.reconstruct(N)
+    # persistence: same bytes as the one-GPU writer; loads back sharded and on one GPU
+    p1, pm = str(tmp_path / "one.bin"), str(tmp_path / "multi.bin")
+    one.save(p1)
+    multi.save(pm)
+    assert open(p1, "rb").read() == open(pm, "rb").read()
+    back = pkg.MultiGpuFlatIndex.load(p1, store, devices=_multi_devices())
+    back.set_labels(labels)
+    Db, Ib, Lb = back.search(xq, k, return_labels=True)
+    np.testing.assert_array_equal(Ib, I1)
+    np.testing.assert_array_equal(Db, D1)
+    np.testing.assert_array_equal(Lb, L1)
+
+
+def test_vector_database_on_several_gpus(pkg, tmp_path):
+    """config.db_devices: the unmodified VectorDatabase / retrieve_similar_vectors surface on a row-sharded index."""
+    import torch
+    g = _load(os.path.join(GOLDEN, "search_gauss_l2.npz"))
+    base = pkg.VectorDatabase(Cfg(tmp_path / "a", "L2", top_k=5))
+    many = pkg.VectorDatabase(Cfg(tmp_path / "b", "L2", top_k=5, db_devices=_multi_devices()))
+    _fill(base, g)
+    _fill(many, g)
+    assert type(many.index).__name__ == "MultiGpuFlatIndex" and many.index.ntotal == base.index.ntotal
+    D0, I0 = base.search_batch(g["xq"], k=15)
+    D1, I1 = many.search_batch(g["xq"], k=15)
+    np.testing.assert_array_equal(I1, I0)
+    np.testing.assert_array_equal(D1, D0)
+    q = torch.from_numpy(g["xq"][:16]).cuda()
+    qp = [base.vector_paths[int(i)] for i in I0[:16, 0]]
+    v0, l0, p0, d0 = pkg.retrieve_similar_vectors(base, q, 5, query_paths=qp, return_info=True, return_distances=True)
+    v1, l1, p1, d1 = pkg.retrieve_similar_vectors(many, q, 5, query_paths=qp, return_info=True, return_distances=True)
+    assert p0 == p1
+    assert torch.equal(v0, v1) and torch.equal(l0, l1) and torch.equal(d0.nan_to_num(-1), d1.nan_to_num(-1))
+    many.save()
+    again = pkg.VectorDatabase(Cfg(tmp_path / "b", "L2", top_k=5, db_devices=_multi_devices()))
+    again.load()
+    D2, I2 = again.search_batch(g["xq"], k=15)
+    np.testing.assert_array_equal(I2, I0)

@@ -57,3 +57,29 @@ def test_basename_codes(pkg):
         vector_paths = ["/a/x.wav", "/b/x.wav", "/a/y.wav"]
     codes, table = r._basename_codes(V)
     assert codes.tolist() == [0, 0, 1] and table == {"x.wav": 0, "y.wav": 1}
+
+
+def test_multi_gpu_water_filling_plan(pkg):
+    """Placement of add() calls over the shards of MultiGpuFlatIndex (pure host logic; no GPU needed)."""
+    m = pkg.MultiGpuFlatIndex.__new__(pkg.MultiGpuFlatIndex)
+
+    class _S:
+        def __init__(self):
+            self.ntotal = 0
+    m.shards = [_S() for _ in range(4)]
+
+    def apply(n):
+        plan = m._plan(n)
+        assert sum(c for _, c in plan) == n and all(c > 0 for _, c in plan)
+        for g, c in plan:
+            m.shards[g].ntotal += c
+        return plan
+
+    assert apply(100) == [(0, 100)]                        # tiny add: whole call to the least-loaded shard
+    assert apply(100) == [(1, 100)]
+    apply(1_000_000)
+    sizes = [s.ntotal for s in m.shards]
+    assert sum(sizes) == 1_000_200 and max(sizes) - min(sizes) <= 1
+    apply(10_000)                                          # reference slice size (vector_add_batch_size)
+    sizes = [s.ntotal for s in m.shards]
+    assert sum(sizes) == 1_010_200 and max(sizes) - min(sizes) <= 1
