@@ -25,35 +25,40 @@ __device__ __forceinline__ bool head_better(uint32_t ok_a, long long id_a, uint3
 // lbl_in [Q][L][kc] (optional, labels that travelled with the candidates) or labels[] indexed by local id.
 // metric_l2: dist = max(0, qnorm[q] - key) else dist = key.
 // out_* [Q][kout]; missing results: id -1, dist +inf (L2) / -inf (IP), label 0 (faiss convention).
+// One warp folds the L lists of query q.  Candidate loads are L2-coherent (ld.cg), so the function may also run in
+// the kernel that produced the lists (the streaming scorer's last block) after a __threadfence().  kth_out (optional)
+// receives the key of rank kout - 1 (-inf when fewer candidates exist); every out_* pointer may be null.
 template <typename IdxT>
-__global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restrict__ key_in,
-                                                          const IdxT* __restrict__ idx_in,
-                                                          const float* __restrict__ lbl_in, int Q, int L, int kc,
-                                                          int kout, int metric_l2, const float* __restrict__ qnorm,
-                                                          long long id_offset, const float* __restrict__ labels,
-                                                          float* __restrict__ out_dist,
-                                                          long long* __restrict__ out_idx,
-                                                          float* __restrict__ out_lbl,
-                                                          float* __restrict__ out_key) {
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (q >= Q) return;
+__device__ __forceinline__ void merge_lists_warp(const float* key_in, const IdxT* idx_in, const float* lbl_in, int q, int L,
+                                                 int kc, int kout, int metric_l2, const float* qnorm, long long id_offset,
+                                                 const float* labels, float* out_dist, long long* out_idx,
+                                                 float* out_lbl, float* out_key, int lane, float* kth_out) {
   const long long qbase = (long long)q * L * kc;
 
+  // Per list: the head and (prefetched up-front, so all loads of the prologue are independent) the entry behind it.
+  // With many lists per query most lists contribute at most two results, so the dependent load after a win -- one L2
+  // round trip per output rank -- is paid only from a list's third entry on.
   int ptr[MERGE_LPL];
-  uint32_t hok[MERGE_LPL];
-  long long hid[MERGE_LPL];
-  float hkey[MERGE_LPL];
+  uint32_t hok[MERGE_LPL], sok[MERGE_LPL];
+  long long hid[MERGE_LPL], sid[MERGE_LPL];
+  float hkey[MERGE_LPL], skey[MERGE_LPL];
 #pragma unroll
   for (int i = 0; i < MERGE_LPL; ++i) {
     ptr[i] = 0; hok[i] = 0; hid[i] = 0x7FFFFFFFFFFFFFFFll; hkey[i] = 0.f;
+    sok[i] = 0; sid[i] = 0x7FFFFFFFFFFFFFFFll; skey[i] = 0.f;
     const int l = lane + 32 * i;
     if (l < L && kc > 0) {
-      const long long id = (long long)idx_in[qbase + (long long)l * kc];
-      if (id >= 0) { hkey[i] = key_in[qbase + (long long)l * kc]; hok[i] = ordered_f32(hkey[i]); hid[i] = id; }
+      const long long o0 = qbase + (long long)l * kc;
+      const long long id = (long long)__ldcg(idx_in + o0);
+      const float kv = __ldcg(key_in + o0);
+      long long id2 = -1; float kv2 = 0.f;
+      if (kc > 1) { id2 = (long long)__ldcg(idx_in + o0 + 1); kv2 = __ldcg(key_in + o0 + 1); }
+      if (id >= 0) { hkey[i] = kv; hok[i] = ordered_f32(kv); hid[i] = id; }
+      if (id >= 0 && id2 >= 0) { skey[i] = kv2; sok[i] = ordered_f32(kv2); sid[i] = id2; }
     }
   }
 
+  float kth = -CUDART_INF_F;
   for (int r = 0; r < kout; ++r) {
     // lane-local best head
     uint32_t bok = 0; long long bid = 0x7FFFFFFFFFFFFFFFll; int bi = 0;
@@ -73,17 +78,19 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
     if (wok == 0) {
       if (lane == 0) {
         if (out_dist) out_dist[o] = metric_l2 ? CUDART_INF_F : -CUDART_INF_F;
-        out_idx[o] = -1;
+        if (out_idx) out_idx[o] = -1;
         if (out_lbl) out_lbl[o] = 0.f;
         if (out_key) out_key[o] = -CUDART_INF_F;
       }
       continue;
     }
+    if (r == kout - 1) kth = unordered_f32(wok);
     if (lane == wl) {
       // emit + advance the winning list
       float kv = 0.f; int p = 0;
+      uint32_t nok = 0; long long nid = 0x7FFFFFFFFFFFFFFFll; float nkey = 0.f;
 #pragma unroll
-      for (int i = 0; i < MERGE_LPL; ++i) if (i == bi) { kv = hkey[i]; p = ptr[i]; }
+      for (int i = 0; i < MERGE_LPL; ++i) if (i == bi) { kv = hkey[i]; p = ptr[i]; nok = sok[i]; nid = sid[i]; nkey = skey[i]; }
       const int l = lane + 32 * bi;
       const long long src = qbase + (long long)l * kc + p;
       if (out_dist) {
@@ -91,20 +98,40 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
         if (metric_l2) d = fmaxf(0.f, qnorm[q] - kv);
         out_dist[o] = d;
       }
-      out_idx[o] = wid + id_offset;   // wid is a local id when id_offset != 0, already global otherwise
+      if (out_idx) out_idx[o] = wid + id_offset;   // wid is a local id when id_offset != 0, already global otherwise
       if (out_key) out_key[o] = kv;
-      if (out_lbl) out_lbl[o] = lbl_in ? lbl_in[src] : (labels ? labels[wid] : 0.f);
+      if (out_lbl) out_lbl[o] = lbl_in ? __ldcg(lbl_in + src) : (labels ? labels[wid] : 0.f);
       ++p;
-      uint32_t nok = 0; long long nid = 0x7FFFFFFFFFFFFFFFll; float nkey = 0.f;
-      if (p < kc) {
-        const long long id = (long long)idx_in[src + 1];
-        if (id >= 0) { nkey = key_in[src + 1]; nok = ordered_f32(nkey); nid = id; }
+      if (p >= 2) {                                // beyond the prefetched pair: dependent load
+        nok = 0; nid = 0x7FFFFFFFFFFFFFFFll; nkey = 0.f;
+        if (p < kc) {
+          const long long id = (long long)__ldcg(idx_in + src + 1);
+          if (id >= 0) { nkey = __ldcg(key_in + src + 1); nok = ordered_f32(nkey); nid = id; }
+        }
       }
 #pragma unroll
       for (int i = 0; i < MERGE_LPL; ++i) if (i == bi) { ptr[i] = p; hok[i] = nok; hid[i] = nid; hkey[i] = nkey; }
     }
     __syncwarp();
   }
+  if (kth_out) *kth_out = kth;
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restrict__ key_in,
+                                                          const IdxT* __restrict__ idx_in,
+                                                          const float* __restrict__ lbl_in, int Q, int L, int kc,
+                                                          int kout, int metric_l2, const float* __restrict__ qnorm,
+                                                          long long id_offset, const float* __restrict__ labels,
+                                                          float* __restrict__ out_dist,
+                                                          long long* __restrict__ out_idx,
+                                                          float* __restrict__ out_lbl,
+                                                          float* __restrict__ out_key) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  merge_lists_warp<IdxT>(key_in, idx_in, lbl_in, q, L, kc, kout, metric_l2, qnorm, id_offset, labels, out_dist, out_idx,
+                         out_lbl, out_key, lane, nullptr);
 }
 
 // Exact fp32 re-rank.  One warp per query.

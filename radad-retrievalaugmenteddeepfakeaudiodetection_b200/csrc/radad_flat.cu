@@ -91,7 +91,9 @@ struct rdb_handle {
   std::mutex mu;
   // scratch
   DevBuf add_stage, q_stage, qf, qhi, qlo, qnorm, cand_key, cand_idx, o_dist, o_idx, o_lbl, ids_stage, rec_stage;
-  DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l, qs16, gthr, tcsync;
+  DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l, gthr, tcsync, stream_ctl, fkey, fidx;
+  void* pin = nullptr;            // pinned host staging of the small-batch path
+  size_t pin_bytes = 0;
   float* d_ynorm_max = nullptr;   // max |y|^2 over the shard (device scalar; feeds the re-rank certificate)
   int64_t last_uncertified = 0;
   bool has_master() const { return store == RDB_STORE_F32 || (flags & RDB_FLAG_KEEP_F32_MASTER); }
@@ -365,43 +367,132 @@ struct QueryView {
   const void* qlo;    // 16-bit [nq, Dp] (split-precision)
   const float* qnorm; // [nq]
   int nq;
-  const float* qs16 = nullptr;  // fp32 [nq, Dp] copy of the ROUNDED 16-bit queries (stream scorer, 16-bit stores)
 };
 
-template <typename T, bool L2>
-int launch_stream_t(rdb_handle* h, const T* Y, int ld, const float* Qs, int nq, int blocks, int rpb, float* ck, int* ci,
-                    int kout) {
-  const int nqt = nq <= 1 ? 1 : (nq <= 2 ? 2 : 4);
-  const int kl = kout <= 32 ? 1 : 4;
-  const size_t smem = stream_smem_bytes(nqt, ld, kl);
-  // lanes per row: whole warp for long rows, 16 / 8 lanes when a row is only a few 128-bit vectors
-  const int nvec = ld / StreamVec<T>::EPV;
-  const int lpr_log2 = nvec >= 96 ? 5 : (nvec >= 48 ? 4 : 3);
-#define STREAM_LAUNCH(NQ, KL)                                                                                \
-  do {                                                                                                       \
-    auto kern = score_select_stream_kernel<T, NQ, L2, KL>;                                                   \
-    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-    kern<<<dim3(blocks), dim3(STREAM_THREADS), smem, h->stream>>>(Y, ld, h->ynorm, int(h->n), Qs, nq, rpb, ck, ci, \
-                                                                  kout, lpr_log2);                           \
-  } while (0)
-  if (kl == 1) { if (nqt == 1) STREAM_LAUNCH(1, 1); else if (nqt == 2) STREAM_LAUNCH(2, 1); else STREAM_LAUNCH(4, 1); }
-  else         { if (nqt == 1) STREAM_LAUNCH(1, 4); else if (nqt == 2) STREAM_LAUNCH(2, 4); else STREAM_LAUNCH(4, 4); }
-#undef STREAM_LAUNCH
+// ---- small-batch streaming search (nq <= 4): ONE launch per pass does query prep + stream + final merge
+template <typename T, int NQ, bool L2, int MODE>
+int launch_stream_kernel(rdb_handle* h, const StreamParams& p, int blocks, size_t smem) {
+  auto kern = score_select_stream_kernel<T, NQ, L2, MODE>;
+  CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3(blocks), dim3(STREAM_THREADS), smem, h->stream>>>(p);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return RDB_OK;
 }
-
-int launch_stream(rdb_handle* h, const QueryView& qv, int k, int blocks, int rpb, float* ck, int* ci) {
+template <typename T, bool L2>
+int launch_stream_mode(rdb_handle* h, const StreamParams& p, int blocks, int mode) {
+  const int nqt = p.nq <= 1 ? 1 : (p.nq <= 2 ? 2 : 4);
+  const size_t smem = stream_smem_bytes(nqt, p.ld, mode);
+#define STREAM_NQ(MODE)                                                                         \
+  (nqt == 1 ? launch_stream_kernel<T, 1, L2, MODE>(h, p, blocks, smem)                          \
+            : (nqt == 2 ? launch_stream_kernel<T, 2, L2, MODE>(h, p, blocks, smem)              \
+                        : launch_stream_kernel<T, 4, L2, MODE>(h, p, blocks, smem)))
+  if (mode == STREAM_LIST1) return STREAM_NQ(STREAM_LIST1);
+  if (mode == STREAM_LIST4) return STREAM_NQ(STREAM_LIST4);
+  return STREAM_NQ(STREAM_FILTER);
+#undef STREAM_NQ
+}
+int launch_stream(rdb_handle* h, StreamParams& p, int blocks, int mode) {
   const bool l2 = h->metric == RDB_METRIC_L2;
+  p.metric_l2 = l2 ? 1 : 0;
+  int nvec;
+  if (h->store == RDB_STORE_F32) { p.Y = h->master; p.ld = h->d; nvec = p.ld / 4; }
+  else { p.Y = h->hi; p.ld = h->dp; nvec = p.ld / 8; }
+  // lanes per row: whole warp for long rows, 16 / 8 lanes when a row is only a few 128-bit vectors
+  p.lpr_log2 = nvec >= 96 ? 5 : (nvec >= 48 ? 4 : 3);
   if (h->store == RDB_STORE_F32)
-    return l2 ? launch_stream_t<float, true>(h, h->master, h->d, qv.qf, qv.nq, blocks, rpb, ck, ci, k)
-              : launch_stream_t<float, false>(h, h->master, h->d, qv.qf, qv.nq, blocks, rpb, ck, ci, k);
+    return l2 ? launch_stream_mode<float, true>(h, p, blocks, mode) : launch_stream_mode<float, false>(h, p, blocks, mode);
   if (h->f16())
-    return l2 ? launch_stream_t<__half, true>(h, (const __half*)h->hi, h->dp, qv.qs16, qv.nq, blocks, rpb, ck, ci, k)
-              : launch_stream_t<__half, false>(h, (const __half*)h->hi, h->dp, qv.qs16, qv.nq, blocks, rpb, ck, ci, k);
-  return l2 ? launch_stream_t<__nv_bfloat16, true>(h, (const __nv_bfloat16*)h->hi, h->dp, qv.qs16, qv.nq, blocks, rpb, ck, ci, k)
-            : launch_stream_t<__nv_bfloat16, false>(h, (const __nv_bfloat16*)h->hi, h->dp, qv.qs16, qv.nq, blocks, rpb, ck, ci, k);
+    return l2 ? launch_stream_mode<__half, true>(h, p, blocks, mode) : launch_stream_mode<__half, false>(h, p, blocks, mode);
+  return l2 ? launch_stream_mode<__nv_bfloat16, true>(h, p, blocks, mode)
+            : launch_stream_mode<__nv_bfloat16, false>(h, p, blocks, mode);
+}
+
+constexpr int64_t kStreamFilterMinRows = 131072;   // the 1/64 sample must hold far more than 16 rows
+
+// The whole nq <= 4 search.  Host buffers go through one pinned staging area: one H2D copy of the queries, the
+// launches, ONE D2H copy of the packed results.
+int search_stream(rdb_handle* h, const float* q, int nq, int k, int mem, int normalize, bool shard_mode, float* out_a,
+                  int64_t* out_idx, float* out_lbl, float* out_qnorm) {
+  const int D = h->d;
+  const bool host = mem == RDB_MEM_HOST;
+  cudaStream_t s = h->stream;
+  const float* labels = (h->labels && h->nlabels == h->n) ? h->labels : nullptr;
+  const int blocks0 = int(std::min<int64_t>(h->num_sms, (h->n + 31) / 32));
+  const int rpb = int(round_up((h->n + blocks0 - 1) / blocks0, 32));
+  const int S = int((h->n + rpb - 1) / rpb);
+  const int mode = k <= 32 ? STREAM_LIST1 : (h->n >= kStreamFilterMinRows ? STREAM_FILTER : STREAM_LIST4);
+  const int kc = std::max(k, STREAM_PIVOT_RANK);
+  CUDA_TRY(h, h->cand_key.ensure(size_t(nq) * S * kc * 4));
+  CUDA_TRY(h, h->cand_idx.ensure(size_t(nq) * S * kc * 4));
+  if (!h->stream_ctl.p) {
+    CUDA_TRY(h, h->stream_ctl.ensure(sizeof(StreamCtl)));
+    CUDA_TRY(h, cudaMemsetAsync(h->stream_ctl.p, 0, sizeof(StreamCtl), s));
+  }
+  // packed device outputs (host path): [a nq*k f32][lbl nq*k f32][qnorm 4 f32][idx nq*k i64]
+  const size_t nk = size_t(nq) * k;
+  const size_t off_l = nk * 4, off_qn = 2 * nk * 4, off_i = 2 * nk * 4 + 16, pack_bytes = off_i + nk * 8;
+  const size_t q_bytes = size_t(nq) * D * 4;
+  float* d_a = out_a; int64_t* d_i = out_idx; float* d_l = out_lbl; float* d_qn = out_qnorm;
+  const float* qsrc = q;
+  if (host) {
+    if (h->pin_bytes < pack_bytes + q_bytes) {
+      if (h->pin) cudaFreeHost(h->pin);
+      h->pin = nullptr; h->pin_bytes = 0;
+      const size_t want = std::max<size_t>(pack_bytes + q_bytes, 1 << 16);
+      CUDA_TRY(h, cudaHostAlloc(&h->pin, want, cudaHostAllocDefault));
+      h->pin_bytes = want;
+    }
+    CUDA_TRY(h, h->q_stage.ensure(q_bytes));
+    CUDA_TRY(h, h->o_dist.ensure(pack_bytes));
+    memcpy(static_cast<char*>(h->pin) + pack_bytes, q, q_bytes);
+    CUDA_TRY(h, cudaMemcpyAsync(h->q_stage.p, static_cast<char*>(h->pin) + pack_bytes, q_bytes, cudaMemcpyHostToDevice, s));
+    qsrc = h->q_stage.as<float>();
+    char* base = static_cast<char*>(h->o_dist.p);
+    d_a = reinterpret_cast<float*>(base);
+    d_l = out_lbl ? reinterpret_cast<float*>(base + off_l) : nullptr;
+    d_qn = reinterpret_cast<float*>(base + off_qn);
+    d_i = reinterpret_cast<int64_t*>(base + off_i);
+  }
+  StreamParams p;
+  memset(&p, 0, sizeof(p));
+  p.ynorm = h->ynorm; p.N = int(h->n);
+  p.q_raw = qsrc; p.nq = nq; p.D = D; p.normalize = normalize;
+  p.rows_per_block = rpb; p.kout = k; p.step_mul = 1;
+  p.cand_key = h->cand_key.as<float>(); p.cand_idx = h->cand_idx.as<int>();
+  p.ctl = h->stream_ctl.as<StreamCtl>();
+  p.id_offset = h->id_offset; p.labels = labels;
+  p.out_dist = shard_mode ? nullptr : d_a; p.out_key = shard_mode ? d_a : nullptr;
+  p.out_idx = reinterpret_cast<long long*>(d_i); p.out_lbl = d_l; p.out_qnorm = d_qn;
+  int rc;
+  cudaEventRecord(h->ev0, s);
+  if (mode == STREAM_FILTER) {
+    CUDA_TRY(h, h->fkey.ensure(size_t(4) * STREAM_FCAP * 4));
+    CUDA_TRY(h, h->fidx.ensure(size_t(4) * STREAM_FCAP * 4));
+    p.fkey = h->fkey.as<float>(); p.fidx = h->fidx.as<int>();
+    StreamParams ps = p;                       // 1) pivot from a strided 1/64 sample (LIST, k = 16)
+    ps.kout = STREAM_PIVOT_RANK; ps.step_mul = STREAM_SAMPLE; ps.use_pivot_out = 1;
+    ps.out_dist = nullptr; ps.out_key = nullptr; ps.out_idx = nullptr; ps.out_lbl = nullptr; ps.out_qnorm = nullptr;
+    if ((rc = launch_stream(h, ps, S, STREAM_LIST1))) return rc;
+    if ((rc = launch_stream(h, p, S, STREAM_FILTER))) return rc;      // 2) full pass: append key >= pivot, rank, emit
+    StreamParams pf = p;                       // 3) exits at once unless the FILTER pass raised the fallback flag
+    pf.run_if_fallback = 1;
+    if ((rc = launch_stream(h, pf, S, STREAM_LIST4))) return rc;
+  } else {
+    if ((rc = launch_stream(h, p, S, mode))) return rc;
+  }
+  cudaEventRecord(h->ev1, s);
+  h->ev_valid = true; h->last_algo = RDB_ALGO_STREAM; h->last_S = S;
+  if (host) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->pin, h->o_dist.p, pack_bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    const char* base = static_cast<const char*>(h->pin);
+    memcpy(out_a, base, nk * 4);
+    if (out_lbl) memcpy(out_lbl, base + off_l, nk * 4);
+    if (out_qnorm) memcpy(out_qnorm, base + off_qn, size_t(nq) * 4);
+    memcpy(out_idx, base + off_i, nk * 8);
+  }
+  return RDB_OK;
 }
 
 // score + select over the local shard into h->cand_key / h->cand_idx; *L_out = lists per query (width kc each)
@@ -422,17 +513,6 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
                         h->cand_idx.as<int>()))) return rc;
     if (timed) cudaEventRecord(h->ev1, s);
     *L_out = S * TC_LISTS;
-  } else if (algo == RDB_ALGO_STREAM) {
-    // small batch: one block per SM streams a contiguous slice of the stored rows; one list per block
-    const int blocks = int(std::min<int64_t>(h->num_sms, (h->n + 31) / 32));
-    const int rpb = int(round_up((h->n + blocks - 1) / blocks, 32));
-    S = int((h->n + rpb - 1) / rpb);
-    CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * kc * 4));
-    CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * kc * 4));
-    if (timed) cudaEventRecord(h->ev0, s);
-    if ((rc = launch_stream(h, qv, kc, S, rpb, h->cand_key.as<float>(), h->cand_idx.as<int>()))) return rc;
-    if (timed) cudaEventRecord(h->ev1, s);
-    *L_out = S;
   } else {
     const int ntiles = int((h->n + SIMT_BN - 1) / SIMT_BN);
     S = choose_splits(nqt, ntiles, 2 * h->num_sms, 256 / SIMT_LISTS, 2, &tpc);
@@ -492,6 +572,8 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   const float* labels = (h->labels && h->nlabels == h->n) ? h->labels : nullptr;
   cudaStream_t s = h->stream;
   h->last_uncertified = 0;
+  if (algo == RDB_ALGO_STREAM)
+    return search_stream(h, q, int(nq), k, mem, normalize, shard_mode, out_a, out_idx, out_lbl, out_qnorm);
 
   for (int64_t b0 = 0; b0 < nq; b0 += kQueryBatch) {
     const int nb = int(std::min<int64_t>(kQueryBatch, nq - b0));
@@ -509,15 +591,6 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
       CUDA_TRY(h, h->qhi.ensure(size_t(nb) * Dp * 2));
       if ((rc = launch_ingest(h, qsrc, nb, normalize, 1, nullptr, h->qhi.p, nullptr, h->qnorm.as<float>()))) return rc;
       qv.qhi = h->qhi.p;
-      if (algo == RDB_ALGO_STREAM) {
-        // fp32 copy of the rounded queries, pitch Dp (what the streaming scorer keeps in shared memory)
-        CUDA_TRY(h, h->qs16.ensure(size_t(nb) * Dp * 4));
-        if (h->f16()) gather_rows_kernel<__half><<<(nb + 7) / 8, 256, 0, s>>>(nullptr, nb, nb, Dp, Dp, nullptr, (const __half*)h->qhi.p, 0, 0, h->qs16.as<float>());
-        else gather_rows_kernel<__nv_bfloat16><<<(nb + 7) / 8, 256, 0, s>>>(nullptr, nb, nb, Dp, Dp, nullptr, (const __nv_bfloat16*)h->qhi.p, 0, 0, h->qs16.as<float>());
-        h->launches++;
-        CUDA_TRY(h, cudaGetLastError());
-        qv.qs16 = h->qs16.as<float>();
-      }
     } else {
       CUDA_TRY(h, h->qf.ensure(size_t(nb) * D * 4));
       if (split) {
@@ -676,8 +749,9 @@ int rdb_destroy(rdb_handle* h) {
     cudaFree(h->d_ynorm_max);
     for (DevBuf* b : {&h->add_stage, &h->q_stage, &h->qf, &h->qhi, &h->qlo, &h->qnorm, &h->cand_key, &h->cand_idx,
                       &h->o_dist, &h->o_idx, &h->o_lbl, &h->ids_stage, &h->rec_stage, &h->rr_key, &h->rr_idx,
-                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l, &h->qs16, &h->gthr, &h->tcsync})
+                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l, &h->gthr, &h->tcsync, &h->stream_ctl, &h->fkey, &h->fidx})
       b->release();
+    if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -3,13 +3,29 @@
 // through HBM (2*D flops per 2*D or 4*D bytes), so this kernel is built around the memory system instead of the
 // tensor cores: every warp reads whole rows with 128-bit coalesced loads (rows are contiguous -> full DRAM
 // pages, unlike 128-byte TMA box slices), 4 rows in flight per warp, fp32 FMA against the queries held in
-// shared memory, butterfly reduction, and a warp-distributed sorted top-k (lane j holds ranks [KL*j, KL*j+KL); insertion
-// is a ballot + shuffle-shift).  The 16 warps of a block merge their lists in shared memory so each block emits
-// ONE sorted list per query; merge.cuh folds the gridDim.x lists.  Arithmetic is exact fp32 for fp32 stores
-// (no split / re-rank needed) and fp32-accumulated products of the stored 16-bit values otherwise.
+// shared memory, butterfly reduction.  Arithmetic is exact fp32 for fp32 stores (no split / re-rank needed) and
+// fp32-accumulated products of the stored 16-bit values otherwise.
+//
+// ONE launch does the whole search (the latency path is launch- and round-trip-bound once the stream itself runs at
+// HBM speed): every block prepares the queries itself (normalise, round to the store dtype, |q|^2 -- the same
+// arithmetic as ingest.cuh), streams its slice of the rows, and the LAST block to finish (atomic ticket) folds the
+// per-block results into the final best-first lists -- distances, global ids, labels -- in the caller's buffers.
+//
+// Selection is a policy:
+//   LIST   (k <= 32: 1 entry per lane, k <= 128: 4 per lane)  warp-distributed sorted top-k in registers (lane j holds
+//          ranks [KL*j, KL*j+KL); insertion is a ballot + shuffle-shift), 16 warp lists merged per block, the
+//          gridDim.x block lists merged by the last block.
+//   FILTER (large k on large databases)  maintaining k = 100 sorted entries per warp costs more issue slots than the
+//          stream itself (each warp sees only N / 2368 rows, so ~10 % of its rows still insert).  Instead a first
+//          LIST launch over a 1/64 strided SAMPLE of the rows yields a per-query pivot (the sample's 16th best key:
+//          ~1000 rows of the whole database beat it), and the full pass merely appends the rows with key >= pivot to
+//          a per-query buffer; the last block ranks those ~1000 candidates by counting.  Exactness does not depend
+//          on the sample: the result is the exact top-k whenever k <= count <= capacity, and otherwise a flag makes
+//          the (always enqueued, normally empty) LIST launch redo the search.
 #pragma once
 #include "common.cuh"
 #include "ingest.cuh"
+#include "merge.cuh"
 
 namespace rdb {
 
@@ -86,39 +102,137 @@ struct WarpList {
   }
 };
 
+enum { STREAM_LIST1 = 0, STREAM_LIST4 = 1, STREAM_FILTER = 2 };
+constexpr int STREAM_FCAP = 4096;       // FILTER: candidate slots per query
+constexpr int STREAM_SAMPLE = 64;       // FILTER: the pivot pass reads every 64th warp step of the rows
+constexpr int STREAM_PIVOT_RANK = 16;   // FILTER: pivot = this rank of the sample -> ~RANK * SAMPLE rows pass
+
+struct StreamCtl {                      // device control block owned by the handle (zero-initialised once)
+  unsigned int ticket;                  // blocks finished (self-resetting)
+  int fallback;                         // FILTER pass could not produce the result -> the LIST launch must run
+  int fcount[4];                        // FILTER: appended candidates per query (self-resetting)
+  float pivot[4];                       // FILTER: per-query pivot key from the sample pass
+};
+
+struct StreamParams {
+  const void* Y; int ld; const float* ynorm; int N;       // stored rows [N, ld] (T), |y|^2
+  const float* q_raw; int nq, D, normalize;               // raw fp32 queries [nq, D] (device)
+  int rows_per_block, kout, lpr_log2, step_mul;           // step_mul > 1: strided sample pass
+  float* cand_key; int* cand_idx;                         // LIST: block lists [nq][gridDim.x][kout]
+  float* fkey; int* fidx;                                 // FILTER: candidates [nq][STREAM_FCAP]
+  StreamCtl* ctl;
+  int use_pivot_out;                                      // sample pass: only write ctl->pivot (rank STREAM_PIVOT_RANK)
+  int run_if_fallback;                                    // fallback launch: exit at once unless ctl->fallback != 0
+  int metric_l2; long long id_offset; const float* labels;
+  float* out_dist; long long* out_idx; float* out_lbl; float* out_key; float* out_qnorm;
+};
+
+template <> __device__ __forceinline__ float to16<float>(float v) { return v; }
+template <> __device__ __forceinline__ float from16<float>(float v) { return v; }
+
+// Query prep of ONE query by one warp, arithmetic identical to ingest_rows_kernel (same loop order and fmaf chain):
+// v = x / (|x| + 1e-12) when `normalize`; stored value = round_T(v) (16-bit stores) or v (fp32); returns the sum of
+// squares of the STORED values.  dst is fp32 [ld], pad columns [D, ld) zero.
+template <typename T>
+__device__ __forceinline__ float stream_prep_query(const float* __restrict__ xr, int D, int ld, int normalize,
+                                                   float* __restrict__ dst, int lane) {
+  const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(xr) & 15) == 0);
+  float denom = 1.0f;
+  if (normalize) {
+    float s = 0.f;
+    if (vec4) {
+      const float4* x4 = reinterpret_cast<const float4*>(xr);
+      for (int c = lane; c < (D >> 2); c += 32) {
+        const float4 v = x4[c];
+        s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+      }
+    } else {
+      for (int c = lane; c < D; c += 32) { const float v = xr[c]; s = fmaf(v, v, s); }
+    }
+    s = warp_sum(s);
+    denom = sqrtf(s) + 1e-12f;
+  }
+  float acc = 0.f;
+  if (vec4) {
+    const float4* x4 = reinterpret_cast<const float4*>(xr);
+    for (int c = lane; c < (ld >> 2); c += 32) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < (D >> 2)) {
+        v = x4[c];
+        if (normalize) { v.x = v.x / denom; v.y = v.y / denom; v.z = v.z / denom; v.w = v.w / denom; }
+      }
+      if (sizeof(T) == 2) {
+        v.x = from16<T>(to16<T>(v.x)); v.y = from16<T>(to16<T>(v.y));
+        v.z = from16<T>(to16<T>(v.z)); v.w = from16<T>(to16<T>(v.w));
+      }
+      reinterpret_cast<float4*>(dst)[c] = v;
+      if (c < (D >> 2)) { acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc); }
+    }
+  } else {
+    for (int c = lane; c < ld; c += 32) {
+      float v = 0.f;
+      if (c < D) { v = xr[c]; if (normalize) v = v / denom; }
+      if (sizeof(T) == 2) v = from16<T>(to16<T>(v));
+      dst[c] = v;
+      if (c < D) acc = fmaf(v, v, acc);
+    }
+  }
+  return warp_sum(acc);
+}
+
 // Y [N, ld] stored rows (T = fp32 master or the 16-bit store), ld multiple of EPV, columns [D, ld) zero (16-bit) --
 // D itself must be a multiple of EPV for fp32 (checked by the host; otherwise another scorer is used).
-// Qs: queries as fp32 [NQ][ld] in global memory (already normalised / rounded to the store dtype).
-// cand_* [nq][gridDim.x][kout].
-template <typename T, int NQ, bool L2, int KL>
-__global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
-    const T* __restrict__ Y, int ld, const float* __restrict__ ynorm, int N, const float* __restrict__ Qs, int nq,
-    int rows_per_block, float* __restrict__ cand_key, int* __restrict__ cand_idx, int kout, int lpr_log2) {
+template <typename T, int NQ, bool L2, int MODE>
+__global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(const StreamParams p) {
+  constexpr int KL = (MODE == STREAM_LIST4) ? 4 : 1;
   extern __shared__ __align__(16) float sm[];
+  __shared__ float s_qnorm[NQ];
+  __shared__ float s_pivot[NQ];
+  __shared__ unsigned int s_ticket;
   float* qs = sm;                                        // [NQ][ld]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < NQ * ld; i += STREAM_THREADS) qs[i] = (i / ld < nq) ? Qs[i] : 0.f;
+  const int ld = p.ld, nq = p.nq, kout = p.kout, N = p.N;
+  const T* __restrict__ Y = reinterpret_cast<const T*>(p.Y);
+  if (p.run_if_fallback && __ldcg(&p.ctl->fallback) == 0) return;
+
+  // ---- query prep (every block, redundantly: nq * D elements)
+  if (warp < NQ) {
+    if (warp < nq) {
+      const float n2 = stream_prep_query<T>(p.q_raw + (long long)warp * p.D, p.D, ld, p.normalize, qs + warp * ld, lane);
+      if (lane == 0) {
+        s_qnorm[warp] = n2;
+        if (MODE == STREAM_FILTER) s_pivot[warp] = __ldcg(&p.ctl->pivot[warp]);
+        if (blockIdx.x == 0 && p.out_qnorm) p.out_qnorm[warp] = n2;
+      }
+    } else {
+      for (int c = lane; c < ld; c += 32) qs[warp * ld + c] = 0.f;
+    }
+  }
   __syncthreads();
 
   constexpr int EPV = StreamVec<T>::EPV;
   const int nvec = ld / EPV;                             // 128-bit vectors per row
-  const int row_begin = blockIdx.x * rows_per_block;
-  const int row_end = min(N, row_begin + rows_per_block);
+  const int row_begin = blockIdx.x * p.rows_per_block;
+  const int row_end = min(N, row_begin + p.rows_per_block);
 
   WarpList<KL> top[NQ];
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) top[q].init();
   float thr[NQ];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) thr[q] = -CUDART_INF_F;
+  for (int q = 0; q < NQ; ++q) {
+    top[q].init();
+    thr[q] = -CUDART_INF_F;
+    // FILTER admits key >= pivot: compare against the next float below it
+    if (MODE == STREAM_FILTER) thr[q] = (q < nq) ? floor_from_gthr(ordered_f32(s_pivot[q])) : CUDART_INF_F;
+  }
 
   // Lane groups of `lpr` lanes own rows (short rows: 8 or 16 lanes per row, so the shuffle reduction is amortised over
   // several rows per warp step).  Per step a warp takes RW = R * G consecutive rows: group g rows r0 + g*R .. + R.
   constexpr int R = StreamVec<T>::R;
+  const int lpr_log2 = p.lpr_log2;
   const int lpr = 1 << lpr_log2, G = 32 >> lpr_log2;
   const int grp = lane >> lpr_log2, l = lane & (lpr - 1);
   const int RW = R * G;
-  for (int r0 = row_begin + warp * RW; r0 < row_end; r0 += STREAM_WARPS * RW) {
+  for (int r0 = row_begin + warp * RW; r0 < row_end; r0 += STREAM_WARPS * RW * p.step_mul) {
     float acc[R][NQ];
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -150,21 +264,44 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
       for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int q = 0; q < NQ; ++q) acc[r][q] += __shfl_xor_sync(0xffffffffu, acc[r][q], o);
+    // keys of this lane group's R rows (lane l == 0 of each group holds the full sums after the butterfly: all do)
+    bool any = false;
+    float keyv[R][NQ];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = r0 + grp * R + r;
+      float yn = 0.f;
+      if (L2 && row < row_end) yn = __ldg(p.ynorm + row);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        keyv[r][q] = L2 ? fmaf(2.0f, acc[r][q], -yn) : acc[r][q];
+        any = any || (q < nq && row < row_end && keyv[r][q] > thr[q]);
+      }
+    }
+    // steady state: no row of this step beats any threshold -> skip the serial offer loop entirely
+    if (!__any_sync(0xffffffffu, any)) continue;
     // offer the RW scores in ascending row order (warp-uniform control flow)
     for (int gg = 0; gg < G; ++gg) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int row = r0 + gg * R + r;
         if (row < row_end) {
-          float yn = 0.f;
-          if (L2) yn = __ldg(ynorm + row);
 #pragma unroll
           for (int q = 0; q < NQ; ++q) {
-            const float sc = __shfl_sync(0xffffffffu, acc[r][q], gg << lpr_log2);
-            const float key = L2 ? fmaf(2.0f, sc, -yn) : sc;
+            const float key = __shfl_sync(0xffffffffu, keyv[r][q], gg << lpr_log2);
             if (q < nq && key > thr[q]) {
-              top[q].insert(key, row, lane);
-              thr[q] = top[q].threshold(kout);
+              if (MODE == STREAM_FILTER) {
+                int slot = 0;
+                if (lane == 0) slot = atomicAdd(&p.ctl->fcount[q], 1);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (lane == 0 && slot < STREAM_FCAP) {
+                  p.fkey[q * STREAM_FCAP + slot] = key;
+                  p.fidx[q * STREAM_FCAP + slot] = row;
+                }
+              } else {
+                top[q].insert(key, row, lane);
+                thr[q] = top[q].threshold(kout);
+              }
             }
           }
         }
@@ -172,51 +309,120 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
     }
   }
 
-  // ---- in-block merge: 16 warp lists -> 1 list per query
+  // ---- LIST: in-block merge, 16 warp lists -> 1 list per query in global memory
   __syncthreads();                                       // queries no longer needed: reuse smem
-  constexpr int LW = 32 * KL;                            // entries per warp list
-  float* lk = sm;                                        // [NQ][STREAM_WARPS][LW]
-  int* li = reinterpret_cast<int*>(sm + NQ * STREAM_WARPS * LW);
+  if (MODE != STREAM_FILTER) {
+    constexpr int LW = 32 * KL;                          // entries per warp list
+    float* lk = sm;                                      // [NQ][STREAM_WARPS][LW]
+    int* li = reinterpret_cast<int*>(sm + NQ * STREAM_WARPS * LW);
 #pragma unroll
-  for (int q = 0; q < NQ; ++q)
+    for (int q = 0; q < NQ; ++q)
 #pragma unroll
-    for (int sl = 0; sl < KL; ++sl) {
-      lk[(q * STREAM_WARPS + warp) * LW + lane * KL + sl] = top[q].key[sl];
-      li[(q * STREAM_WARPS + warp) * LW + lane * KL + sl] = top[q].idx[sl];
-    }
-  __syncthreads();
-  if (warp < nq) {
-    const int q = warp;
-    // lane w < STREAM_WARPS owns list w; k rounds of warp arg-best over the heads (key desc, id asc)
-    int ptr = 0;
-    const bool own = lane < STREAM_WARPS;
-    const float* mk = lk + (q * STREAM_WARPS + (own ? lane : 0)) * LW;
-    const int* mi = li + (q * STREAM_WARPS + (own ? lane : 0)) * LW;
-    for (int r = 0; r < kout; ++r) {
-      uint32_t ok = 0; int id = 0x7FFFFFFF; float kv = 0.f;
-      if (own && ptr < LW && mi[ptr] >= 0) { kv = mk[ptr]; ok = ordered_f32(kv); id = mi[ptr]; }
-      uint32_t wok = ok; int wid = id; int wl = lane;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t ook = __shfl_xor_sync(0xffffffffu, wok, o);
-        const int oid = __shfl_xor_sync(0xffffffffu, wid, o);
-        const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
-        if (ook > wok || (ook == wok && oid < wid) || (ook == wok && oid == wid && ol < wl)) { wok = ook; wid = oid; wl = ol; }
+      for (int sl = 0; sl < KL; ++sl) {
+        lk[(q * STREAM_WARPS + warp) * LW + lane * KL + sl] = top[q].key[sl];
+        li[(q * STREAM_WARPS + warp) * LW + lane * KL + sl] = top[q].idx[sl];
       }
-      const long long o = ((long long)q * gridDim.x + blockIdx.x) * kout + r;
-      if (wok == 0) {
-        if (lane == 0) { cand_key[o] = -CUDART_INF_F; cand_idx[o] = -1; }
-      } else if (lane == wl) {
-        cand_key[o] = kv; cand_idx[o] = id;
-        ++ptr;
+    __syncthreads();
+    if (warp < nq) {
+      const int q = warp;
+      // lane w < STREAM_WARPS owns list w; k rounds of warp arg-best over the heads (key desc, id asc)
+      int ptr = 0;
+      const bool own = lane < STREAM_WARPS;
+      const float* mk = lk + (q * STREAM_WARPS + (own ? lane : 0)) * LW;
+      const int* mi = li + (q * STREAM_WARPS + (own ? lane : 0)) * LW;
+      for (int r = 0; r < kout; ++r) {
+        uint32_t ok = 0; int id = 0x7FFFFFFF; float kv = 0.f;
+        if (own && ptr < LW && mi[ptr] >= 0) { kv = mk[ptr]; ok = ordered_f32(kv); id = mi[ptr]; }
+        uint32_t wok = ok; int wid = id; int wl = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const uint32_t ook = __shfl_xor_sync(0xffffffffu, wok, o);
+          const int oid = __shfl_xor_sync(0xffffffffu, wid, o);
+          const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+          if (ook > wok || (ook == wok && oid < wid) || (ook == wok && oid == wid && ol < wl)) { wok = ook; wid = oid; wl = ol; }
+        }
+        const long long o = ((long long)q * gridDim.x + blockIdx.x) * kout + r;
+        if (wok == 0) {
+          if (lane == 0) { p.cand_key[o] = -CUDART_INF_F; p.cand_idx[o] = -1; }
+        } else if (lane == wl) {
+          p.cand_key[o] = kv; p.cand_idx[o] = id;
+          ++ptr;
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
+
+  // ---- the last block to finish produces the final result
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.ctl->ticket, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+
+  if (MODE != STREAM_FILTER) {
+    if (warp < nq) {
+      if (p.use_pivot_out) {
+        // sample pass: only the pivot (key of rank STREAM_PIVOT_RANK, -inf if the sample holds fewer rows)
+        float kth = -CUDART_INF_F;
+        merge_lists_warp<int>(p.cand_key, p.cand_idx, nullptr, warp, int(gridDim.x), kout, kout, 0, nullptr, 0, nullptr,
+                              nullptr, nullptr, nullptr, nullptr, lane, &kth);
+        if (lane == 0) p.ctl->pivot[warp] = kth;
+      } else {
+        merge_lists_warp<int>(p.cand_key, p.cand_idx, nullptr, warp, int(gridDim.x), kout, kout, p.metric_l2,
+                              s_qnorm, p.id_offset, p.labels, p.out_dist, p.out_idx, p.out_lbl, p.out_key, lane, nullptr);
+      }
+    }
+    if (p.run_if_fallback && threadIdx.x == 0) p.ctl->fallback = 0;
+  } else {
+    // FILTER: rank the appended candidates by counting (key desc, id asc); each of rank < kout writes its slot
+    uint32_t* ck = reinterpret_cast<uint32_t*>(sm);               // [STREAM_FCAP] ordered keys
+    int* ci = reinterpret_cast<int*>(sm) + STREAM_FCAP;           // [STREAM_FCAP]
+    bool failed = false;
+    for (int q = 0; q < nq; ++q) {
+      const int cnt = __ldcg(&p.ctl->fcount[q]);
+      if (cnt > STREAM_FCAP || cnt < min(kout, N)) { failed = true; continue; }
+      __syncthreads();
+      for (int i = threadIdx.x; i < cnt; i += STREAM_THREADS) {
+        ck[i] = ordered_f32(__ldcg(p.fkey + q * STREAM_FCAP + i));
+        ci[i] = __ldcg(p.fidx + q * STREAM_FCAP + i);
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < cnt; i += STREAM_THREADS) {
+        const uint32_t mk = ck[i];
+        const int mi = ci[i];
+        int rank = 0;
+        for (int j = 0; j < cnt; ++j) rank += (ck[j] > mk || (ck[j] == mk && ci[j] < mi)) ? 1 : 0;
+        if (rank < kout) {
+          const long long o = (long long)q * kout + rank;
+          const float kv = unordered_f32(mk);
+          if (p.out_dist) p.out_dist[o] = p.metric_l2 ? fmaxf(0.f, s_qnorm[q] - kv) : kv;
+          p.out_idx[o] = (long long)mi + p.id_offset;
+          if (p.out_key) p.out_key[o] = kv;
+          if (p.out_lbl) p.out_lbl[o] = p.labels ? p.labels[mi] : 0.f;
+        }
+      }
+      // fewer rows than kout in the whole index: pad (faiss convention)
+      for (int r = cnt + threadIdx.x; r < kout; r += STREAM_THREADS) {
+        const long long o = (long long)q * kout + r;
+        if (p.out_dist) p.out_dist[o] = p.metric_l2 ? CUDART_INF_F : -CUDART_INF_F;
+        p.out_idx[o] = -1;
+        if (p.out_key) p.out_key[o] = -CUDART_INF_F;
+        if (p.out_lbl) p.out_lbl[o] = 0.f;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) p.ctl->fallback = failed ? 1 : 0;
+    if (threadIdx.x < 4) p.ctl->fcount[threadIdx.x] = 0;
+  }
+  if (threadIdx.x == 0) p.ctl->ticket = 0;
 }
 
-constexpr size_t stream_smem_bytes(int nq_t, int ld, int kl) {
-  const size_t a = size_t(nq_t) * ld * 4, b = size_t(nq_t) * STREAM_WARPS * 32 * kl * 8;
+constexpr size_t stream_smem_bytes(int nq_t, int ld, int mode) {
+  const size_t a = size_t(nq_t) * ld * 4;
+  const size_t b = (mode == STREAM_FILTER) ? size_t(STREAM_FCAP) * 8
+                                           : size_t(nq_t) * STREAM_WARPS * 32 * (mode == STREAM_LIST4 ? 4 : 1) * 8;
   return a > b ? a : b;
 }
 

@@ -119,6 +119,10 @@ CASES = [
     ("stream_ip_bf16_q1_k100", 40000, 256, 1, 100, "IP", True, "bf16", "stream"),   # C5, Q = 1
     ("stream_l2_f32_q4_k128",  9000,  128, 4, 128, "L2", False, "f32", "stream"),
     ("stream_l2_bf16_q2_k33",  5001,  64,  2, 33,  "L2", False, "bf16", "stream"),
+    # large k on a large database: sampled pivot + filter pass (N >= 131072, k > 32)
+    ("stream_filter_cos_bf16_q1_k100", 200000, 128, 1, 100, "IP", True,  "bf16", "stream"),
+    ("stream_filter_l2_f32_q3_k64",    150000, 64,  3, 64,  "L2", False, "f32",  "stream"),
+    ("stream_filter_l2_f16_q4_k128",   140001, 72,  4, 128, "L2", False, "f16",  "stream"),
     # large k on the tensor cores: local-memory reservoir + exact bisection prune (C5: k = 100, D = 256)
     ("ip_bf16_tc_k100", 60000, 256, 300, 100, "IP", True,  "bf16", "tc"),
     ("l2_bf16_tc_k64",  20000, 128, 130, 64,  "L2", False, "bf16", "tc"),
@@ -172,6 +176,43 @@ def test_lattice_bit_exact_stream(pkg, name, store):
         D, I = idx.search(g["xq"][q0:q0 + nq], k, algo="stream")
         np.testing.assert_array_equal(I, g["idx"][q0:q0 + nq])
         np.testing.assert_array_equal(D, g["dist"][q0:q0 + nq])
+
+
+@pytest.mark.parametrize("store", ["bf16", "f32"])
+@pytest.mark.parametrize("metric_s", ["L2", "IP"])
+def test_stream_filter_fallback_on_heavy_ties(pkg, oracle, metric_s, store):
+    """Streaming scorer, large k, large N, lattice data: only a handful of distinct scores exist, so far more than the
+    4096 candidate slots tie with the sampled pivot -> the filter pass must raise its fallback flag and the list pass
+    must deliver the exact result (ids and distances bit-for-bit, lowest id on ties).  A second query set whose
+    candidates fit exercises the filter path itself, and repeating the calls checks the self-resetting counters."""
+    rng = np.random.default_rng(21)
+    N, Dm, k = 140000, 16, 50
+    xb = rng.integers(-1, 2, size=(N, Dm)).astype(np.float32)
+    xq = rng.integers(-1, 2, size=(3, Dm)).astype(np.float32)
+    metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
+    idx = pkg.FlatIndex(Dm, metric, store)
+    idx.add(xb)
+    ref = oracle.FlatIndexOracle(Dm, metric)
+    ref.add(xb)
+    Dr, Ir = ref.search(xq, k, direct=False)
+    for _ in range(2):
+        D, I = idx.search(xq, k, algo="stream")
+        np.testing.assert_array_equal(I, Ir)
+        np.testing.assert_array_equal(D, Dr)
+    # distinct scores: every row gets its own tiny integer offset in one extra-wide coordinate -> no ties at all
+    extra = np.zeros((N, 4), dtype=np.float32)
+    extra[:, 0] = np.arange(N, dtype=np.float32) % 4093
+    xb2 = np.concatenate([xb, extra], axis=1)
+    xq2 = np.concatenate([xq, np.ones((3, 4), dtype=np.float32)], axis=1)
+    idx2 = pkg.FlatIndex(Dm + 4, pkg.METRIC_IP, "f32")
+    idx2.add(xb2)
+    ref2 = oracle.FlatIndexOracle(Dm + 4, pkg.METRIC_IP)
+    ref2.add(xb2)
+    Dr2, Ir2 = ref2.search(xq2, k, direct=False)
+    for nq in (3, 1, 2):
+        D2, I2 = idx2.search(xq2[:nq], k, algo="stream")
+        np.testing.assert_array_equal(I2, Ir2[:nq])
+        np.testing.assert_array_equal(D2, Dr2[:nq])
 
 
 @pytest.mark.parametrize("metric_s", ["L2", "IP"])
