@@ -126,10 +126,12 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
                                                           float* __restrict__ out_dist,
                                                           long long* __restrict__ out_idx,
                                                           float* __restrict__ out_lbl,
-                                                          float* __restrict__ out_key) {
+                                                          float* __restrict__ out_key,
+                                                          const int* __restrict__ run_if = nullptr) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= Q) return;
+  if (run_if && __ldcg(run_if) == 0) return;
   merge_lists_warp<IdxT>(key_in, idx_in, lbl_in, q, L, kc, kout, metric_l2, qnorm, id_offset, labels, out_dist, out_idx,
                          out_lbl, out_key, lane, nullptr);
 }
@@ -199,6 +201,25 @@ __global__ void __launch_bounds__(128) rerank_exact_kernel(const long long* __re
     const bool ok = (nvalid >= ntotal) || (nvalid == kc && has && kth_key > approx_worst + bound);
     if (!ok) uncert_list[atomicAdd(uncert_count, 1)] = q;
   }
+}
+
+// ---- sampled pivot for the large-k tensor-core path (see launch_tc_pivoted in radad_flat.cu) ---------------------------
+// gthr[q] <- ordered(key of rank `rank` of the sample's merged list), 0 (= no bound) when the sample holds fewer rows
+__global__ void gthr_from_pivot_kernel(const float* __restrict__ sample_key, int Q, int kc, int rank,
+                                       uint32_t* __restrict__ gthr) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const float v = sample_key[(long long)q * kc + rank];
+  gthr[q] = (v > -CUDART_INF_F) ? ordered_f32(v) : 0u;
+}
+// flag <- 1 if any query ended with fewer than min(k, N) neighbours (the pivot was too high for it); gthr <- 0 so the
+// fallback launch starts without any bound
+__global__ void check_complete_kernel(const long long* __restrict__ out_idx, int Q, int k, int need,
+                                      uint32_t* __restrict__ gthr, int* __restrict__ flag) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  gthr[q] = 0u;
+  if (need > 0 && out_idx[(long long)q * k + need - 1] < 0) atomicExch(flag, 1);
 }
 
 // max over rows of |y|^2 (positive floats order like their bit patterns) -- feeds the re-rank certificate

@@ -85,6 +85,8 @@ struct rdb_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
   int last_algo = 0, last_S = 0;
+  bool tc_pivoted = false;        // last tensor-core search used the sampled pivot (needs the completeness check)
+  int tc_cg = 1, tc_nqg = 0, tc_S = 0, tc_tpc = 0, tc_ntiles = 0;
   int num_sms = 148;
   int64_t launches = 0;
   std::string err;
@@ -316,7 +318,8 @@ int launch_tc_cg(rdb_handle* h, TcParams& p, int k) {
 
 // nqg = query-tile GROUPS (128 * cg queries each); S chunks of tiles_per_chunk 256-row database tiles
 int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, int cg, int nqg, int S, int tiles_per_chunk,
-              int ntiles, int nterms, float* ck, int* ci) {
+              int ntiles, int nterms, float* ck, int* ci, int tile_step = 1, bool keep_gthr = false,
+              const int* run_if = nullptr) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -325,7 +328,9 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
   else p.tmap_q[1] = p.tmap_q[0];
   p.ynorm = h->ynorm; p.cand_key = ck; p.cand_idx = ci;
   CUDA_TRY(h, h->gthr.ensure(size_t(nq) * 4));
-  CUDA_TRY(h, cudaMemsetAsync(h->gthr.p, 0, size_t(nq) * 4, h->stream));
+  if (!keep_gthr) CUDA_TRY(h, cudaMemsetAsync(h->gthr.p, 0, size_t(nq) * 4, h->stream));
+  p.tile_step = tile_step; p.run_if = run_if;
+  p.astat = (nterms == 1 && h->d <= TcCfg<1>::ASTAT_MAX_KS * TC_BK && !getenv("RDB_TC_NO_ASTAT")) ? 1 : 0;
   p.gthr = (S > 1 || TC_LISTS > 1) ? h->gthr.as<uint32_t>() : nullptr;
   p.nq = nq; p.N = int(h->n); p.D = h->d;
   p.nqt = nqg; p.S = S; p.tiles_per_chunk = tiles_per_chunk; p.ntiles = ntiles; p.kout = k;
@@ -340,7 +345,7 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
     int window = 8;
     if (const char* v = getenv("RDB_TC_LOCKSTEP")) window = atoi(v);
     const int sync_groups = (tiles_per_chunk + TC_SYNC_GS - 1) / TC_SYNC_GS;
-    if (window > 0 && nqg >= ngroups && sync_groups > 2 * window) {
+    if (window > 0 && tile_step == 1 && nqg >= ngroups && sync_groups > 2 * window) {
       const size_t slots = size_t((p.num_units + ngroups - 1) / ngroups);
       const size_t bytes = slots * 2 * size_t(sync_groups) * 4;
       CUDA_TRY(h, h->tcsync.ensure(bytes));
@@ -360,6 +365,9 @@ constexpr int kMaxK = 128;
 constexpr int kMaxKTc = 128;       // k <= 32: register-resident list; 32 < k <= 128: local-memory reservoir
 constexpr int kMaxKSplit = 24;     // split-precision path keeps kc = 16 / 32 candidates: slack >= 6
 constexpr int64_t kMinRowsTc = 1024;
+constexpr int kTcSample = 64;          // large-k pivot: every 64th DB tile
+constexpr int kTcPivotRank = 16;       // ... and the sample's 16th best key
+constexpr int kTcPivotMinTiles = 1024; // >= 16 sampled tiles (N >= 262144)
 
 struct QueryView {
   const float* qf;    // fp32 [nq, D] (fp32 stores)
@@ -509,9 +517,35 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
     CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * TC_LISTS * kc * 4));
     CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * TC_LISTS * kc * 4));
     if (timed) cudaEventRecord(h->ev0, s);
+    const bool pivoted = kc > 32 && nterms == 1 && ntiles >= kTcPivotMinTiles && !getenv("RDB_TC_NO_PIVOT");
+    if (pivoted) {
+      // Large k: seed every query's admission bound from a strided 1/64 sample of the DB tiles (rank-16 key of the
+      // sample: ~1000 rows of the shard beat it), so the reservoirs admit ~1000 rows per query in total instead of
+      // k*ln(n/k) per work unit.  Exact whenever >= k rows pass; rdb checks that on the device (pivot_check below).
+      const int ntiles_s = (ntiles + kTcSample - 1) / kTcSample;
+      int tpc_s;
+      const int S_s = choose_splits(nqg, ntiles_s, h->num_sms / cg, 256 / TC_LISTS, 1, &tpc_s);
+      CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S_s * TC_LISTS * kTcPivotRank * 4));
+      CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S_s * TC_LISTS * kTcPivotRank * 4));
+      CUDA_TRY(h, h->rr_key.ensure(size_t(qv.nq) * kTcPivotRank * 4));
+      if ((rc = launch_tc(h, qv.qhi, qv.qlo, qv.nq, kTcPivotRank, cg, nqg, S_s, tpc_s, ntiles_s, 1,
+                          h->cand_key.as<float>(), h->cand_idx.as<int>(), kTcSample))) return rc;
+      {
+        const int warps = 4;
+        dim3 grid((qv.nq + warps - 1) / warps), block(32 * warps);
+        merge_lists_kernel<int><<<grid, block, 0, s>>>(h->cand_key.as<float>(), h->cand_idx.as<int>(), nullptr, qv.nq,
+                                                       S_s * TC_LISTS, kTcPivotRank, kTcPivotRank, 0, nullptr, 0, nullptr,
+                                                       nullptr, nullptr, nullptr, h->rr_key.as<float>());
+        gthr_from_pivot_kernel<<<(qv.nq + 255) / 256, 256, 0, s>>>(h->rr_key.as<float>(), qv.nq, kTcPivotRank,
+                                                                   kTcPivotRank - 1, h->gthr.as<uint32_t>());
+        h->launches += 2;
+        CUDA_TRY(h, cudaGetLastError());
+      }
+    }
     if ((rc = launch_tc(h, qv.qhi, qv.qlo, qv.nq, kc, cg, nqg, S, tpc, ntiles, nterms, h->cand_key.as<float>(),
-                        h->cand_idx.as<int>()))) return rc;
+                        h->cand_idx.as<int>(), 1, pivoted))) return rc;
     if (timed) cudaEventRecord(h->ev1, s);
+    h->tc_pivoted = pivoted; h->tc_cg = cg; h->tc_nqg = nqg; h->tc_S = S; h->tc_tpc = tpc; h->tc_ntiles = ntiles;
     *L_out = S * TC_LISTS;
   } else {
     const int ntiles = int((h->n + SIMT_BN - 1) / SIMT_BN);
@@ -530,13 +564,14 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
 
 // fold the local candidate lists: final form (dist or key, global id, label)
 int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float* qnorm, bool shard_mode, float* d_a,
-                    int64_t* d_i, float* d_l, long long id_offset, const float* labels, float* raw_key) {
+                    int64_t* d_i, float* d_l, long long id_offset, const float* labels, float* raw_key,
+                    const int* run_if = nullptr) {
   const int warps = 4;
   dim3 grid((nq + warps - 1) / warps), block(32 * warps);
   merge_lists_kernel<int><<<grid, block, 0, h->stream>>>(
       h->cand_key.as<float>(), h->cand_idx.as<int>(), nullptr, nq, L, kc, kout, h->metric == RDB_METRIC_L2 ? 1 : 0,
       qnorm, id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l,
-      shard_mode ? d_a : raw_key);
+      shard_mode ? d_a : raw_key, run_if);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return RDB_OK;
@@ -614,9 +649,24 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
     int L = 0;
     if (!split) {
       // ---- score + select, then merge
+      h->tc_pivoted = false;
       if (h->n > 0 && (rc = run_scorer(h, algo, 1, qv, k, &L, true))) return rc;
       if ((rc = run_merge_local(h, nb, L, k, k, qv.qnorm, shard_mode, d_a, d_i, d_l, h->id_offset, labels, nullptr)))
         return rc;
+      if (h->tc_pivoted) {
+        // every query must have found min(k, n) rows above its sampled pivot; otherwise (flag) the two launches below
+        // redo the batch without any bound -- they exit at once when the flag is clear (the normal case)
+        CUDA_TRY(h, h->uncert.ensure(8));
+        int* flag = h->uncert.as<int>();
+        CUDA_TRY(h, cudaMemsetAsync(flag, 0, 4, s));
+        check_complete_kernel<<<(nb + 255) / 256, 256, 0, s>>>(reinterpret_cast<const long long*>(d_i), nb, k,
+                                                              int(std::min<int64_t>(k, h->n)), h->gthr.as<uint32_t>(), flag);
+        h->launches++;
+        if ((rc = launch_tc(h, qv.qhi, qv.qlo, nb, k, h->tc_cg, h->tc_nqg, h->tc_S, h->tc_tpc, h->tc_ntiles, 1,
+                            h->cand_key.as<float>(), h->cand_idx.as<int>(), 1, true, flag))) return rc;
+        if ((rc = run_merge_local(h, nb, L, k, k, qv.qnorm, shard_mode, d_a, d_i, d_l, h->id_offset, labels, nullptr,
+                                  flag))) return rc;
+      }
     } else {
       // ---- split-precision tensor-core pass keeping kc > k candidates
       const int kc = (k <= 10) ? 16 : 32;

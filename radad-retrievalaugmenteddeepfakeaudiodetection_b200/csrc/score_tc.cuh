@@ -40,6 +40,15 @@ template <int CG> struct TcCfg {
   static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + 256 + 1024;
+  // Query-stationary form (D <= 256, one MMA term): the whole 128 x D query tile (<= 4 K-slices = 64 KB) is loaded
+  // ONCE per work unit and stays in shared memory; the ring then holds database slices only (twice as many stages in
+  // the same shared memory).  A third less L2->SM operand traffic and half the TMA / mbarrier operations per tile --
+  // what matters at D = 256, where a tile is only 16 MMAs long.
+  static constexpr int ASTAT_MAX_KS = 4;
+  static constexpr int ASTAT_A_BYTES = ASTAT_MAX_KS * TC_A_BYTES;
+  static constexpr int ASTAT_STAGES = (STAGES * STAGE_BYTES - ASTAT_A_BYTES) / B_BYTES;
+  static constexpr int MAX_STAGES = ASTAT_STAGES > STAGES ? ASTAT_STAGES : STAGES;
+  static_assert(MAX_STAGES * 16 + 6 * 8 + 8 <= 256, "barrier block");
 };
 constexpr int TC_EPI_WARPS = 8;        // two per TMEM lane quarter: each takes one half of the 256 columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
@@ -62,6 +71,9 @@ struct TcParams {
   // Lock-step window (see tc_lockstep_* below): progress counters [slot][2][sync_groups], or null = off
   uint32_t* sync;
   int sync_groups, sync_window;
+  int tile_step;            // 1 = every DB tile; > 1: strided sample pass (tile index t stands for tile t * tile_step)
+  int astat;                // query-stationary form (host: nterms == 1 && D <= 256)
+  const int* run_if;        // fallback launch: all CTAs exit at once unless *run_if != 0 (null = always run)
 };
 
 // ---- lock-step window ----------------------------------------------------------------------------------------------
@@ -180,15 +192,23 @@ template <class Sel, bool L2, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __grid_constant__ TcParams p) {
   using Cfg = TcCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
+  if (p.run_if && __ldcg(p.run_if) == 0) return;     // uniform across the grid (and both CTAs of a pair)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
+  const bool astat = p.astat != 0;
+  const int nst = astat ? Cfg::ASTAT_STAGES : STAGES;                 // ring depth
+  const int ring_stride = astat ? Cfg::B_BYTES : Cfg::STAGE_BYTES;    // bytes per ring slot
+  uint8_t* ring = smem + (astat ? Cfg::ASTAT_A_BYTES : 0);            // slot s: [A slice |] B slice
+  const int b_off = astat ? 0 : TC_A_BYTES;                           // offset of the B slice inside a slot
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + Cfg::MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* afull_bar = tempty_bar + 2;                               // query tile resident (astat)
+  uint64_t* aempty_bar = afull_bar + 1;                               // query tile no longer read by any MMA (astat)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aempty_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -201,8 +221,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_q[0]);
     tma_prefetch_desc(&p.tmap_y[0]);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < Cfg::MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS * CG); }
+    mbar_init(afull_bar, 1); mbar_init(aempty_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -220,7 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, aphase = 0;
       int slot = 0;
       for (int unit = group; unit < p.num_units; unit += ngroups, ++slot) {
         const int qtile = (unit % p.nqt) * CG + rank, chunk = unit / p.nqt;
@@ -234,6 +255,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
         bool waiting = counted;
         uint32_t* ctr = p.sync + (size_t(slot) * 2 + size_t(chunk - (slot * ngroups) / p.nqt)) * p.sync_groups;
         uint32_t seen = 0;
+        if (astat) {
+          // the unit's query tile: loaded once, after every MMA of the previous unit has retired
+          mbar_wait(aempty_bar, aphase ^ 1);
+          if (CG == 2) {
+            if (rank == 0) mbar_expect_tx(afull_bar, 2 * nks * TC_A_BYTES);
+            for (int ks = 0; ks < nks; ++ks)
+              tma_load_2d_pair(smem + ks * TC_A_BYTES, &p.tmap_q[0], afull_bar, ks * TC_BK, qtile * TC_BM, p.hint_q);
+          } else {
+            mbar_expect_tx(afull_bar, nks * TC_A_BYTES);
+            for (int ks = 0; ks < nks; ++ks)
+              tma_load_2d(smem + ks * TC_A_BYTES, &p.tmap_q[0], afull_bar, ks * TC_BK, qtile * TC_BM, p.hint_q);
+          }
+          aphase ^= 1;
+        }
         for (int t = t0; t < t1; ++t) {
           if (counted) {
             const int tau = t - t0, g = tau / TC_SYNC_GS;
@@ -254,19 +289,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
             const int ysel = (p.nterms == 3 && term == 1) ? 1 : 0;
             for (int ks = 0; ks < nks; ++ks) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              uint8_t* sa = ring + stage * ring_stride;
+              const int slot_bytes = astat ? Cfg::B_BYTES : Cfg::STAGE_BYTES;
               if (CG == 2) {
                 // both CTAs' bytes complete on the leader's barrier; the leader posts the expectation for both
-                if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                tma_load_2d_pair(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
-                tma_load_2d_pair(sa + TC_A_BYTES, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK,
-                                 t * TC_BN + rank * Cfg::B_ROWS, p.hint_y);
+                if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * slot_bytes);
+                if (!astat) tma_load_2d_pair(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
+                tma_load_2d_pair(sa + b_off, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK,
+                                 t * p.tile_step * TC_BN + rank * Cfg::B_ROWS, p.hint_y);
               } else {
-                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                tma_load_2d(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
-                tma_load_2d(sa + TC_A_BYTES, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK, t * TC_BN, p.hint_y);
+                mbar_expect_tx(&full_bar[stage], slot_bytes);
+                if (!astat) tma_load_2d(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
+                tma_load_2d(sa + b_off, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK, t * p.tile_step * TC_BN, p.hint_y);
               }
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              if (++stage == nst) { stage = 0; phase ^= 1; }
             }
           }
           if (counted && (t - t0) % TC_SYNC_GS == TC_SYNC_GS - 1) red_add_u32(ctr + (t - t0) / TC_SYNC_GS);
@@ -277,10 +313,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
     // ------------------------------------------------------------------ MMA issuer (single thread; leader CTA only)
     if (lane == 0 && rank == 0) {
       int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      uint32_t phase = 0, acc_phase = 0, aphase = 0;
       for (int unit = group; unit < p.num_units; unit += ngroups) {
         const int chunk = unit / p.nqt;
         const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
+        if (astat) { mbar_wait(afull_bar, aphase); tc_fence_after(); aphase ^= 1; }
         for (int t = t0; t < t1; ++t) {
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
@@ -289,9 +326,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
           for (int ks = 0; ks < nslices; ++ks) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-            const uint64_t da = make_sw128_kmajor_desc(sa);
-            const uint64_t db = make_sw128_kmajor_desc(sa + TC_A_BYTES);
+            const uint32_t sa = smem_u32(ring + stage * ring_stride);
+            const uint64_t da = make_sw128_kmajor_desc(astat ? smem_u32(smem + ks * TC_A_BYTES) : sa);
+            const uint64_t db = make_sw128_kmajor_desc(sa + b_off);
 #pragma unroll
             for (int kk = 0; kk < TC_BK / 16; ++kk) {
               // +32 bytes per K=16 step inside the 128-byte swizzle atom (descriptor address unit = 16 B)
@@ -300,13 +337,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
             }
             // frees the smem slot (in both CTAs of a pair) when these MMAs retire
             if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == nst) { stage = 0; phase ^= 1; }
           }
           // accumulator complete -> epilogue (of both CTAs of a pair)
           if (CG == 2) umma_commit_pair(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
+        // every MMA that reads this unit's query tile has been issued: release it when they retire
+        if (astat) { if (CG == 2) umma_commit_pair(aempty_bar); else umma_commit(aempty_bar); }
       }
     }
   } else {
@@ -326,7 +365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * TC_BN + half * (TC_BN / 2));
-        const int n0 = t * TC_BN + half * (TC_BN / 2);
+        const int n0 = t * p.tile_step * TC_BN + half * (TC_BN / 2);
         const int nvalid = p.N - n0;         // >= 128 for full tiles
         if (p.dbg & 1) {
           tc_fence_before();

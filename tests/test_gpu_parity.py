@@ -128,6 +128,9 @@ CASES = [
     ("l2_bf16_tc_k64",  20000, 128, 130, 64,  "L2", False, "bf16", "tc"),
     ("l2_bf16_tc_k128", 9000,  96,  40,  128, "L2", False, "bf16", "tc"),
     ("ip_f16_tc_k33",   5000,  64,  33,  33,  "IP", False, "f16",  "tc"),
+    # large k on a large shard: admission bound seeded from a strided 1/64 tile sample (N >= 262144)
+    ("ip_bf16_tc_k100_pivot", 300000, 64, 200, 100, "IP", True,  "bf16", "tc"),
+    ("l2_bf16_tc_k64_pivot",  280003, 40, 140, 64,  "L2", False, "bf16", "tc"),
 ]
 
 
@@ -176,6 +179,36 @@ def test_lattice_bit_exact_stream(pkg, name, store):
         D, I = idx.search(g["xq"][q0:q0 + nq], k, algo="stream")
         np.testing.assert_array_equal(I, g["idx"][q0:q0 + nq])
         np.testing.assert_array_equal(D, g["dist"][q0:q0 + nq])
+
+
+@pytest.mark.parametrize("metric_s", ["L2", "IP"])
+def test_tc_pivot_fallback_when_sample_overestimates(pkg, oracle, metric_s):
+    """Large-k tensor-core path with the sampled admission bound: 20 copies of a query sit in the FIRST (sampled) tile,
+    so the sample's 16th best key is the exact-match score and only 20 < k rows of the whole shard reach it.  The
+    device-side completeness check must then rerun the batch without the bound; the other queries (heavy lattice ties)
+    take the normal path.  Ids and distances must equal the oracle bit-for-bit either way."""
+    rng = np.random.default_rng(5)
+    N, Dm, Q, k = 270000, 32, 150, 50
+    xb = rng.integers(-2, 3, size=(N, Dm)).astype(np.float32)
+    xq = rng.integers(-2, 3, size=(Q, Dm)).astype(np.float32)
+    special = np.full((Dm,), 2.0, dtype=np.float32)
+    special[::2] = -2.0
+    xb[:20] = special
+    xq[7] = special
+    metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
+    idx = pkg.FlatIndex(Dm, metric, "bf16")
+    idx.add(xb)
+    ref = oracle.FlatIndexOracle(Dm, metric)
+    ref.add(xb)
+    Dr, Ir = ref.search(xq, k, direct=False)
+    for _ in range(2):
+        D, I = idx.search(xq, k, algo="tc")
+        np.testing.assert_array_equal(I, Ir)
+        np.testing.assert_array_equal(D, Dr)
+    np.testing.assert_array_equal(Ir[7, :20], np.arange(20))
+    D2, I2 = idx.search(xq[8:140], k, algo="tc")                  # no special query: the bound holds, no rerun
+    np.testing.assert_array_equal(I2, Ir[8:140])
+    np.testing.assert_array_equal(D2, Dr[8:140])
 
 
 @pytest.mark.parametrize("store", ["bf16", "f32"])
