@@ -197,6 +197,55 @@ def c5():
     idx.close()
 
 
+def refscale():
+    """Reference scale R: N = 25 423, D = 5376 (7 x 768 TPP), one training batch of Q = 256 queries,
+    K = 5 neighbours of the K + 10 searched, L2 fp32 -- the whole caller step pipeline.py:449-532 (search + rank-ordered
+    self-exclusion + gather of [B, K, D] neighbours + labels), device tensors in and out, against the caller restated
+    on the CPU port (oracle index + the reference's Python double loop)."""
+    import tempfile
+
+    class Cfg:
+        vector_db_path = tempfile.mkdtemp()
+        vector_db_index_type = "L2"
+        top_k = 5
+        use_float16 = False
+        vector_add_batch_size = 10000
+
+    N, Dm, Q, K = 25423, 5376, 256, 5
+    xb = gen(N, Dm, 1234).cpu().numpy()
+    paths = [f"/data/spk{i % 97}/utt_{i:06d}.wav" for i in range(N)]
+    labels = [int(i % 2) for i in range(N)]
+    q = torch.from_numpy(xb[:Q] + 0.05 * gen(Q, Dm, 5678).cpu().numpy()).cuda()
+    qpaths = paths[:Q]                                         # the batch's own files are in the DB: exclusion matters
+    for store in ("f32", "bf16"):
+        cfg = Cfg()
+        cfg.db_dtype = store
+        vdb = pkg.VectorDatabase(cfg)
+        vdb.add_vectors(xb, paths, labels, {"speaker_id": [p.split("/")[2] for p in paths]})
+
+        def step():
+            out = pkg.retrieve_similar_vectors(vdb, q, K, query_paths=qpaths, exclude_self=True, return_distances=True)
+            return out
+        dt, out = timed(step, 20, warm=3)
+        emit(config=f"R: retrieve_similar_vectors, N=25423 D=5376 Q=256 K=5(+10) L2, store {store}, device in/out",
+             ms=dt * 1e3, batches_per_s=1.0 / dt, scorer=vdb.index.last_kernel_ms()[1],
+             search_kernel_ms=vdb.index.last_kernel_ms()[0])
+        if store == "f32":
+            ours = [t.cpu().numpy() for t in out]
+        vdb.index.close()
+    torch.set_num_threads(os.cpu_count())
+    ovdb = orc.OracleVectorDatabase(Cfg())
+    ovdb.add_vectors(xb, paths, labels, {"speaker_id": [p.split("/")[2] for p in paths]})
+    qn = q.cpu().numpy()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        v, l, p_, d = orc.retrieve_similar_vectors_oracle(ovdb, qn, K, Dm, query_paths=qpaths, exclude_self=True)
+    dt = (time.perf_counter() - t0) / 3
+    same = bool(np.array_equal(ours[1], l)) and bool(np.allclose(ours[0], v, rtol=0, atol=0))
+    emit(config="R: the same caller step on the CPU port (oracle index, reference's Python loop)", cores=os.cpu_count(),
+         ms=dt * 1e3, batches_per_s=1.0 / dt, neighbours_and_labels_identical_to_gpu_f32=same)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c1", "ingest", "c4", "c2"]
     for w in which:
