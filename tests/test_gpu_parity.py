@@ -588,3 +588,38 @@ def test_vector_database_on_several_gpus(pkg, tmp_path):
     again.load()
     D2, I2 = again.search_batch(g["xq"], k=15)
     np.testing.assert_array_equal(I2, I0)
+
+
+def test_random_shapes_lattice_fuzz(pkg, oracle):
+    """Seeded fuzz over shapes / metrics / stores / k / batch sizes on lattice data (exact arithmetic in every store
+    dtype): whatever scorer AUTO picks (stream, tensor cores incl. query-stationary and split-precision forms, exact
+    CUDA cores) must return the oracle's ids and distances bit-for-bit, lowest id on ties.  Covers ragged N, D not a
+    multiple of 8 / 64, nq around the 128-query tile boundary, k = 1, k > 32, k > N clamped by the caller."""
+    rng = np.random.default_rng(20261018)
+    for trial in range(36):
+        N = int(rng.choice([257, 1000, 4097, 9001, 20011]))
+        Dm = int(rng.choice([8, 20, 64, 100, 192, 256, 260, 520]))
+        nq = int(rng.choice([1, 3, 4, 5, 64, 127, 129, 257]))
+        k = int(rng.choice([1, 5, 10, 16, 17, 32, 33, 100]))
+        store = str(rng.choice(["f32", "bf16", "f16"]))
+        metric_s = str(rng.choice(["L2", "IP"]))
+        if store == "f32" and Dm % 4 != 0 and nq <= 4:
+            Dm += 4 - Dm % 4
+        k = min(k, N)
+        metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
+        xb = rng.integers(-2, 3, size=(N, Dm)).astype(np.float32)
+        xq = rng.integers(-2, 3, size=(nq, Dm)).astype(np.float32)
+        xb[N // 2] = xb[1]
+        xq[0] = xb[1]
+        idx = pkg.FlatIndex(Dm, metric, store)
+        cut = int(rng.integers(1, N))
+        idx.add(xb[:cut])
+        idx.add(xb[cut:])
+        D, I = idx.search(xq, k)
+        ref = oracle.FlatIndexOracle(Dm, metric)
+        ref.add(xb)
+        Dr, Ir = ref.search(xq, k, direct=False)
+        tag = f"trial {trial}: N={N} D={Dm} nq={nq} k={k} {store} {metric_s} scorer={idx.last_kernel_ms()[1]}"
+        np.testing.assert_array_equal(I, Ir, err_msg=tag)
+        np.testing.assert_array_equal(D, Dr, err_msg=tag)
+        idx.close()
