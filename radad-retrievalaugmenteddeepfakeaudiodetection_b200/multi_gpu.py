@@ -52,6 +52,8 @@ class MultiGpuFlatIndex:
             self.shards[0].enable_peer_access(g)        # the merge kernel on the primary reads every shard's lists
         self.nprobe = 1
         self._ntotal = 0
+        self._pool = None                               # host threads driving the shards (fp32 stores only)
+        self._cap = [0] * len(self.devices)            # rows reserved per shard (grown geometrically, before any add)
         # per shard: parallel lists of segment (local_start, global_start, count), ascending in both
         self._seg: List[List[Tuple[int, int, int]]] = [[] for _ in self.devices]
         self._seg_dev = [None] * len(self.devices)      # device copies (local_starts, deltas), rebuilt lazily
@@ -95,8 +97,16 @@ class MultiGpuFlatIndex:
 
     def reserve(self, n_total: int) -> None:
         per = -(-int(n_total) // len(self.shards))
-        for s in self.shards:
-            s.reserve(max(per, 1))
+        for g in range(len(self.shards)):
+            self._reserve_shard(g, max(per, 1))
+
+    def _reserve_shard(self, g: int, need: int) -> None:
+        """Make room for `need` rows on shard g (x1.5 growth).  All shards of an add() are reserved BEFORE any row is
+        stored, so an out-of-memory failure leaves the index exactly as it was (faiss `add` is all-or-nothing too)."""
+        if need > self._cap[g]:
+            cap = max(need, self._cap[g] + self._cap[g] // 2)
+            self.shards[g].reserve(cap)
+            self._cap[g] = cap
 
     # ------------------------------------------------------------------ ingest
     def _plan(self, n: int) -> List[Tuple[int, int]]:
@@ -121,8 +131,14 @@ class MultiGpuFlatIndex:
         n = int(x.shape[0])
         if x.ndim != 2 or int(x.shape[1]) != self._d:
             raise RuntimeError(f"expected float32 [n, {self._d}], got {tuple(x.shape)}")
+        plan = self._plan(n)
+        want = {}
+        for g, cnt in plan:
+            want[g] = want.get(g, 0) + cnt
+        for g, cnt in want.items():
+            self._reserve_shard(g, self.shards[g].ntotal + cnt)
         r0 = 0
-        for g, cnt in self._plan(n):
+        for g, cnt in plan:
             piece = x[r0:r0 + cnt]
             shard = self.shards[g]
             if _is_cuda_tensor(piece):
@@ -201,21 +217,30 @@ class MultiGpuFlatIndex:
             raise RuntimeError("search on an empty index")
         # 1) broadcast the queries first: torch runs a cross-device copy on the SOURCE device's stream, so a copy issued
         #    after the primary's own search had been enqueued would wait for it and serialise the GPUs
-        qs = {}
+        qs, streams = {}, {}
         for g in live:
             dev = torch.device("cuda", self.devices[g])
             qs[g] = qp if dev == prim else qp.to(dev, non_blocking=True)        # P2P over NVLink
-        # 2) every GPU searches its shard concurrently (asynchronous launches on each device's current stream)
-        keys, gids, labs, events, qn_first = [], [], [], [], None
-        for g in live:
-            with torch.cuda.device(self.devices[g]):
+            streams[g] = torch.cuda.current_stream(dev)     # the caller's stream (current streams are thread-local)
+        # 2) every GPU searches its shard concurrently.  16-bit stores are fully asynchronous (the launches return at
+        #    once); the certified fp32 path reads one counter back per batch, so each shard is driven from its own
+        #    host thread (ctypes releases the GIL inside the C call) and no GPU waits for another one's round trip.
+        def run(g):
+            with torch.cuda.device(self.devices[g]), torch.cuda.stream(streams[g]):
                 key, lid, lab, qn = self.shards[g].search_shard(qs[g], k, normalize=normalize)
                 gid = self._local_to_global(g, lid)
                 ev = torch.cuda.Event()
                 ev.record()
-            keys.append(key); gids.append(gid); labs.append(lab); events.append(ev)
-            if qn_first is None:
-                qn_first = qn
+            return key, gid, lab, qn, ev
+        if len(live) > 1 and self.store == "f32":
+            if self._pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._pool = ThreadPoolExecutor(max_workers=len(self.shards), thread_name_prefix="rdb-shard")
+            results = list(self._pool.map(run, live))
+        else:
+            results = [run(g) for g in live]
+        keys, gids, labs = [r[0] for r in results], [r[1] for r in results], [r[2] for r in results]
+        events, qn_first = [r[4] for r in results], results[0][3]
         with torch.cuda.device(prim):
             ps = torch.cuda.current_stream()
             for ev in events:
@@ -335,6 +360,7 @@ class MultiGpuFlatIndex:
 
     def _add_to_shard(self, g: int, rows: np.ndarray) -> None:
         shard, cnt = self.shards[g], rows.shape[0]
+        self._reserve_shard(g, shard.ntotal + cnt)
         shard.add(rows)
         local0 = shard.ntotal - cnt
         seg = self._seg[g]
@@ -348,6 +374,9 @@ class MultiGpuFlatIndex:
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:
+        if getattr(self, "_pool", None) is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
         for s in self.shards:
             s.close()
 

@@ -20,13 +20,14 @@ D = int(os.environ.get("RDB_BENCH_D", 768))
 Q = int(os.environ.get("RDB_BENCH_Q", 65536))
 K = int(os.environ.get("RDB_BENCH_K", 10))
 STEPS = int(os.environ.get("RDB_BENCH_STEPS", 5))
+DTYPE = os.environ.get("RDB_BENCH_DTYPE", "bf16")
 
 
 class Cfg:
     vector_db_path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"rdb_sp_{os.getpid()}")
     vector_db_index_type = "IP"
     top_k = K
-    db_dtype = "bf16"
+    db_dtype = DTYPE
     db_devices = "all"
 
 
@@ -62,7 +63,7 @@ def main():
     torch.cuda.synchronize(0)
     dt_dev = (time.perf_counter() - t0) / STEPS
     print(json.dumps({"what": "single-process multi-GPU VectorDatabase.search_batch (host numpy in/out)",
-                      "workload": f"{N}x{D} bf16, {Q} queries, k={K}, cosine", "n_gpus": G,
+                      "workload": f"{N}x{D} {DTYPE}, {Q} queries, k={K}, cosine", "n_gpus": G,
                       "shard_sizes": idx.shard_sizes if hasattr(idx, "shard_sizes") else [idx.ntotal],
                       "e2e_qps": Q / dt, "e2e_ms": dt * 1e3, "device_qps": Q / dt_dev, "device_ms": dt_dev * 1e3,
                       "kernel_ms_max": idx.last_kernel_ms()[0],
