@@ -623,3 +623,40 @@ def test_random_shapes_lattice_fuzz(pkg, oracle):
         np.testing.assert_array_equal(I, Ir, err_msg=tag)
         np.testing.assert_array_equal(D, Dr, err_msg=tag)
         idx.close()
+
+
+@pytest.mark.parametrize("store,algo", [("bf16", "tc"), ("f32", "tc"), ("f32", "simt"), ("bf16", "stream")])
+def test_clustered_distribution_with_duplicates_and_vote(pkg, oracle, store, algo):
+    """SURVEY 8(d) Dist-B: rows = centroid + 0.3 N(0,1) around 512 centroids, label = centroid id mod 2, queries =
+    perturbed database rows with exact duplicates of database rows mixed in (distance 0 / self-match, the case the
+    caller's exclude-self depth K + 10 exists for).  Ids within the stated tolerance, labels = labels[ids], and the kNN
+    label vote equals the sum of the first K neighbour labels."""
+    rng = np.random.default_rng(77)
+    N, Dm, Q, k, K = 40000, 128, 4 if algo == "stream" else 300, 15, 5
+    cent = rng.standard_normal((512, Dm)).astype(np.float32)
+    cid = rng.integers(0, 512, size=N)
+    xb = (cent[cid] + 0.3 * rng.standard_normal((N, Dm))).astype(np.float32)
+    labels = (cid % 2).astype(np.float32)
+    src = rng.integers(0, N, size=Q)
+    xq = (xb[src] + 0.1 * rng.standard_normal((Q, Dm))).astype(np.float32)
+    dup = np.arange(0, Q, 3)
+    xq[dup] = xb[src[dup]]                                     # exact duplicates of database rows
+    idx = pkg.FlatIndex(Dm, pkg.METRIC_L2, store)
+    idx.add(xb)
+    idx.set_labels(labels)
+    D, I, L = idx.search(xq, k, algo=algo, return_labels=True)
+    ref = oracle.FlatIndexOracle(Dm, pkg.METRIC_L2, store=store)
+    ref.add(xb)
+    Dr, Ir = ref.search(xq, k + 8, direct=False)
+    scale = float((xq * xq).sum(1).max() + (xb * xb).sum(1).max())
+    floor = (2e-6 if (store == "f32") else 1e-4) * scale
+    st = oracle.compare_topk(D, I, Dr, Ir, lambda ids: ref.exact_scores(xq, ids), pkg.METRIC_L2, tol=TOL_F32 if store == "f32" else TOL_BF16, abs_floor=floor)
+    assert st["recall"] >= 0.999, st
+    np.testing.assert_array_equal(I[dup, 0], src[dup])         # the duplicate finds its own row first ...
+    assert float(D[dup, 0].max()) <= floor                     # ... at distance ~0
+    np.testing.assert_array_equal(L, labels[I])
+    vote = idx.label_vote(L, K)
+    np.testing.assert_allclose(vote, labels[I][:, :K].sum(1))
+    # same-cluster neighbours dominate: the vote agrees with the query's own cluster label for almost every query
+    agree = np.mean((vote >= (K + 1) // 2) == (labels[src] > 0.5))
+    assert agree > 0.95, agree
