@@ -222,6 +222,18 @@ __global__ void check_complete_kernel(const long long* __restrict__ out_idx, int
   if (need > 0 && out_idx[(long long)q * k + need - 1] < 0) atomicExch(flag, 1);
 }
 
+// min |y|^2 over aligned groups of 32 rows: out[g0 + i] for i < ngroups (one warp per group).  Lets the tcgen05
+// epilogue reject a whole 32-column group in the L2 metric with one compare: key_j = 2 s_j - |y_j|^2 <= 2 max(s) - min.
+__global__ void ynorm_min32_kernel(const float* __restrict__ ynorm, long long g0, long long ngroups,
+                                   float* __restrict__ out) {
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= ngroups) return;
+  float m = ynorm[(g0 + w) * 32 + (threadIdx.x & 31)];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) out[g0 + w] = m;
+}
+
 // max over rows of |y|^2 (positive floats order like their bit patterns) -- feeds the re-rank certificate
 __global__ void ynorm_max_kernel(const float* __restrict__ ynorm, long long n, float* __restrict__ out) {
   float m = 0.f;

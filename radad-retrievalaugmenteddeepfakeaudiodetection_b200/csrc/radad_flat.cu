@@ -80,6 +80,7 @@ struct rdb_handle {
   void* hi = nullptr;
   void* lo = nullptr;
   float* ynorm = nullptr;
+  float* ynmin32 = nullptr;       // [cap / 32] min |y|^2 over each aligned group of 32 rows (L2 coarse filter of the tcgen05 epilogue)
   float* labels = nullptr;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -136,13 +137,14 @@ int grow_to(rdb_handle* h, int64_t need, bool exact = false) {
   cap = round_up(std::max<int64_t>(cap, 256), 256);
   if (cap >= (int64_t(1) << 31)) return fail(h, RDB_ERR_UNSUPPORTED, "more than 2^31-1 rows per shard");
   const size_t D = h->d, Dp = h->dp;
-  float* master = nullptr; void* hi = nullptr; void* lo = nullptr; float* ynorm = nullptr;
-  auto cleanup = [&] { cudaFree(master); cudaFree(hi); cudaFree(lo); cudaFree(ynorm); cudaGetLastError(); };
+  float* master = nullptr; void* hi = nullptr; void* lo = nullptr; float* ynorm = nullptr; float* ynmin32 = nullptr;
+  auto cleanup = [&] { cudaFree(master); cudaFree(hi); cudaFree(lo); cudaFree(ynorm); cudaFree(ynmin32); cudaGetLastError(); };
   cudaError_t e = cudaSuccess;
   if (h->has_master()) e = cudaMalloc(&master, size_t(cap) * D * 4);
   if (e == cudaSuccess) e = cudaMalloc(&hi, size_t(cap) * Dp * 2);
   if (e == cudaSuccess && h->has_lo()) e = cudaMalloc(&lo, size_t(cap) * Dp * 2);
   if (e == cudaSuccess) e = cudaMalloc(&ynorm, size_t(cap) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&ynmin32, size_t(cap / 32) * 4);
   if (e != cudaSuccess) {
     cleanup();
     return fail(h, RDB_ERR_NOMEM, std::string("device allocation for ") + std::to_string(cap) + " rows failed: " +
@@ -156,10 +158,12 @@ int grow_to(rdb_handle* h, int64_t need, bool exact = false) {
     cudaMemcpyAsync(ynorm, h->ynorm, size_t(h->n) * 4, cudaMemcpyDeviceToDevice, s);
   }
   cudaMemsetAsync(ynorm + h->n, 0, size_t(cap - h->n) * 4, s);
+  cudaMemsetAsync(ynmin32, 0, size_t(cap / 32) * 4, s);
+  if (h->n > 0) cudaMemcpyAsync(ynmin32, h->ynmin32, size_t((h->n + 31) / 32) * 4, cudaMemcpyDeviceToDevice, s);
   cudaError_t es = cudaStreamSynchronize(s);
   if (es != cudaSuccess) { cleanup(); return fail(h, RDB_ERR_CUDA, std::string("grow copy: ") + cudaGetErrorString(es)); }
-  cudaFree(h->master); cudaFree(h->hi); cudaFree(h->lo); cudaFree(h->ynorm);
-  h->master = master; h->hi = hi; h->lo = lo; h->ynorm = ynorm; h->cap = cap;
+  cudaFree(h->master); cudaFree(h->hi); cudaFree(h->lo); cudaFree(h->ynorm); cudaFree(h->ynmin32);
+  h->master = master; h->hi = hi; h->lo = lo; h->ynorm = ynorm; h->ynmin32 = ynmin32; h->cap = cap;
   return RDB_OK;
 }
 
@@ -330,7 +334,7 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
   if ((rc = encode_2d(h, &p.tmap_q[0], qhi, nq, h->d, h->dp, TC_BM))) return rc;
   if (nterms == 3) { if ((rc = encode_2d(h, &p.tmap_q[1], qlo, nq, h->d, h->dp, TC_BM))) return rc; }
   else p.tmap_q[1] = p.tmap_q[0];
-  p.ynorm = h->ynorm; p.cand_key = ck; p.cand_idx = ci;
+  p.ynorm = h->ynorm; p.ynmin32 = h->ynmin32; p.cand_key = ck; p.cand_idx = ci;
   CUDA_TRY(h, h->gthr.ensure(size_t(nq) * 4));
   if (!keep_gthr) CUDA_TRY(h, cudaMemsetAsync(h->gthr.p, 0, size_t(nq) * 4, h->stream));
   p.tile_step = tile_step; p.run_if = run_if;
@@ -799,7 +803,7 @@ int rdb_destroy(rdb_handle* h) {
   {
     DeviceGuard dg(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->master); cudaFree(h->hi); cudaFree(h->lo); cudaFree(h->ynorm); cudaFree(h->labels);
+    cudaFree(h->master); cudaFree(h->hi); cudaFree(h->lo); cudaFree(h->ynorm); cudaFree(h->ynmin32); cudaFree(h->labels);
     cudaFree(h->d_ynorm_max);
     for (DevBuf* b : {&h->add_stage, &h->q_stage, &h->qf, &h->qhi, &h->qlo, &h->qnorm, &h->cand_key, &h->cand_idx,
                       &h->o_dist, &h->o_idx, &h->o_lbl, &h->ids_stage, &h->rec_stage, &h->rr_key, &h->rr_idx,
@@ -875,7 +879,13 @@ int rdb_add(rdb_handle* h, const float* x, int64_t n, int mem, int normalize) {
     if ((rc = launch_ingest(h, src, m, normalize, norm_of_hi, master, hi, lo, h->ynorm + row0))) return rc;
     ynorm_max_kernel<<<unsigned(std::min<int64_t>((m + 255) / 256, 1024)), 256, 0, h->stream>>>(h->ynorm + row0, m,
                                                                                             h->d_ynorm_max);
-    h->launches++;
+    {
+      // minima of the (aligned) 32-row groups these rows touch; unfilled rows of the last group still hold |y|^2 = 0,
+      // which only loosens the bound until they are added
+      const int64_t g0 = row0 / 32, g1 = (row0 + m - 1) / 32;
+      ynorm_min32_kernel<<<unsigned((g1 - g0 + 1 + 7) / 8), 256, 0, h->stream>>>(h->ynorm, g0, g1 - g0 + 1, h->ynmin32);
+    }
+    h->launches += 2;
     if (mem == RDB_MEM_HOST) CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // staging buffer reuse
   }
   h->n += n;

@@ -60,6 +60,7 @@ struct TcParams {
   CUtensorMap tmap_q[2];  // [0] = hi, [1] = lo   bf16/f16 [nq, D], box {64, 128}, SWIZZLE_128B
   CUtensorMap tmap_y[2];  // [0] = hi, [1] = lo   bf16/f16 [N,  D], box {64, 256 / CG}, SWIZZLE_128B
   const float* ynorm;     // [N] |y|^2 (L2 only)
+  const float* ynmin32;   // [N / 32] min |y|^2 per aligned 32-row group (L2 only): coarse filter
   float* cand_key;        // [nq][S * TC_LISTS][kout]
   int* cand_idx;          // [nq][S * TC_LISTS][kout]  local row ids, -1 = empty
   uint32_t* gthr;         // [nq] shared lower bound of the global k-th best key (ordered uint, 0 = none), or null
@@ -117,21 +118,16 @@ __device__ __forceinline__ void tc_load_yn(float4 (&y)[8], const float* __restri
   for (int g = 0; g < 8; ++g) y[g] = __ldg(yn4 + g);
 }
 
+// One 32-column group of one query row.  L2 metric: key_j = 2 s_j - |y_j|^2.  The exact fix-up (8 x 128-bit norm loads
+// + 32 FFMA) is skipped in the common case: with ynmin = min |y|^2 over the group (precomputed at ingest),
+// key_j <= 2 max_j(s_j) - ynmin, so a group whose raw maximum cannot reach the admission threshold is rejected with
+// one FFMA and one compare -- the same cost as the inner-product metric.  The filter is conservative, hence exact.
 template <class Sel, bool L2>
-__device__ __forceinline__ void tc_process32(uint32_t (&r)[32], Sel& sel, const float4 (&y)[8],
+__device__ __forceinline__ void tc_process32(uint32_t (&r)[32], Sel& sel, const float* __restrict__ ynorm, float ynmin,
                                              int col0 /*global row id of column 0 of this group*/, int nvalid) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  if (L2) {
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      v[4 * g + 0] = fmaf(2.0f, v[4 * g + 0], -y[g].x);
-      v[4 * g + 1] = fmaf(2.0f, v[4 * g + 1], -y[g].y);
-      v[4 * g + 2] = fmaf(2.0f, v[4 * g + 2], -y[g].z);
-      v[4 * g + 3] = fmaf(2.0f, v[4 * g + 3], -y[g].w);
-    }
-  }
   const float worst = sel.threshold();
   // fast path: a depth-5 max tree (31 independent FMNMX) decides whether ANY of the 32 columns can survive;
   // in steady state almost no group does, so the per-element compare/mask work below is skipped entirely.
@@ -143,7 +139,31 @@ __device__ __forceinline__ void tc_process32(uint32_t (&r)[32], Sel& sel, const 
   float oct[4];                                   // maxima of columns [8o, 8o + 8)
 #pragma unroll
   for (int o = 0; o < 4; ++o) oct[o] = fmaxf(m[2 * o], m[2 * o + 1]);
-  const float mx = fmaxf(fmaxf(oct[0], oct[1]), fmaxf(oct[2], oct[3]));
+  float mx = fmaxf(fmaxf(oct[0], oct[1]), fmaxf(oct[2], oct[3]));
+  if (L2) {
+    if (nvalid >= 32 && !(fmaf(2.0f, mx, -ynmin) > worst)) {   // no column of this group can beat the threshold
+      __syncwarp();
+      sel.end_group(32);
+      return;
+    }
+    // rare: exact keys for the whole group, then the common logic below on the fixed-up values
+    float4 y[8];
+    tc_load_yn(y, ynorm, col0);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      v[4 * g + 0] = fmaf(2.0f, v[4 * g + 0], -y[g].x);
+      v[4 * g + 1] = fmaf(2.0f, v[4 * g + 1], -y[g].y);
+      v[4 * g + 2] = fmaf(2.0f, v[4 * g + 2], -y[g].z);
+      v[4 * g + 3] = fmaf(2.0f, v[4 * g + 3], -y[g].w);
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      float a = fmaxf(fmaxf(v[8 * o], v[8 * o + 1]), fmaxf(v[8 * o + 2], v[8 * o + 3]));
+      float b = fmaxf(fmaxf(v[8 * o + 4], v[8 * o + 5]), fmaxf(v[8 * o + 6], v[8 * o + 7]));
+      oct[o] = fmaxf(a, b);
+    }
+    mx = fmaxf(fmaxf(oct[0], oct[1]), fmaxf(oct[2], oct[3]));
+  }
   if (nvalid < 32) {
     // ragged last tile (rare): generic 32-wide mask
     uint32_t mask = 0;
@@ -376,16 +396,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
           continue;
         }
         uint32_t ra[32], rb[32];
-        float4 ya[8], yb[8];
-        if (L2) tc_load_yn(ya, p.ynorm, n0);
+        // L2: minima of |y|^2 over this half-tile's four 32-row groups (one 128-bit load; n0 is a multiple of 128)
+        float ymin[4] = {0.f, 0.f, 0.f, 0.f};
+        if (L2) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.ynmin32 + (n0 >> 5)));
+          ymin[0] = t4.x; ymin[1] = t4.y; ymin[2] = t4.z; ymin[3] = t4.w;
+        }
         tmem_ld_32x32(taddr, ra);
 #pragma unroll
         for (int c = 0; c < TC_BN / 64; c += 2) {
-          if (L2) tc_load_yn(yb, p.ynorm, n0 + (c + 1) * 32);
           tmem_ld_wait_regs(ra);
           tmem_ld_32x32(taddr + (c + 1) * 32, rb);
-          tc_process32<Sel, L2>(ra, sel, ya, n0 + c * 32, nvalid - c * 32);
-          if (L2 && c + 2 < TC_BN / 64) tc_load_yn(ya, p.ynorm, n0 + (c + 2) * 32);
+          tc_process32<Sel, L2>(ra, sel, p.ynorm, ymin[c], n0 + c * 32, nvalid - c * 32);
           tmem_ld_wait_regs(rb);
           if (c + 2 < TC_BN / 64) tmem_ld_32x32(taddr + (c + 2) * 32, ra);
           else {
@@ -394,7 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
             __syncwarp();
             if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
           }
-          tc_process32<Sel, L2>(rb, sel, yb, n0 + (c + 1) * 32, nvalid - (c + 1) * 32);
+          tc_process32<Sel, L2>(rb, sel, p.ynorm, ymin[c + 1], n0 + (c + 1) * 32, nvalid - (c + 1) * 32);
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
