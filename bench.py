@@ -39,7 +39,11 @@ K = int(os.environ.get("RDB_BENCH_K", 10))
 GEN_CHUNK = 250_000            # rows per generation chunk; chunk c uses seed DB_SEED + c on every rank
 DB_SEED, Q_SEED, LABEL_SEED = 1234, 5678, 91011
 METRIC_NAME = "QPS @k=10 on 10M x 768 DB (exact flat search)"
-WORKLOAD = f"C3: {N_DB}x{DIM} bf16 DB, {NQ}-query batch, k={K}, cosine (IP + L2-normalise), exact flat search"
+_CFG = "C3" if (N_DB, DIM, NQ, K) == (10_000_000, 768, 65536, 10) else \
+    ("C5" if (N_DB, DIM, K) == (100_000_000, 256, 100) else "custom (RDB_BENCH_* overrides)")
+WORKLOAD = f"{_CFG}: {N_DB}x{DIM} bf16 DB, {NQ}-query batch, k={K}, cosine (IP + L2-normalise), exact flat search"
+if _CFG != "C3":
+    METRIC_NAME = f"QPS @k={K} on {N_DB} x {DIM} DB (exact flat search)"
 
 
 def ncu_traffic():
@@ -49,7 +53,7 @@ def ncu_traffic():
     try:
         with open(p) as f:
             j = json.load(f)
-        if j.get("workload", "").startswith(f"C3: {N_DB}x{DIM} bf16 DB, {NQ}-query batch, k={K},"):
+        if _CFG == "C3" and j.get("workload", "").startswith(f"C3: {N_DB}x{DIM} bf16 DB, {NQ}-query batch, k={K},"):
             return float(j["traffic_bytes_per_launch"])
     except Exception:  # noqa: BLE001
         pass
