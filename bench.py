@@ -84,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -284,7 +284,8 @@ def main():
             return vdb.search_batch(q_np, k=K)
     else:
         def step_e2e():
-            D, I, L = sidx.search(q_host.to(dev, non_blocking=True), K, normalize=True)
+            # every rank uploads 1/G of the (pinned host) batch; one all-gather over NVLink assembles it on every GPU
+            D, I, L = sidx.search_from_host(q_host, K, normalize=True)
             return D.cpu(), I.cpu()
 
     # ---- device-resident timing
@@ -338,7 +339,10 @@ def main():
                        "db_chunks_per_query_tile": nsplits,
                        "l2_policy": "inputs larger than L2 (database shard >> 126 MB), no flush needed"},
             "e2e": {"value": NQ / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": NQ * DIM * 4, "d2h_bytes_per_step": NQ * K * 12},
+                    "h2d_bytes_per_step": NQ * DIM * 4, "d2h_bytes_per_step": NQ * K * 12 * world,
+                    "note": ("host numpy in/out through VectorDatabase.search_batch" if world == 1 else
+                             "each rank uploads 1/N of the pinned host batch (total = h2d_bytes_per_step), NVLink "
+                             "all-gather, sharded search, every rank reads the merged result back")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",

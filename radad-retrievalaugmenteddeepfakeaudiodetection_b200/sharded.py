@@ -69,6 +69,7 @@ class ShardedFlatIndex:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.local = FlatIndex(d, metric, store, device=device, keep_f32_master=keep_f32_master)
+        self.device_index = device
         self.ntotal_global = 0
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' or 'nccl'")
@@ -120,6 +121,25 @@ class ShardedFlatIndex:
 
     def set_labels_local(self, labels) -> None:
         self.local.set_labels(labels)
+
+    def search_from_host(self, q_host, k: int, normalize: bool = False):
+        """Queries in (pinned) HOST memory, identical on every rank: each rank uploads only its 1/G slice over PCIe and
+        the full batch is assembled with one all-gather over NVLink (G x less host->device traffic than G full
+        uploads), then ``search``.  q_host: torch CPU float32 [nq, d].  Returns (D, I, L) on every rank (device)."""
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", self.device_index if self.device_index is not None else torch.cuda.current_device())
+        nq, d = q_host.shape
+        if self.world == 1:
+            return self.search(q_host.to(dev, non_blocking=True), k, normalize=normalize)
+        per = -(-nq // self.world)
+        lo, hi = min(nq, self.rank * per), min(nq, (self.rank + 1) * per)
+        mine = torch.zeros((per, d), dtype=torch.float32, device=dev)
+        if hi > lo:
+            mine[:hi - lo].copy_(q_host[lo:hi], non_blocking=True)
+        full = torch.empty((per * self.world, d), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(full, mine, group=self.group)
+        return self.search(full[:nq], k, normalize=normalize)
 
     def search(self, q, k: int, normalize: bool = False):
         """q: torch CUDA [nq, d], identical on every rank.  Returns (D, I, L) on every rank."""

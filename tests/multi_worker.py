@@ -34,7 +34,11 @@ def main():
         q = torch.from_numpy(xq).to(dev)
         for rep in range(3):                                # repeated calls alternate the two peer half-buffers
             D, I, L = sh.search(q, k, normalize=cos)
+        # host ingress: every rank uploads 1/G of the (pinned) batch, NVLink all-gather assembles it (Q = 333: ragged)
+        qh = torch.from_numpy(xq).pin_memory()
+        D2, I2, L2 = sh.search_from_host(qh, k, normalize=cos)
         torch.cuda.synchronize()
+        assert torch.equal(I2, I) and torch.equal(D2, D) and torch.equal(L2, L), f"rank {rank}: host-ingress path differs"
         full = pkg.FlatIndex(Dm, metric, store, device=local)
         full.add(xb, normalize=cos)
         full.set_labels(labels)
