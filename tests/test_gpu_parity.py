@@ -660,3 +660,40 @@ def test_clustered_distribution_with_duplicates_and_vote(pkg, oracle, store, alg
     # same-cluster neighbours dominate: the vote agrees with the query's own cluster label for almost every query
     agree = np.mean((vote >= (K + 1) // 2) == (labels[src] > 0.5))
     assert agree > 0.95, agree
+
+
+def test_multi_gpu_tiny_and_uneven_shards(pkg, oracle):
+    """MultiGpuFlatIndex corner cases: fewer rows than shards (empty shards), shards holding fewer than k rows (their
+    lists end in -1 slots), k == ntotal, labels set before further adds, and a stream-scorer sized batch (nq <= 4)."""
+    rng = np.random.default_rng(9)
+    Dm = 24
+    xb = rng.integers(-2, 3, size=(5000, Dm)).astype(np.float32)
+    xq = rng.integers(-2, 3, size=(6, Dm)).astype(np.float32)
+    multi = pkg.MultiGpuFlatIndex(Dm, pkg.METRIC_L2, "bf16", devices=_multi_devices())
+    ref = oracle.FlatIndexOracle(Dm, pkg.METRIC_L2)
+    multi.add(xb[:2])                                   # 2 rows, >= 3 shards: at least one shard stays empty
+    ref.add(xb[:2])
+    D, I = multi.search(xq, 2)
+    Dr, Ir = ref.search(xq, 2, direct=False)
+    np.testing.assert_array_equal(I, Ir)
+    np.testing.assert_array_equal(D, Dr)
+    for a, b in ((2, 9), (9, 40), (40, 41)):            # tiny adds: each goes whole to the least-loaded shard
+        multi.add(xb[a:b])
+        ref.add(xb[a:b])
+    assert multi.ntotal == 41 and min(multi.shard_sizes) < 15
+    D, I = multi.search(xq, 41)                         # k == ntotal > rows of any single shard
+    Dr, Ir = ref.search(xq, 41, direct=False)
+    np.testing.assert_array_equal(I, Ir)
+    np.testing.assert_array_equal(D, Dr)
+    labels = (np.arange(41) % 2).astype(np.float32)
+    multi.set_labels(labels)
+    D, I, L = multi.search(xq[:3], 7, return_labels=True)          # nq <= 4: streaming scorer on every shard
+    np.testing.assert_array_equal(I, Ir[:3, :7])
+    np.testing.assert_array_equal(L, labels[I])
+    multi.add(xb[41:])                                  # big add: water-filled over all shards
+    ref.add(xb[41:])
+    D, I = multi.search(xq, 15)
+    Dr, Ir = ref.search(xq, 15, direct=False)
+    np.testing.assert_array_equal(I, Ir)
+    np.testing.assert_array_equal(D, Dr)
+    assert max(multi.shard_sizes) - min(multi.shard_sizes) <= 41
