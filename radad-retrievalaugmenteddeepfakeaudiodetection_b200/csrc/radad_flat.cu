@@ -355,10 +355,13 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
     const int sync_groups = (tiles_per_chunk + TC_SYNC_GS - 1) / TC_SYNC_GS;
     if (window > 0 && tile_step == 1 && nqg >= ngroups && sync_groups > 2 * window) {
       const size_t slots = size_t((p.num_units + ngroups - 1) / ngroups);
-      const size_t bytes = slots * 2 * size_t(sync_groups) * 4;
+      const size_t bytes = (slots * 2 * size_t(sync_groups) + 1) * 4;     // + the "broken" flag
       CUDA_TRY(h, h->tcsync.ensure(bytes));
       CUDA_TRY(h, cudaMemsetAsync(h->tcsync.p, 0, bytes, h->stream));
       p.sync = h->tcsync.as<uint32_t>(); p.sync_groups = sync_groups; p.sync_window = window;
+      p.sync_broken = p.sync + slots * 2 * size_t(sync_groups);
+      p.sync_spins = 4096;                                                // ~5 ms of patience
+      if (const char* v = getenv("RDB_TC_LOCKSTEP_SPINS")) p.sync_spins = atoi(v);
     }
   }
   rc = (cg == 2) ? launch_tc_cg<2>(h, p, k) : launch_tc_cg<1>(h, p, k);

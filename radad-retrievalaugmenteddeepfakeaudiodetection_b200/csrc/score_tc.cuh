@@ -71,7 +71,8 @@ struct TcParams {
   uint64_t hint_q, hint_y;  // TMA L2 eviction-priority hints for the query / database operand
   // Lock-step window (see tc_lockstep_* below): progress counters [slot][2][sync_groups], or null = off
   uint32_t* sync;
-  int sync_groups, sync_window;
+  int sync_groups, sync_window, sync_spins;   // sync_spins: polls (~1 us each) before a producer gives lock-step up
+  uint32_t* sync_broken;    // set by the first producer that gives up: nobody waits any more in this launch
   int tile_step;            // 1 = every DB tile; > 1: strided sample pass (tile index t stands for tile t * tile_step)
   int astat;                // query-stationary form (host: nterms == 1 && D <= 256)
   const int* run_if;        // fallback launch: all CTAs exit at once unless *run_if != 0 (null = always run)
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
         const int u_hi = min(min((slot + 1) * ngroups, (chunk + 1) * p.nqt), p.num_units);
         const uint32_t members = uint32_t(u_hi - u_lo);
         const bool counted = p.sync != nullptr && rank == 0 && members > 1;
-        bool waiting = counted;
+        bool waiting = counted && ld_relaxed_u32(p.sync_broken) == 0u;
         uint32_t* ctr = p.sync + (size_t(slot) * 2 + size_t(chunk - (slot * ngroups) / p.nqt)) * p.sync_groups;
         uint32_t seen = 0;
         if (astat) {
@@ -296,8 +297,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
               if (waiting && g >= p.sync_window && seen < members) {
                 int spins = 0;
                 while ((seen = ld_relaxed_u32(ctr + g - p.sync_window)) < members) {
-                  if (++spins > 256) { waiting = false; break; }
-                  __nanosleep(200);
+                  // patience is long (a producer that is ahead SHOULD wait: that is what re-aligns the wave); it only
+                  // ends when a member evidently is not running (GPU shared with another kernel), and then for everybody
+                  if (++spins > p.sync_spins || ld_relaxed_u32(p.sync_broken) != 0u) {
+                    waiting = false;
+                    red_add_u32(p.sync_broken);
+                    break;
+                  }
+                  __nanosleep(500);
                 }
               }
               if (g + 1 >= p.sync_window) seen = ld_relaxed_u32(ctr + g + 1 - p.sync_window);   // for the next check
