@@ -69,9 +69,9 @@ struct TcParams {
   uint32_t idesc;
   int dbg;                  // profiling only (RDB_TC_DEBUG): 1 = skip the selection work (results invalid)
   uint64_t hint_q, hint_y;  // TMA L2 eviction-priority hints for the query / database operand
-  // Lock-step window (see tc_lockstep_* below): progress counters [slot][2][sync_groups], or null = off
+  // Lock-step window (see below): progress counters [slot][sync_span][sync_groups], or null = off
   uint32_t* sync;
-  int sync_groups, sync_window, sync_spins;   // sync_spins: polls (~1 us each) before a producer gives lock-step up
+  int sync_groups, sync_window, sync_span, sync_spins;   // sync_span: chunks one slot can touch;   // sync_spins: polls (~1 us each) before a producer gives lock-step up
   uint32_t* sync_broken;    // set by the first producer that gives up: nobody waits any more in this launch
   int tile_step;            // 1 = every DB tile; > 1: strided sample pass (tile index t stands for tile t * tile_step)
   int astat;                // query-stationary form (host: nterms == 1 && D <= 256)
@@ -267,14 +267,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
       for (int unit = group; unit < p.num_units; unit += ngroups, ++slot) {
         const int qtile = (unit % p.nqt) * CG + rank, chunk = unit / p.nqt;
         const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
-        // lock-step window: members = units of this slot that run this chunk (host enables it only when nqt >= ngroups,
-        // so a slot touches at most two chunks)
+        // lock-step window: members = units of this slot that run this chunk (a slot of ngroups consecutive units
+        // touches at most sync_span = ceil(ngroups / nqt) + 1 chunks)
         const int u_lo = max(slot * ngroups, chunk * p.nqt);
         const int u_hi = min(min((slot + 1) * ngroups, (chunk + 1) * p.nqt), p.num_units);
         const uint32_t members = uint32_t(u_hi - u_lo);
         const bool counted = p.sync != nullptr && rank == 0 && members > 1;
         bool waiting = counted && ld_relaxed_u32(p.sync_broken) == 0u;
-        uint32_t* ctr = p.sync + (size_t(slot) * 2 + size_t(chunk - (slot * ngroups) / p.nqt)) * p.sync_groups;
+        uint32_t* ctr = p.sync + (size_t(slot) * p.sync_span + size_t(chunk - (slot * ngroups) / p.nqt)) * p.sync_groups;
         uint32_t seen = 0;
         if (astat) {
           // the unit's query tile: loaded once, after every MMA of the previous unit has retired
