@@ -278,17 +278,16 @@ int encode_2d(rdb_handle* h, CUtensorMap* m, const void* base, int64_t rows, int
 }
 
 // CTAs per MMA group.  Both forms are built and parity-tested: cta_group::1 (one CTA = one 128-query tile, M = 128)
-// and cta_group::2 (a CTA pair runs M = 256 MMAs, each SM staging half of the database tile).  Measured on B200 at
-// the C3 size (profiles/r01_tc_cta_pair_ab.md) the kernel is POWER-bound: the pair form reaches a higher tensor-pipe
-// utilisation per clock (94 % vs 80 %) but the power cap then holds the SM clock lower (1.04 vs 1.38 GHz) and it
-// ends ~4-11 % slower, so the single-CTA form is the default for the one-term (16-bit store) search.  The three-term
-// split-precision search of fp32 stores moves twice the operand bytes per accumulator tile and is not at the power
-// cap; there the pair form is ~10 % faster (interleaved A/B at C2: 33.8 vs 37.6 ms median) and is the default.
-// RDB_TC_CG=1|2 overrides.
-int tc_cta_group(int nq, int nterms) {
+// and cta_group::2 (a CTA pair runs M = 256 MMAs, each SM staging half of the database tile: a third less L2->SM
+// operand traffic, 6-deep ring).  Interleaved A/Bs on B200 (profiles/r01_session2_notes.md): with the lock-step
+// window holding the wave together the pair form is 2-3.5 % faster for D = 768 one-term searches (C3: 1421-1442 vs
+// 1385-1393 TFLOP/s) and ~10 % faster for the three-term split-precision search (C2); the query-stationary form
+// (D <= 256) already stages database slices only and is faster as a single CTA.  RDB_TC_CG=1|2 overrides.
+int tc_cta_group(int nq, int nterms, int d) {
   if (nq <= TC_BM) return 1;
   if (const char* v = getenv("RDB_TC_CG")) { const int f = atoi(v); if (f == 1 || f == 2) return f; }
-  return nterms == 3 ? 2 : 1;
+  if (nterms == 3) return 2;
+  return d > TcCfg<1>::ASTAT_MAX_KS * TC_BK ? 2 : 1;
 }
 
 template <class SEL, bool L2V, int CG>
@@ -526,7 +525,7 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
   cudaStream_t s = h->stream;
   if (algo == RDB_ALGO_TC) {
     const int ntiles = int((h->n + TC_BN - 1) / TC_BN);
-    const int cg = tc_cta_group(qv.nq, nterms);
+    const int cg = tc_cta_group(qv.nq, nterms, h->d);
     const int nqg = (qv.nq + TC_BM * cg - 1) / (TC_BM * cg);
     // large k: per-unit selection overhead (reservoir warm-up, final sort) is worth ~64 tiles -> fewer, longer units
     S = choose_splits(nqg, ntiles, h->num_sms / cg, 256 / TC_LISTS, kc > 32 ? 64 : 4, &tpc, kc > 32 ? 64.0 : 2.0);
