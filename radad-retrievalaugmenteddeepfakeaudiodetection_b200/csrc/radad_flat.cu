@@ -337,6 +337,8 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
   CUDA_TRY(h, h->gthr.ensure(size_t(nq) * 4));
   if (!keep_gthr) CUDA_TRY(h, cudaMemsetAsync(h->gthr.p, 0, size_t(nq) * 4, h->stream));
   p.tile_step = tile_step; p.run_if = run_if;
+  p.nstages = 64;
+  if (const char* v = getenv("RDB_TC_STAGES")) p.nstages = std::max(2, atoi(v));
   p.astat = (nterms == 1 && h->d <= TcCfg<1>::ASTAT_MAX_KS * TC_BK && !getenv("RDB_TC_NO_ASTAT")) ? 1 : 0;
   p.gthr = (S > 1 || TC_LISTS > 1) ? h->gthr.as<uint32_t>() : nullptr;
   p.nq = nq; p.N = int(h->n); p.D = h->d;

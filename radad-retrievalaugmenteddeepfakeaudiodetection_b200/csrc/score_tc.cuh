@@ -35,7 +35,7 @@ constexpr int TC_BK = 64;
 // a third less L2->SM operand traffic and a 6-deep instead of 4-deep ring in the same shared memory.
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 template <int CG> struct TcCfg {
-  static constexpr int STAGES = (CG == 2) ? 6 : 4;
+  static constexpr int STAGES = (CG == 2) ? 6 : 4;      // ring slots (6 x 32 KB / 4 x 48 KB; 4..7 measured equal for the pair)
   static constexpr int B_ROWS = TC_BN / CG;
   static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
@@ -74,6 +74,7 @@ struct TcParams {
   int sync_groups, sync_window, sync_span, sync_spins;   // sync_span: chunks one slot can touch;   // sync_spins: polls (~1 us each) before a producer gives lock-step up
   uint32_t* sync_broken;    // set by the first producer that gives up: nobody waits any more in this launch
   int tile_step;            // 1 = every DB tile; > 1: strided sample pass (tile index t stands for tile t * tile_step)
+  int nstages;              // ring slots used (<= TcCfg::STAGES; profiling knob RDB_TC_STAGES)
   int astat;                // query-stationary form (host: nterms == 1 && D <= 256)
   const int* run_if;        // fallback launch: all CTAs exit at once unless *run_if != 0 (null = always run)
 };
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
   const bool astat = p.astat != 0;
-  const int nst = astat ? Cfg::ASTAT_STAGES : STAGES;                 // ring depth
+  const int nst = astat ? Cfg::ASTAT_STAGES : min(STAGES, p.nstages);  // ring depth
   const int ring_stride = astat ? Cfg::B_BYTES : Cfg::STAGE_BYTES;    // bytes per ring slot
   uint8_t* ring = smem + (astat ? Cfg::ASTAT_A_BYTES : 0);            // slot s: [A slice |] B slice
   const int b_off = astat ? 0 : TC_A_BYTES;                           // offset of the B slice inside a slot
