@@ -348,9 +348,9 @@ def main():
             "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": ach / pk["bf16_sustained"], "traffic": ncu_traffic() if world == 1 else None,
                          "traffic_note": "dram read+write bytes/launch from the committed ncu --set full capture of this "
-                                         "workload (profiles/r01_ncu_c3_traffic.json): ~4.5 database volumes -- the "
-                                         "schedule streams the 15.36 GB database once per wave of 148 query tiles "
-                                         "(3.5 waves); ~1% of DRAM bandwidth, not the bound",
+                                         "workload (profiles/r01_ncu_c3_traffic.json): 4.5-6 database volumes across "
+                                         "captures -- the schedule streams the 15.36 GB database once per wave of 74 "
+                                         "query-tile pairs (3.5 waves); ~2% of DRAM bandwidth, not the bound",
                          "kernel": "score_select_tc_kernel", "kernel_ms": ms_kern,
                          "flops_per_launch": flops, "peak_source": pk["src"] + " sustained bf16",
                          "frac_of_burst": ach / pk["bf16_burst"],
