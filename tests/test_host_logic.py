@@ -83,3 +83,37 @@ def test_multi_gpu_water_filling_plan(pkg):
     apply(10_000)                                          # reference slice size (vector_add_batch_size)
     sizes = [s.ntotal for s in m.shards]
     assert sum(sizes) == 1_010_200 and max(sizes) - min(sizes) <= 1
+
+
+def test_lockstep_membership_arithmetic():
+    """Mirror of the lock-step window bookkeeping (csrc/score_tc.cuh producer + launch_tc in csrc/radad_flat.cu):
+    every work unit must fall into exactly one (slot, chunk-in-slot) counter group, the chunk-in-slot index must stay
+    below the `span` the host allocates for, and the `members` count every producer derives for its group must equal
+    the number of units that really land in it -- otherwise waiters would expect arrivals that never come (and give
+    the window up) or a group would be released early."""
+    import random
+    rnd = random.Random(7)
+    cases = [(512, 13, 148), (256, 13, 74), (128, 37, 148), (128, 8, 148), (64, 8, 74), (40, 24, 74), (75, 5, 148)]
+    cases += [(rnd.randint(1, 600), rnd.randint(1, 40), rnd.choice([74, 148, 7, 31])) for _ in range(200)]
+    for nqt, S, slots_avail in cases:
+        num_units = nqt * S
+        ngroups = min(num_units, slots_avail)
+        span = (ngroups + nqt - 1) // nqt + 1                     # host: chunks one slot can touch
+        seen = {}
+        for group in range(ngroups):                              # device: persistent loop of one CTA (pair)
+            slot = 0
+            for unit in range(group, num_units, ngroups):
+                chunk = unit // nqt
+                u_lo = max(slot * ngroups, chunk * nqt)
+                u_hi = min((slot + 1) * ngroups, (chunk + 1) * nqt, num_units)
+                members = u_hi - u_lo
+                cidx = chunk - (slot * ngroups) // nqt
+                assert 0 <= cidx < span, (nqt, S, ngroups, unit, cidx, span)
+                assert u_lo <= unit < u_hi
+                seen.setdefault((slot, cidx), []).append(members)
+                slot += 1
+        total = 0
+        for key, ms in seen.items():
+            assert len(set(ms)) == 1 and ms[0] == len(ms), (nqt, S, ngroups, key, ms)
+            total += len(ms)
+        assert total == num_units
