@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
 // exact kout-th key is strictly above that, no outside row can enter the exact top-kout:
 //   cert[q] = 1  iff  exact_key[kout-1] > approx_worst + B        (or the candidate set holds every row).
 // Uncertified queries are appended to `uncert_list` (count in uncert_count) for the exact fallback.
+constexpr int RERANK_MAX_KC = 128;
 template <bool L2>
 __global__ void __launch_bounds__(128) rerank_exact_kernel(const long long* __restrict__ cand_idx,
                                                            const float* __restrict__ cand_key, int Q, int kc, int kout,
@@ -157,17 +158,21 @@ __global__ void __launch_bounds__(128) rerank_exact_kernel(const long long* __re
                                                            long long* __restrict__ out_idx,
                                                            int* __restrict__ uncert_list,
                                                            int* __restrict__ uncert_count) {
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ uint32_t s_ok[4][RERANK_MAX_KC];     // ordered exact keys (0 = empty slot)
+  __shared__ long long s_id[4][RERANK_MAX_KC];
+  __shared__ float s_kth[4];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int q = blockIdx.x * (blockDim.x >> 5) + w;
   if (q >= Q) return;
   const float* qr = qf + (long long)q * D;
-  float my_key = -CUDART_INF_F;
-  long long my_id = -1;
   float approx_worst = CUDART_INF_F;
   int nvalid = 0;
   for (int j = 0; j < kc; ++j) {
     const long long id = cand_idx[(long long)q * kc + j];
-    if (id < 0) continue;
+    if (id < 0) {
+      if (lane == 0) { s_ok[w][j] = 0u; s_id[w][j] = 0x7FFFFFFFFFFFFFFFll; }
+      continue;
+    }
     ++nvalid;
     approx_worst = fminf(approx_worst, cand_key[(long long)q * kc + j]);
     const float* yr = master + id * (long long)D;
@@ -175,28 +180,37 @@ __global__ void __launch_bounds__(128) rerank_exact_kernel(const long long* __re
     for (int c = lane; c < D; c += 32) s = fmaf(qr[c], __ldg(yr + c), s);
     s = warp_sum(s);
     const float key = L2 ? fmaf(2.0f, s, -ynorm[id]) : s;
-    if (lane == j) { my_key = key; my_id = id; }
+    if (lane == 0) { s_ok[w][j] = ordered_f32(key); s_id[w][j] = id; }
   }
-  // rank by counting (kc <= 32): number of candidates strictly better than mine
-  const uint32_t mok = (my_id >= 0) ? ordered_f32(my_key) : 0u;
-  const long long mid = (my_id >= 0) ? my_id : 0x7FFFFFFFFFFFFFFFll;
-  int rank = 0;
-  for (int j = 0; j < kc; ++j) {
-    const uint32_t ook = __shfl_sync(0xffffffffu, mok, j);
-    const long long oid = __shfl_sync(0xffffffffu, mid, j);
-    if (j != lane && head_better(ook, oid, mok, mid)) ++rank;
+  if (lane == 0) s_kth[w] = -CUDART_INF_F;
+  __syncwarp();
+  // rank by counting (kc <= 128): valid candidates by (key desc, id asc), empty slots after them in slot order
+  int empties_before = 0;
+  for (int i0 = 0; i0 < kc; i0 += 32) {
+    const int i = i0 + lane;
+    const bool in = i < kc;
+    const uint32_t mok = in ? s_ok[w][i] : 0u;
+    const long long mid = in ? s_id[w][i] : 0x7FFFFFFFFFFFFFFFll;
+    const bool empty = in && mok == 0u;
+    const uint32_t emask = __ballot_sync(0xffffffffu, empty);
+    if (in) {
+      int pos;
+      if (!empty) {
+        pos = 0;
+        for (int j = 0; j < kc; ++j) pos += (j != i && head_better(s_ok[w][j], s_id[w][j], mok, mid)) ? 1 : 0;
+        if (pos == kout - 1) s_kth[w] = unordered_f32(mok);
+      } else {
+        pos = nvalid + empties_before + __popc(emask & ((1u << lane) - 1u));
+      }
+      out_key[(long long)q * kc + pos] = empty ? -CUDART_INF_F : unordered_f32(mok);
+      out_idx[(long long)q * kc + pos] = empty ? -1 : mid;
+    }
+    empties_before += __popc(emask);
   }
-  const uint32_t invalid_mask = __ballot_sync(0xffffffffu, lane < kc && my_id < 0);
-  if (lane < kc) {
-    int pos = rank;
-    if (my_id < 0) pos = nvalid + __popc(invalid_mask & ((1u << lane) - 1u));
-    out_key[(long long)q * kc + pos] = (my_id >= 0) ? my_key : -CUDART_INF_F;
-    out_idx[(long long)q * kc + pos] = my_id;
-  }
-  const uint32_t has = __ballot_sync(0xffffffffu, lane < kc && my_id >= 0 && rank == kout - 1);
-  float kth_key = -CUDART_INF_F;
-  if (has) kth_key = __shfl_sync(0xffffffffu, my_key, __ffs(has) - 1);
+  __syncwarp();
   if (lane == 0) {
+    const float kth_key = s_kth[w];
+    const bool has = nvalid >= kout;
     const float bound = eps * sqrtf(qnorm[q]) * sqrtf(*ynorm_max) * (L2 ? 2.0f : 1.0f);
     const bool ok = (nvalid >= ntotal) || (nvalid == kc && has && kth_key > approx_worst + bound);
     if (!ok) uncert_list[atomicAdd(uncert_count, 1)] = q;

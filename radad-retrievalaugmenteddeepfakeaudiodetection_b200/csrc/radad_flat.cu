@@ -380,7 +380,7 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
 constexpr int64_t kQueryBatch = 65536;
 constexpr int kMaxK = 128;
 constexpr int kMaxKTc = 128;       // k <= 32: register-resident list; 32 < k <= 128: local-memory reservoir
-constexpr int kMaxKSplit = 24;     // split-precision path keeps kc = 16 / 32 candidates: slack >= 6
+constexpr int kMaxKSplit = 104;    // split-precision path keeps kc = 16 / 32 / 64 / 128 candidates: slack >= 6 / 8 / 16 / 24
 constexpr int64_t kMinRowsTc = 1024;
 constexpr int kTcSample = 64;          // large-k pivot: every 64th DB tile
 constexpr int kTcPivotRank = 16;       // ... and the sample's 16th best key
@@ -619,7 +619,7 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
     return fail(h, RDB_ERR_UNSUPPORTED, "search: streaming scorer needs nq <= 4, k <= 128 (and D % 4 == 0 for fp32 stores)");
   if (algo == RDB_ALGO_TC && !tc_ok)
     return fail(h, RDB_ERR_UNSUPPORTED,
-                "search: tensor-core scorer needs ntotal >= 256 and k <= 128 (16-bit store) / k <= 24 (fp32 store)");
+                "search: tensor-core scorer needs ntotal >= 256 and k <= 128 (16-bit store) / k <= 104 (fp32 store)");
   const bool split = (algo == RDB_ALGO_TC) && !sixteen;
   const float* labels = (h->labels && h->nlabels == h->n) ? h->labels : nullptr;
   cudaStream_t s = h->stream;
@@ -686,7 +686,7 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
       }
     } else {
       // ---- split-precision tensor-core pass keeping kc > k candidates
-      const int kc = (k <= 10) ? 16 : 32;
+      const int kc = (k <= 10) ? 16 : (k <= 24 ? 32 : (k <= 48 ? 64 : 128));
       if ((rc = run_scorer(h, RDB_ALGO_TC, 3, qv, kc, &L, true))) return rc;
       CUDA_TRY(h, h->rr_key.ensure(size_t(nb) * kc * 4));
       CUDA_TRY(h, h->rr_idx.ensure(size_t(nb) * kc * 8));

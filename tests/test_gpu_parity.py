@@ -108,6 +108,8 @@ CASES = [
     ("l2_f32_split_ragged", 5003, 200, 77, 24, "L2", False, "f32", "tc"),
     ("ip_f32_split_q1", 20000, 256, 1,   5,  "IP", False, "f32",  "tc"),
     ("l2_f32_auto",   20000, 768,  1000, 10, "L2", False, "f32",  "auto"),
+    ("l2_f32_split_k40",  30000, 256, 200, 40,  "L2", False, "f32", "tc"),   # kc = 64 (reservoir epilogue + re-rank of 64)
+    ("cos_f32_split_k100", 40000, 128, 150, 100, "IP", True, "f32", "tc"),   # kc = 128
     ("ip_bf16_simt_k100", 5000, 128, 50, 100, "IP", False, "bf16", "simt"),
     # small-batch HBM-streaming scorer (batch-1 latency path; exact fp32 for fp32 stores)
     ("stream_l2_f32_q1",   30000, 768, 1, 15, "L2", False, "f32",  "stream"),
@@ -276,8 +278,8 @@ def test_cta_pair_kernel_bit_exact(pkg, oracle, monkeypatch, metric_s, k, store)
     """The cta_group::2 form of the tensor-core scorer (a CTA pair runs M = 256 MMAs, RDB_TC_CG=2): lattice data, ragged
     query count (an odd number of 128-query tiles, last tile partly empty) and ragged N -- ids and distances must equal
     the oracle bit-for-bit, and the single-CTA form must agree."""
-    if store == "f32" and k > 24:
-        pytest.skip("split-precision path serves k <= 24")
+    if store == "f32" and k > 104:
+        pytest.skip("split-precision path serves k <= 104")
     rng = np.random.default_rng(11)
     N, Dm, nq = 7013, 200, 300
     xb = rng.integers(-2, 3, size=(N, Dm)).astype(np.float32)
@@ -310,6 +312,26 @@ def test_lattice_bit_exact_f32_split(pkg, name):
     D, I = idx.search(g["xq"], int(g["k"]), algo="tc")
     np.testing.assert_array_equal(I, g["idx"])
     np.testing.assert_array_equal(D, g["dist"])
+
+
+@pytest.mark.parametrize("k", [30, 64, 104])
+@pytest.mark.parametrize("name", ["L2", "IP"])
+def test_lattice_bit_exact_f32_split_large_k(pkg, oracle, name, k):
+    """fp32 store, certified split path with kc = 64 / 128 candidates: lattice data (heavy ties -> most queries cannot
+    be certified and take the exact fallback, the rest stay on the tensor cores) must match the oracle bit-for-bit."""
+    rng = np.random.default_rng(31)
+    N, Dm, nq = 6000, 48, 140
+    xb = rng.integers(-2, 3, size=(N, Dm)).astype(np.float32)
+    xq = rng.integers(-2, 3, size=(nq, Dm)).astype(np.float32)
+    metric = pkg.METRIC_IP if name == "IP" else pkg.METRIC_L2
+    idx = pkg.FlatIndex(Dm, metric, "f32")
+    idx.add(xb)
+    ref = oracle.FlatIndexOracle(Dm, metric)
+    ref.add(xb)
+    Dr, Ir = ref.search(xq, k, direct=False)
+    D, I = idx.search(xq, k, algo="tc")
+    np.testing.assert_array_equal(I, Ir)
+    np.testing.assert_array_equal(D, Dr)
 
 
 def test_split_path_certificate_fallback(pkg):
