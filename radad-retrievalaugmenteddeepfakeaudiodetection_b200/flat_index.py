@@ -29,7 +29,37 @@ def _is_cuda_tensor(x) -> bool:
     return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
 
 
-class FlatIndex:
+class _ReconstructCache:
+    """The reference caller fetches every neighbour of a batch with its own ``index.reconstruct(i)`` call
+    (``pipeline.py:491-509``: B x (K+10) calls, 3840 per training batch) -- on a GPU index each one is a device round
+    trip.  After a host-path ``search`` the result ids are remembered; the FIRST ``reconstruct`` that follows gathers
+    all of them with one kernel + one device-to-host copy (if that is at most ``_RC_MAX_BYTES``), and the calls are
+    then served from host memory.  Rows are append-only, so cached rows never go stale; the cache is dropped at the
+    next search.  Nothing is fetched unless ``reconstruct`` is actually called."""
+    _RC_MAX_BYTES = 512 << 20
+
+    def _rc_note_search(self, ids_host) -> None:
+        self._rc_pending, self._rc_rows = ids_host, None
+
+    def _rc_lookup(self, i: int):
+        rows = getattr(self, "_rc_rows", None)
+        if rows is None:
+            pend = getattr(self, "_rc_pending", None)
+            if pend is None:
+                return None
+            self._rc_pending = None
+            ids = np.unique(pend[pend >= 0])
+            if ids.size == 0 or ids.size * self.d * 4 > self._RC_MAX_BYTES:
+                return None
+            rows = self._rc_rows = (ids, self.reconstruct_batch(ids))
+        ids, mat = rows
+        j = int(np.searchsorted(ids, i))
+        if j < ids.size and ids[j] == i:
+            return mat[j].copy()
+        return None
+
+
+class FlatIndex(_ReconstructCache):
     """Exact flat nearest-neighbour index on one B200 (one row shard)."""
 
     is_trained = True          # faiss flat indexes need no training (vector_database.py:124)
@@ -147,10 +177,14 @@ class FlatIndex:
             self._h, q.ctypes.data_as(ctypes.c_void_p), nq, k, MEM_HOST, int(bool(normalize)), algo,
             D.ctypes.data_as(ctypes.c_void_p), I.ctypes.data_as(ctypes.c_void_p),
             L.ctypes.data_as(ctypes.c_void_p) if L is not None else None))
+        self._rc_note_search(I)
         return (D, I, L) if return_labels else (D, I)
 
     def reconstruct(self, i: int) -> np.ndarray:
         """index.reconstruct(i) -> float32[d] (pipeline.py:503)."""
+        hit = self._rc_lookup(int(i))
+        if hit is not None:
+            return hit
         out = np.empty((self.d,), dtype=np.float32)
         self._use_own_stream()
         self._check(self._lib.rdb_reconstruct(self._h, int(i), out.ctypes.data_as(ctypes.c_void_p)))

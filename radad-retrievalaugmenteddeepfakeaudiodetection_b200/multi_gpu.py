@@ -27,12 +27,12 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from ._cabi import ALGO_AUTO, METRIC_IP, METRIC_L2
-from .flat_index import FlatIndex, _is_cuda_tensor
+from .flat_index import FlatIndex, _ReconstructCache, _is_cuda_tensor
 
 _MIN_SPLIT_ROWS = 4096          # smaller add() calls go whole to the least-loaded shard (fewer segments)
 
 
-class MultiGpuFlatIndex:
+class MultiGpuFlatIndex(_ReconstructCache):
     """Exact flat search over a database row-sharded across the GPUs of one box, driven by one process."""
 
     is_trained = True
@@ -255,10 +255,14 @@ class MultiGpuFlatIndex:
             D, I, L = D.to(out_dev), I.to(out_dev), L.to(out_dev)
             return (D, I, L) if return_labels else (D, I)
         Dn, In, Ln = D.cpu().numpy(), I.cpu().numpy(), L.cpu().numpy()
+        self._rc_note_search(In)
         return (Dn, In, Ln) if return_labels else (Dn, In)
 
     # ------------------------------------------------------------------ reconstruct
     def reconstruct(self, i: int) -> np.ndarray:
+        hit = self._rc_lookup(int(i))
+        if hit is not None:
+            return hit
         g, local = self._locate(int(i))
         return self.shards[g].reconstruct(local)
 

@@ -719,3 +719,67 @@ def test_multi_gpu_tiny_and_uneven_shards(pkg, oracle):
     np.testing.assert_array_equal(I, Ir)
     np.testing.assert_array_equal(D, Dr)
     assert max(multi.shard_sizes) - min(multi.shard_sizes) <= 41
+
+
+def test_reconstruct_after_search_is_served_from_one_gather(pkg):
+    """index.reconstruct(i) for ids of the last host-path search (the reference caller's access pattern,
+    pipeline.py:491-509) must return exactly the stored rows -- whether they come from the batched cache or from a
+    single-row device read -- also for ids that were NOT in the search result, after further adds, and it must hand
+    out independent copies."""
+    rng = np.random.default_rng(4)
+    xb = rng.standard_normal((3000, 40)).astype(np.float32)
+    xq = rng.standard_normal((9, 40)).astype(np.float32)
+    for store in ("f32", "bf16"):
+        idx = pkg.FlatIndex(40, pkg.METRIC_L2, store)
+        idx.add(xb)
+        truth = idx.reconstruct_batch(np.arange(3000))
+        D, I = idx.search(xq, 15)
+        launches = idx.launch_count
+        got = np.stack([idx.reconstruct(int(i)) for i in I.ravel()])
+        np.testing.assert_array_equal(got, truth[I.ravel()])
+        assert idx.launch_count - launches <= 1                     # ONE gather kernel for all 135 calls
+        a = idx.reconstruct(int(I[0, 0]))
+        a[:] = 0
+        np.testing.assert_array_equal(idx.reconstruct(int(I[0, 0])), truth[I[0, 0]])
+        miss = int(np.setdiff1d(np.arange(3000), I.ravel())[0])
+        np.testing.assert_array_equal(idx.reconstruct(miss), truth[miss])
+        idx.add(xb[:10] + 1.0)
+        np.testing.assert_array_equal(idx.reconstruct(3005), idx.reconstruct_batch(np.array([3005]))[0])
+        with pytest.raises(RuntimeError):
+            idx.reconstruct(99999)
+
+
+def test_concurrent_searches_from_threads(pkg, oracle):
+    """Several Python threads searching the same index and their own indexes at once (a Flask dev server can call
+    predict concurrently, app.py:351): every handle serialises internally, ctypes releases the GIL inside the C call,
+    and every result must equal the single-threaded one."""
+    import threading
+    rng = np.random.default_rng(8)
+    xb = rng.integers(-2, 3, size=(20000, 64)).astype(np.float32)
+    xq = rng.integers(-2, 3, size=(64, 64)).astype(np.float32)
+    shared = pkg.FlatIndex(64, pkg.METRIC_L2, "bf16")
+    shared.add(xb)
+    Dref, Iref = shared.search(xq, 10)
+    D1ref, I1ref = shared.search(xq[:1], 10)
+    errors = []
+
+    def worker(t):
+        try:
+            own = pkg.FlatIndex(64, pkg.METRIC_L2, "bf16")
+            own.add(xb)
+            for it in range(15):
+                for index in (shared, own):
+                    D, I = index.search(xq, 10)
+                    assert np.array_equal(I, Iref) and np.array_equal(D, Dref)
+                    D1, I1 = index.search(xq[:1], 10)                   # streaming scorer (ticket / control block)
+                    assert np.array_equal(I1, I1ref) and np.array_equal(D1, D1ref)
+            own.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"thread {t}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors

@@ -232,6 +232,18 @@ def refscale():
              search_kernel_ms=vdb.index.last_kernel_ms()[0])
         if store == "f32":
             ours = [t.cpu().numpy() for t in out]
+            # the UNMODIFIED reference caller (per-neighbour index.reconstruct loop, restated in the oracle) on top of
+            # this index: module-replacement integration
+            qn_ = q.cpu().numpy()
+            for _ in range(2):
+                orc.retrieve_similar_vectors_oracle(vdb, qn_, K, Dm, query_paths=qpaths, exclude_self=True)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                v_, l_, p__, d_ = orc.retrieve_similar_vectors_oracle(vdb, qn_, K, Dm, query_paths=qpaths, exclude_self=True)
+            dtu = (time.perf_counter() - t0) / 5
+            emit(config="R: unmodified reference caller loop (search_batch + 256 x <=15 index.reconstruct calls) on this index, f32",
+                 ms=dtu * 1e3, batches_per_s=1.0 / dtu,
+                 identical_to_device_path=bool(np.array_equal(ours[0], v_) and np.array_equal(ours[1], l_)))
         vdb.index.close()
     torch.set_num_threads(os.cpu_count())
     ovdb = orc.OracleVectorDatabase(Cfg())
