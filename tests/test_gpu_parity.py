@@ -783,3 +783,25 @@ def test_concurrent_searches_from_threads(pkg, oracle):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("store", ["bf16", "f32"])
+def test_more_queries_than_one_internal_batch(pkg, oracle, store):
+    """nq > 65 536 is processed in internal batches (scratch reuse between batches, host and device paths)."""
+    import torch
+    rng = np.random.default_rng(12)
+    N, Dm, nq, k = 3000, 16, 70001, 5
+    xb = rng.integers(-2, 3, size=(N, Dm)).astype(np.float32)
+    xq = rng.integers(-2, 3, size=(nq, Dm)).astype(np.float32)
+    idx = pkg.FlatIndex(Dm, pkg.METRIC_L2, store)
+    idx.add(xb)
+    ref = oracle.FlatIndexOracle(Dm, pkg.METRIC_L2)
+    ref.add(xb)
+    Dr, Ir = ref.search(xq, k, direct=False)
+    D, I = idx.search(xq, k)
+    np.testing.assert_array_equal(I, Ir)
+    np.testing.assert_array_equal(D, Dr)
+    Dd, Id = idx.search(torch.from_numpy(xq).cuda(), k)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(Id.cpu().numpy(), Ir)
+    np.testing.assert_array_equal(Dd.cpu().numpy(), Dr)
