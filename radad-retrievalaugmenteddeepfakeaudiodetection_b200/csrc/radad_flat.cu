@@ -433,7 +433,28 @@ int launch_stream(rdb_handle* h, StreamParams& p, int blocks, int mode) {
             : launch_stream_mode<__nv_bfloat16, false>(h, p, blocks, mode);
 }
 
-constexpr int64_t kStreamFilterMinRows = 131072;   // the 1/64 sample must hold far more than 16 rows
+
+// FILTER (sampled pivot) needs a sample that is a known fraction of the rows: the pivot pass takes every
+// `sample_mul`-th warp step (each warp must own at least that many steps) and its rank-r key becomes the pivot.
+// Expected rows above the pivot = r * sample_mul, chosen >= 4k (k of them exist with overwhelming probability) and
+// << STREAM_FCAP; r <= 128 (what the LIST policies hold), so a sample of at most 1/4 of the rows is needed.
+int stream_rows_per_block(rdb_handle* h) {
+  const int blocks0 = int(std::min<int64_t>(h->num_sms, (h->n + 31) / 32));
+  return int(round_up((h->n + blocks0 - 1) / blocks0, 32));
+}
+int stream_sample_mul(rdb_handle* h, int rpb) {
+  const int nvec = (h->store == RDB_STORE_F32) ? h->d / 4 : h->dp / 8;
+  const int lpr_log2 = nvec >= 96 ? 5 : (nvec >= 48 ? 4 : 3);
+  const int rw = ((h->store == RDB_STORE_F32) ? 4 : 8) * (32 >> lpr_log2);        // rows per warp step
+  return std::min(STREAM_SAMPLE, rpb / (STREAM_WARPS * rw));
+}
+// rank of the sample whose key becomes the pivot: ~4k rows of the database should beat it (rank * sample_mul >= 4k)
+int stream_pivot_rank(int k, int sample_mul) {
+  return std::max(STREAM_PIVOT_RANK, (4 * k + sample_mul - 1) / std::max(sample_mul, 1));
+}
+bool stream_filter_ok(int k, int sample_mul) {
+  return k > 32 && sample_mul >= 4 && stream_pivot_rank(k, sample_mul) <= 128;
+}
 
 // The whole nq <= 4 search.  Host buffers go through one pinned staging area: one H2D copy of the queries, the
 // launches, ONE D2H copy of the packed results.
@@ -443,11 +464,13 @@ int search_stream(rdb_handle* h, const float* q, int nq, int k, int mem, int nor
   const bool host = mem == RDB_MEM_HOST;
   cudaStream_t s = h->stream;
   const float* labels = (h->labels && h->nlabels == h->n) ? h->labels : nullptr;
-  const int blocks0 = int(std::min<int64_t>(h->num_sms, (h->n + 31) / 32));
-  const int rpb = int(round_up((h->n + blocks0 - 1) / blocks0, 32));
+  const int rpb = stream_rows_per_block(h);
   const int S = int((h->n + rpb - 1) / rpb);
-  const int mode = k <= 32 ? STREAM_LIST1 : (h->n >= kStreamFilterMinRows ? STREAM_FILTER : STREAM_LIST4);
-  const int kc = std::max(k, STREAM_PIVOT_RANK);
+  const int sample_mul = stream_sample_mul(h, rpb);
+  const bool filter_ok = stream_filter_ok(k, sample_mul);
+  const int mode = k <= 32 ? STREAM_LIST1 : (filter_ok ? STREAM_FILTER : STREAM_LIST4);
+  const int pivot_rank = stream_pivot_rank(k, stream_sample_mul(h, stream_rows_per_block(h)));
+  const int kc = std::max(k, pivot_rank);
   CUDA_TRY(h, h->cand_key.ensure(size_t(nq) * S * kc * 4));
   CUDA_TRY(h, h->cand_idx.ensure(size_t(nq) * S * kc * 4));
   if (!h->stream_ctl.p) {
@@ -496,9 +519,9 @@ int search_stream(rdb_handle* h, const float* q, int nq, int k, int mem, int nor
     CUDA_TRY(h, h->fidx.ensure(size_t(4) * STREAM_FCAP * 4));
     p.fkey = h->fkey.as<float>(); p.fidx = h->fidx.as<int>();
     StreamParams ps = p;                       // 1) pivot from a strided 1/64 sample (LIST, k = 16)
-    ps.kout = STREAM_PIVOT_RANK; ps.step_mul = STREAM_SAMPLE; ps.use_pivot_out = 1;
+    ps.kout = pivot_rank; ps.step_mul = sample_mul; ps.use_pivot_out = 1;
     ps.out_dist = nullptr; ps.out_key = nullptr; ps.out_idx = nullptr; ps.out_lbl = nullptr; ps.out_qnorm = nullptr;
-    if ((rc = launch_stream(h, ps, S, STREAM_LIST1))) return rc;
+    if ((rc = launch_stream(h, ps, S, pivot_rank <= 32 ? STREAM_LIST1 : STREAM_LIST4))) return rc;
     if ((rc = launch_stream(h, p, S, STREAM_FILTER))) return rc;      // 2) full pass: append key >= pivot, rank, emit
     StreamParams pf = p;                       // 3) exits at once unless the FILTER pass raised the fallback flag
     pf.run_if_fallback = 1;
@@ -613,8 +636,9 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   const bool tc_ok = sixteen ? (k <= kMaxKTc && h->n >= TC_BN) : (k <= kMaxKSplit && h->n >= TC_BN);
   // small batches are a pure HBM stream of the stored rows: dedicated streaming scorer (exact fp32 for fp32 stores)
   const bool stream_ok = nq <= 4 && k <= 128 && h->n >= 1 && (sixteen || D % 4 == 0);
-  if (algo == RDB_ALGO_AUTO)
+  if (algo == RDB_ALGO_AUTO) {
     algo = (stream_ok && h->n >= 4096) ? RDB_ALGO_STREAM : ((tc_ok && h->n >= kMinRowsTc) ? RDB_ALGO_TC : RDB_ALGO_SIMT);
+  }
   if (algo == RDB_ALGO_STREAM && !stream_ok)
     return fail(h, RDB_ERR_UNSUPPORTED, "search: streaming scorer needs nq <= 4, k <= 128 (and D % 4 == 0 for fp32 stores)");
   if (algo == RDB_ALGO_TC && !tc_ok)

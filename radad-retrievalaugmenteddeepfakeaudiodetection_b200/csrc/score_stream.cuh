@@ -17,9 +17,10 @@
 //          gridDim.x block lists merged by the last block.
 //   FILTER (large k on large databases)  maintaining k = 100 sorted entries per warp costs more issue slots than the
 //          stream itself (each warp sees only N / 2368 rows, so ~10 % of its rows still insert).  Instead a first
-//          LIST launch over a 1/64 strided SAMPLE of the rows yields a per-query pivot (the sample's 16th best key:
-//          ~1000 rows of the whole database beat it), and the full pass merely appends the rows with key >= pivot to
-//          a per-query buffer; the last block ranks those ~1000 candidates by counting.  Exactness does not depend
+//          LIST launch over a strided SAMPLE of the rows (every m-th warp step, m = min(64, steps per warp) >= 4)
+//          yields a per-query pivot (the sample's rank-r key, r = max(16, 4k / m) <= 128: ~r m >= 4k rows of the whole
+//          database beat it), and the full pass merely appends the rows with key >= pivot to a per-query buffer; the
+//          last block sorts those ~400-1000 candidates (bitonic, shared memory) and emits the first k.  Exactness does not depend
 //          on the sample: the result is the exact top-k whenever k <= count <= capacity, and otherwise a flag makes
 //          the (always enqueued, normally empty) LIST launch redo the search.
 #pragma once
@@ -105,7 +106,7 @@ struct WarpList {
 enum { STREAM_LIST1 = 0, STREAM_LIST4 = 1, STREAM_FILTER = 2 };
 constexpr int STREAM_FCAP = 4096;       // FILTER: candidate slots per query
 constexpr int STREAM_SAMPLE = 64;       // FILTER: the pivot pass reads every 64th warp step of the rows
-constexpr int STREAM_PIVOT_RANK = 16;   // FILTER: pivot = this rank of the sample -> ~RANK * SAMPLE rows pass
+constexpr int STREAM_PIVOT_RANK = 16;   // FILTER: minimum pivot rank in the sample (host raises it for thin samples)
 
 struct StreamCtl {                      // device control block owned by the handle (zero-initialised once)
   unsigned int ticket;                  // blocks finished (self-resetting)
@@ -376,40 +377,54 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
     }
     if (p.run_if_fallback && threadIdx.x == 0) p.ctl->fallback = 0;
   } else {
-    // FILTER: rank the appended candidates by counting (key desc, id asc); each of rank < kout writes its slot
-    uint32_t* ck = reinterpret_cast<uint32_t*>(sm);               // [STREAM_FCAP] ordered keys
-    int* ci = reinterpret_cast<int*>(sm) + STREAM_FCAP;           // [STREAM_FCAP]
+    // FILTER: sort the appended candidates (key desc, id asc) with a block-wide bitonic sort of packed 64-bit words
+    // in shared memory (<= STREAM_FCAP entries = 32 KB) and emit the first kout
+    unsigned long long* cw = reinterpret_cast<unsigned long long*>(sm);
     bool failed = false;
     for (int q = 0; q < nq; ++q) {
       const int cnt = __ldcg(&p.ctl->fcount[q]);
       if (cnt > STREAM_FCAP || cnt < min(kout, N)) { failed = true; continue; }
+      int np2 = 1;
+      while (np2 < cnt) np2 <<= 1;
       __syncthreads();
-      for (int i = threadIdx.x; i < cnt; i += STREAM_THREADS) {
-        ck[i] = ordered_f32(__ldcg(p.fkey + q * STREAM_FCAP + i));
-        ci[i] = __ldcg(p.fidx + q * STREAM_FCAP + i);
+      for (int i = threadIdx.x; i < np2; i += STREAM_THREADS) {
+        unsigned long long wv = 0ull;                       // padding sorts last
+        if (i < cnt) {
+          const uint32_t ok = ordered_f32(__ldcg(p.fkey + q * STREAM_FCAP + i));
+          const uint32_t id = uint32_t(__ldcg(p.fidx + q * STREAM_FCAP + i));
+          wv = (static_cast<unsigned long long>(ok) << 32) | (0xFFFFFFFFu - id);   // larger = better (lower id wins ties)
+        }
+        cw[i] = wv;
       }
       __syncthreads();
-      for (int i = threadIdx.x; i < cnt; i += STREAM_THREADS) {
-        const uint32_t mk = ck[i];
-        const int mi = ci[i];
-        int rank = 0;
-        for (int j = 0; j < cnt; ++j) rank += (ck[j] > mk || (ck[j] == mk && ci[j] < mi)) ? 1 : 0;
-        if (rank < kout) {
-          const long long o = (long long)q * kout + rank;
-          const float kv = unordered_f32(mk);
+      for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int i = threadIdx.x; i < (np2 >> 1); i += STREAM_THREADS) {
+            const int lo = ((i / stride) * (stride << 1)) + (i % stride), hi = lo + stride;
+            const bool desc = ((lo & size) == 0);           // descending runs first -> whole array descending
+            const unsigned long long a = cw[lo], b = cw[hi];
+            if ((a < b) == desc) { cw[lo] = b; cw[hi] = a; }
+          }
+          __syncthreads();
+        }
+      }
+      for (int r = threadIdx.x; r < kout; r += STREAM_THREADS) {
+        const long long o = (long long)q * kout + r;
+        if (r < cnt) {
+          const unsigned long long wv = cw[r];
+          const float kv = unordered_f32(uint32_t(wv >> 32));
+          const int mi = int(0xFFFFFFFFu - uint32_t(wv & 0xFFFFFFFFull));
           if (p.out_dist) p.out_dist[o] = p.metric_l2 ? fmaxf(0.f, s_qnorm[q] - kv) : kv;
           p.out_idx[o] = (long long)mi + p.id_offset;
           if (p.out_key) p.out_key[o] = kv;
           if (p.out_lbl) p.out_lbl[o] = p.labels ? p.labels[mi] : 0.f;
+        } else {
+          // fewer rows than kout in the whole index: pad (faiss convention)
+          if (p.out_dist) p.out_dist[o] = p.metric_l2 ? CUDART_INF_F : -CUDART_INF_F;
+          p.out_idx[o] = -1;
+          if (p.out_key) p.out_key[o] = -CUDART_INF_F;
+          if (p.out_lbl) p.out_lbl[o] = 0.f;
         }
-      }
-      // fewer rows than kout in the whole index: pad (faiss convention)
-      for (int r = cnt + threadIdx.x; r < kout; r += STREAM_THREADS) {
-        const long long o = (long long)q * kout + r;
-        if (p.out_dist) p.out_dist[o] = p.metric_l2 ? CUDART_INF_F : -CUDART_INF_F;
-        p.out_idx[o] = -1;
-        if (p.out_key) p.out_key[o] = -CUDART_INF_F;
-        if (p.out_lbl) p.out_lbl[o] = 0.f;
       }
     }
     __syncthreads();

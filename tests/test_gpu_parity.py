@@ -122,9 +122,10 @@ CASES = [
     ("stream_l2_f32_q4_k128",  9000,  128, 4, 128, "L2", False, "f32", "stream"),
     ("stream_l2_bf16_q2_k33",  5001,  64,  2, 33,  "L2", False, "bf16", "stream"),
     # large k on a large database: sampled pivot + filter pass (N >= 131072, k > 32)
-    ("stream_filter_cos_bf16_q1_k100", 200000, 128, 1, 100, "IP", True,  "bf16", "stream"),
-    ("stream_filter_l2_f32_q3_k64",    150000, 64,  3, 64,  "L2", False, "f32",  "stream"),
-    ("stream_filter_l2_f16_q4_k128",   140001, 72,  4, 128, "L2", False, "f16",  "stream"),
+    # (the pivot pass samples every m-th warp step, m = min(64, steps per warp), and needs 16 m >= 4 k: millions of rows)
+    ("stream_filter_cos_bf16_q1_k100", 2000000, 64, 1, 100, "IP", True,  "bf16", "stream"),
+    ("stream_filter_l2_f32_q3_k64",    1000000, 64, 3, 64,  "L2", False, "f32",  "stream"),
+    ("stream_list4_l2_f16_q4_k128",    140001, 72,  4, 128, "L2", False, "f16",  "stream"),   # too few rows: LIST policy
     # large k on the tensor cores: local-memory reservoir + exact bisection prune (C5: k = 100, D = 256)
     ("ip_bf16_tc_k100", 60000, 256, 300, 100, "IP", True,  "bf16", "tc"),
     ("l2_bf16_tc_k64",  20000, 128, 130, 64,  "L2", False, "bf16", "tc"),
@@ -221,7 +222,7 @@ def test_stream_filter_fallback_on_heavy_ties(pkg, oracle, metric_s, store):
     must deliver the exact result (ids and distances bit-for-bit, lowest id on ties).  A second query set whose
     candidates fit exercises the filter path itself, and repeating the calls checks the self-resetting counters."""
     rng = np.random.default_rng(21)
-    N, Dm, k = 140000, 16, 50
+    N, Dm, k = 2000000, 16, 50
     xb = rng.integers(-1, 2, size=(N, Dm)).astype(np.float32)
     xq = rng.integers(-1, 2, size=(3, Dm)).astype(np.float32)
     metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
