@@ -146,70 +146,99 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
 //   cert[q] = 1  iff  exact_key[kout-1] > approx_worst + B        (or the candidate set holds every row).
 // Uncertified queries are appended to `uncert_list` (count in uncert_count) for the exact fallback.
 constexpr int RERANK_MAX_KC = 128;
+constexpr int RERANK_THREADS = 128;
+// One BLOCK (4 warps) per query: the warps share the candidates (each exact dot product runs 4 independent 128-bit
+// loads per lane deep, so long rows -- the reference's D = 5376 -- are bandwidth- not latency-bound), then the block
+// ranks the kc exact keys by counting and thread 0 evaluates the certificate.
 template <bool L2>
-__global__ void __launch_bounds__(128) rerank_exact_kernel(const long long* __restrict__ cand_idx,
-                                                           const float* __restrict__ cand_key, int Q, int kc, int kout,
-                                                           const float* __restrict__ qf,
-                                                           const float* __restrict__ master,
-                                                           const float* __restrict__ ynorm, int D, float eps,
-                                                           const float* __restrict__ qnorm,
-                                                           const float* __restrict__ ynorm_max, long long ntotal,
-                                                           float* __restrict__ out_key,
-                                                           long long* __restrict__ out_idx,
-                                                           int* __restrict__ uncert_list,
-                                                           int* __restrict__ uncert_count) {
-  __shared__ uint32_t s_ok[4][RERANK_MAX_KC];     // ordered exact keys (0 = empty slot)
-  __shared__ long long s_id[4][RERANK_MAX_KC];
-  __shared__ float s_kth[4];
+__global__ void __launch_bounds__(RERANK_THREADS) rerank_exact_kernel(const long long* __restrict__ cand_idx,
+                                                                      const float* __restrict__ cand_key, int Q, int kc,
+                                                                      int kout, const float* __restrict__ qf,
+                                                                      const float* __restrict__ master,
+                                                                      const float* __restrict__ ynorm, int D, float eps,
+                                                                      const float* __restrict__ qnorm,
+                                                                      const float* __restrict__ ynorm_max,
+                                                                      long long ntotal, float* __restrict__ out_key,
+                                                                      long long* __restrict__ out_idx,
+                                                                      int* __restrict__ uncert_list,
+                                                                      int* __restrict__ uncert_count) {
+  __shared__ uint32_t s_ok[RERANK_MAX_KC];     // ordered exact keys (0 = empty slot)
+  __shared__ long long s_id[RERANK_MAX_KC];
+  __shared__ float s_kth;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int q = blockIdx.x * (blockDim.x >> 5) + w;
+  const int q = blockIdx.x;
   if (q >= Q) return;
   const float* qr = qf + (long long)q * D;
-  float approx_worst = CUDART_INF_F;
-  int nvalid = 0;
-  for (int j = 0; j < kc; ++j) {
+  const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(qr) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(master) & 15) == 0);
+  for (int j = w; j < kc; j += RERANK_THREADS / 32) {
     const long long id = cand_idx[(long long)q * kc + j];
     if (id < 0) {
-      if (lane == 0) { s_ok[w][j] = 0u; s_id[w][j] = 0x7FFFFFFFFFFFFFFFll; }
+      if (lane == 0) { s_ok[j] = 0u; s_id[j] = 0x7FFFFFFFFFFFFFFFll; }
       continue;
     }
-    ++nvalid;
-    approx_worst = fminf(approx_worst, cand_key[(long long)q * kc + j]);
     const float* yr = master + id * (long long)D;
     float s = 0.f;
-    for (int c = lane; c < D; c += 32) s = fmaf(qr[c], __ldg(yr + c), s);
+    if (vec4) {
+      const float4* q4 = reinterpret_cast<const float4*>(qr);
+      const float4* y4 = reinterpret_cast<const float4*>(yr);
+      const int n4 = D >> 2;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int c = lane;
+      for (; c + 96 < n4; c += 128) {
+        const float4 y0 = __ldg(y4 + c), y1 = __ldg(y4 + c + 32), y2 = __ldg(y4 + c + 64), y3 = __ldg(y4 + c + 96);
+        const float4 x0 = q4[c], x1 = q4[c + 32], x2 = q4[c + 64], x3 = q4[c + 96];
+        a0 = fmaf(x0.x, y0.x, a0); a0 = fmaf(x0.y, y0.y, a0); a0 = fmaf(x0.z, y0.z, a0); a0 = fmaf(x0.w, y0.w, a0);
+        a1 = fmaf(x1.x, y1.x, a1); a1 = fmaf(x1.y, y1.y, a1); a1 = fmaf(x1.z, y1.z, a1); a1 = fmaf(x1.w, y1.w, a1);
+        a2 = fmaf(x2.x, y2.x, a2); a2 = fmaf(x2.y, y2.y, a2); a2 = fmaf(x2.z, y2.z, a2); a2 = fmaf(x2.w, y2.w, a2);
+        a3 = fmaf(x3.x, y3.x, a3); a3 = fmaf(x3.y, y3.y, a3); a3 = fmaf(x3.z, y3.z, a3); a3 = fmaf(x3.w, y3.w, a3);
+      }
+      for (; c < n4; c += 32) {
+        const float4 y0 = __ldg(y4 + c);
+        const float4 x0 = q4[c];
+        a0 = fmaf(x0.x, y0.x, a0); a0 = fmaf(x0.y, y0.y, a0); a0 = fmaf(x0.z, y0.z, a0); a0 = fmaf(x0.w, y0.w, a0);
+      }
+      s = (a0 + a1) + (a2 + a3);
+    } else {
+      for (int c = lane; c < D; c += 32) s = fmaf(qr[c], __ldg(yr + c), s);
+    }
     s = warp_sum(s);
     const float key = L2 ? fmaf(2.0f, s, -ynorm[id]) : s;
-    if (lane == 0) { s_ok[w][j] = ordered_f32(key); s_id[w][j] = id; }
+    if (lane == 0) { s_ok[j] = ordered_f32(key); s_id[j] = id; }
   }
-  if (lane == 0) s_kth[w] = -CUDART_INF_F;
-  __syncwarp();
-  // rank by counting (kc <= 128): valid candidates by (key desc, id asc), empty slots after them in slot order
-  int empties_before = 0;
-  for (int i0 = 0; i0 < kc; i0 += 32) {
-    const int i = i0 + lane;
-    const bool in = i < kc;
-    const uint32_t mok = in ? s_ok[w][i] : 0u;
-    const long long mid = in ? s_id[w][i] : 0x7FFFFFFFFFFFFFFFll;
-    const bool empty = in && mok == 0u;
-    const uint32_t emask = __ballot_sync(0xffffffffu, empty);
-    if (in) {
-      int pos;
-      if (!empty) {
-        pos = 0;
-        for (int j = 0; j < kc; ++j) pos += (j != i && head_better(s_ok[w][j], s_id[w][j], mok, mid)) ? 1 : 0;
-        if (pos == kout - 1) s_kth[w] = unordered_f32(mok);
-      } else {
-        pos = nvalid + empties_before + __popc(emask & ((1u << lane) - 1u));
-      }
-      out_key[(long long)q * kc + pos] = empty ? -CUDART_INF_F : unordered_f32(mok);
-      out_idx[(long long)q * kc + pos] = empty ? -1 : mid;
+  if (threadIdx.x == 0) s_kth = -CUDART_INF_F;
+  __syncthreads();
+  // rank by counting (kc <= 128 = one candidate per thread): valid candidates by (key desc, id asc), empty slots
+  // after them in slot order
+  const int i = threadIdx.x;
+  const bool in = i < kc;
+  const uint32_t mok = in ? s_ok[i] : 0u;
+  const long long mid = in ? s_id[i] : 0x7FFFFFFFFFFFFFFFll;
+  const bool empty = in && mok == 0u;
+  int nvalid = 0, empties_before = 0;
+  for (int j = 0; j < kc; ++j) {
+    const bool ej = s_ok[j] == 0u;
+    nvalid += ej ? 0 : 1;
+    empties_before += (ej && j < i) ? 1 : 0;
+  }
+  if (in) {
+    int pos;
+    if (!empty) {
+      pos = 0;
+      for (int j = 0; j < kc; ++j) pos += (j != i && head_better(s_ok[j], s_id[j], mok, mid)) ? 1 : 0;
+      if (pos == kout - 1) s_kth = unordered_f32(mok);
+    } else {
+      pos = nvalid + empties_before;
     }
-    empties_before += __popc(emask);
+    out_key[(long long)q * kc + pos] = empty ? -CUDART_INF_F : unordered_f32(mok);
+    out_idx[(long long)q * kc + pos] = empty ? -1 : mid;
   }
-  __syncwarp();
-  if (lane == 0) {
-    const float kth_key = s_kth[w];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float approx_worst = CUDART_INF_F;
+    for (int j = 0; j < kc; ++j)
+      if (cand_idx[(long long)q * kc + j] >= 0) approx_worst = fminf(approx_worst, cand_key[(long long)q * kc + j]);
+    const float kth_key = s_kth;
     const bool has = nvalid >= kout;
     const float bound = eps * sqrtf(qnorm[q]) * sqrtf(*ynorm_max) * (L2 ? 2.0f : 1.0f);
     const bool ok = (nvalid >= ntotal) || (nvalid == kc && has && kth_key > approx_worst + bound);

@@ -552,8 +552,14 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
     const int ntiles = int((h->n + TC_BN - 1) / TC_BN);
     const int cg = tc_cta_group(qv.nq, nterms, h->d);
     const int nqg = (qv.nq + TC_BM * cg - 1) / (TC_BM * cg);
-    // large k: per-unit selection overhead (reservoir warm-up, final sort) is worth ~64 tiles -> fewer, longer units
-    S = choose_splits(nqg, ntiles, h->num_sms / cg, 256 / TC_LISTS, kc > 32 ? 64 : 4, &tpc, kc > 32 ? 64.0 : 2.0);
+    // large k: per-unit selection overhead (reservoir warm-up, final sort) is worth ~64 tiles -> fewer, longer units.
+    // The minimum unit length is expressed in tiles of the C3 shape (12 K-slices, one term): long rows / three terms
+    // make every tile proportionally longer, so small databases at the reference's D = 5376 still fill the machine.
+    const int slices_per_tile = ((h->d + TC_BK - 1) / TC_BK) * nterms;
+    const int base_min = kc > 32 ? 64 : 4;
+    const int min_tiles = std::max(1, std::min(base_min, base_min * 12 / slices_per_tile));
+    S = choose_splits(nqg, ntiles, h->num_sms / cg, 256 / TC_LISTS, min_tiles, &tpc,
+                      (kc > 32 ? 64.0 : 2.0) * min_tiles / base_min);
     CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * TC_LISTS * kc * 4));
     CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * TC_LISTS * kc * 4));
     if (timed) cudaEventRecord(h->ev0, s);
@@ -730,10 +736,11 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
       {
         const int warps = 4;
         dim3 grid((nb + warps - 1) / warps), block(32 * warps);
-        if (l2) rerank_exact_kernel<true><<<grid, block, 0, s>>>(
+        dim3 rgrid(nb), rblock(RERANK_THREADS);                       // re-rank: one block per query
+        if (l2) rerank_exact_kernel<true><<<rgrid, rblock, 0, s>>>(
             h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, qv.qf, h->master, h->ynorm, D, eps, qv.qnorm,
             h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount);
-        else rerank_exact_kernel<false><<<grid, block, 0, s>>>(
+        else rerank_exact_kernel<false><<<rgrid, rblock, 0, s>>>(
             h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, qv.qf, h->master, h->ynorm, D, eps, qv.qnorm,
             h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount);
         h->launches++;
