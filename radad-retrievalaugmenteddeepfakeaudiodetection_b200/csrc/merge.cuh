@@ -28,31 +28,34 @@ __device__ __forceinline__ bool head_better(uint32_t ok_a, long long id_a, uint3
 // One warp folds the L lists of query q.  Candidate loads are L2-coherent (ld.cg), so the function may also run in
 // the kernel that produced the lists (the streaming scorer's last block) after a __threadfence().  kth_out (optional)
 // receives the key of rank kout - 1 (-inf when fewer candidates exist); every out_* pointer may be null.
-template <typename IdxT>
+template <typename IdxT, bool STAGED = false, int LPL = MERGE_LPL>
 __device__ __forceinline__ void merge_lists_warp(const float* key_in, const IdxT* idx_in, const float* lbl_in, int q, int L,
                                                  int kc, int kout, int metric_l2, const float* qnorm, long long id_offset,
                                                  const float* labels, float* out_dist, long long* out_idx,
                                                  float* out_lbl, float* out_key, int lane, float* kth_out) {
-  const long long qbase = (long long)q * L * kc;
+  // STAGED: key_in / idx_in point at this query's lists copied to shared memory (plain loads, base 0)
+  const long long qbase = STAGED ? 0ll : (long long)q * L * kc;
+  auto ld_idx = [&](long long o) -> long long { return STAGED ? (long long)idx_in[o] : (long long)__ldcg(idx_in + o); };
+  auto ld_key = [&](long long o) -> float { return STAGED ? key_in[o] : __ldcg(key_in + o); };
 
   // Per list: the head and (prefetched up-front, so all loads of the prologue are independent) the entry behind it.
   // With many lists per query most lists contribute at most two results, so the dependent load after a win -- one L2
   // round trip per output rank -- is paid only from a list's third entry on.
-  int ptr[MERGE_LPL];
-  uint32_t hok[MERGE_LPL], sok[MERGE_LPL];
-  long long hid[MERGE_LPL], sid[MERGE_LPL];
-  float hkey[MERGE_LPL], skey[MERGE_LPL];
+  int ptr[LPL];
+  uint32_t hok[LPL], sok[LPL];
+  long long hid[LPL], sid[LPL];
+  float hkey[LPL], skey[LPL];
 #pragma unroll
-  for (int i = 0; i < MERGE_LPL; ++i) {
+  for (int i = 0; i < LPL; ++i) {
     ptr[i] = 0; hok[i] = 0; hid[i] = 0x7FFFFFFFFFFFFFFFll; hkey[i] = 0.f;
     sok[i] = 0; sid[i] = 0x7FFFFFFFFFFFFFFFll; skey[i] = 0.f;
     const int l = lane + 32 * i;
     if (l < L && kc > 0) {
       const long long o0 = qbase + (long long)l * kc;
-      const long long id = (long long)__ldcg(idx_in + o0);
-      const float kv = __ldcg(key_in + o0);
+      const long long id = ld_idx(o0);
+      const float kv = ld_key(o0);
       long long id2 = -1; float kv2 = 0.f;
-      if (kc > 1) { id2 = (long long)__ldcg(idx_in + o0 + 1); kv2 = __ldcg(key_in + o0 + 1); }
+      if (kc > 1) { id2 = ld_idx(o0 + 1); kv2 = ld_key(o0 + 1); }
       if (id >= 0) { hkey[i] = kv; hok[i] = ordered_f32(kv); hid[i] = id; }
       if (id >= 0 && id2 >= 0) { skey[i] = kv2; sok[i] = ordered_f32(kv2); sid[i] = id2; }
     }
@@ -63,7 +66,7 @@ __device__ __forceinline__ void merge_lists_warp(const float* key_in, const IdxT
     // lane-local best head
     uint32_t bok = 0; long long bid = 0x7FFFFFFFFFFFFFFFll; int bi = 0;
 #pragma unroll
-    for (int i = 0; i < MERGE_LPL; ++i)
+    for (int i = 0; i < LPL; ++i)
       if (head_better(hok[i], hid[i], bok, bid)) { bok = hok[i]; bid = hid[i]; bi = i; }
     // warp arg-best
     uint32_t wok = bok; long long wid = bid; int wl = lane;
@@ -90,7 +93,7 @@ __device__ __forceinline__ void merge_lists_warp(const float* key_in, const IdxT
       float kv = 0.f; int p = 0;
       uint32_t nok = 0; long long nid = 0x7FFFFFFFFFFFFFFFll; float nkey = 0.f;
 #pragma unroll
-      for (int i = 0; i < MERGE_LPL; ++i) if (i == bi) { kv = hkey[i]; p = ptr[i]; nok = sok[i]; nid = sid[i]; nkey = skey[i]; }
+      for (int i = 0; i < LPL; ++i) if (i == bi) { kv = hkey[i]; p = ptr[i]; nok = sok[i]; nid = sid[i]; nkey = skey[i]; }
       const int l = lane + 32 * bi;
       const long long src = qbase + (long long)l * kc + p;
       if (out_dist) {
@@ -100,24 +103,33 @@ __device__ __forceinline__ void merge_lists_warp(const float* key_in, const IdxT
       }
       if (out_idx) out_idx[o] = wid + id_offset;   // wid is a local id when id_offset != 0, already global otherwise
       if (out_key) out_key[o] = kv;
-      if (out_lbl) out_lbl[o] = lbl_in ? __ldcg(lbl_in + src) : (labels ? labels[wid] : 0.f);
+      // labels[] indexed by row id: gathered AFTER the loop, all ranks at once (a random read per rank inside the
+      // loop would stall every round for a DRAM round trip)
+      if (out_lbl && (lbl_in || !labels || !out_idx)) out_lbl[o] = lbl_in ? __ldcg(lbl_in + (long long)q * L * kc + (src - qbase)) : 0.f;
       ++p;
       if (p >= 2) {                                // beyond the prefetched pair: dependent load
         nok = 0; nid = 0x7FFFFFFFFFFFFFFFll; nkey = 0.f;
         if (p < kc) {
-          const long long id = (long long)__ldcg(idx_in + src + 1);
-          if (id >= 0) { nkey = __ldcg(key_in + src + 1); nok = ordered_f32(nkey); nid = id; }
+          const long long id = ld_idx(src + 1);
+          if (id >= 0) { nkey = ld_key(src + 1); nok = ordered_f32(nkey); nid = id; }
         }
       }
 #pragma unroll
-      for (int i = 0; i < MERGE_LPL; ++i) if (i == bi) { ptr[i] = p; hok[i] = nok; hid[i] = nid; hkey[i] = nkey; }
+      for (int i = 0; i < LPL; ++i) if (i == bi) { ptr[i] = p; hok[i] = nok; hid[i] = nid; hkey[i] = nkey; }
     }
     __syncwarp();
+  }
+  if (out_lbl && out_idx && !lbl_in && labels) {
+    __syncwarp();
+    for (int r = lane; r < kout; r += 32) {
+      const long long gid = __ldcg(out_idx + (long long)q * kout + r);
+      out_lbl[(long long)q * kout + r] = gid >= 0 ? __ldg(labels + (gid - id_offset)) : 0.f;
+    }
   }
   if (kth_out) *kth_out = kth;
 }
 
-template <typename IdxT>
+template <typename IdxT, int LPL = MERGE_LPL>
 __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restrict__ key_in,
                                                           const IdxT* __restrict__ idx_in,
                                                           const float* __restrict__ lbl_in, int Q, int L, int kc,
@@ -127,13 +139,36 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
                                                           long long* __restrict__ out_idx,
                                                           float* __restrict__ out_lbl,
                                                           float* __restrict__ out_key,
-                                                          const int* __restrict__ run_if = nullptr) {
+                                                          const int* __restrict__ run_if = nullptr,
+                                                          int stage_bytes_per_warp = 0) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= Q) return;
   if (run_if && __ldcg(run_if) == 0) return;
-  merge_lists_warp<IdxT>(key_in, idx_in, lbl_in, q, L, kc, kout, metric_l2, qnorm, id_offset, labels, out_dist, out_idx,
-                         out_lbl, out_key, lane, nullptr);
+  if (stage_bytes_per_warp > 0) {
+    // long merges (many lists x large k): every output rank would otherwise pay a dependent L2 round trip after a list's
+    // second entry.  Copy this query's L x kc candidates to shared memory once (coalesced) and merge from there.
+    extern __shared__ __align__(16) unsigned char merge_smem[];
+    unsigned char* mine = merge_smem + size_t(threadIdx.x >> 5) * stage_bytes_per_warp;
+    const int n = L * kc;
+    IdxT* sidx = reinterpret_cast<IdxT*>(mine);                                     // [n] ids first (8-byte aligned)
+    float* skey = reinterpret_cast<float*>(mine + size_t(n) * sizeof(IdxT));        // [n] keys
+    const long long qbase = (long long)q * n;
+    for (int i = lane; i < n; i += 32) { sidx[i] = __ldcg(idx_in + qbase + i); skey[i] = __ldcg(key_in + qbase + i); }
+    __syncwarp();
+    merge_lists_warp<IdxT, true, LPL>(skey, sidx, lbl_in, q, L, kc, kout, metric_l2, qnorm, id_offset, labels, out_dist,
+                                 out_idx, out_lbl, out_key, lane, nullptr);
+    return;
+  }
+  merge_lists_warp<IdxT, false, LPL>(key_in, idx_in, lbl_in, q, L, kc, kout, metric_l2, qnorm, id_offset, labels, out_dist,
+                                     out_idx, out_lbl, out_key, lane, nullptr);
+}
+
+// host helper: bytes of dynamic shared memory per warp for the staged form, or 0 when staging does not pay / fit
+template <typename IdxT>
+inline size_t merge_stage_bytes(int L, int kc, int kout) {
+  const size_t b = (size_t(L) * kc * (sizeof(IdxT) + 4) + 15) & ~size_t(15);
+  return (kout >= 16 && L >= 4 && b <= 24 * 1024) ? b : 0;
 }
 
 // Exact fp32 re-rank.  One warp per query.

@@ -612,12 +612,17 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
 int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float* qnorm, bool shard_mode, float* d_a,
                     int64_t* d_i, float* d_l, long long id_offset, const float* labels, float* raw_key,
                     const int* run_if = nullptr) {
-  const int warps = 4;
+  const size_t stage = merge_stage_bytes<int>(L, kc, kout);
+  const int warps = stage > 12 * 1024 ? 2 : 4;             // <= 48 KB of dynamic shared memory per block
   dim3 grid((nq + warps - 1) / warps), block(32 * warps);
-  merge_lists_kernel<int><<<grid, block, 0, h->stream>>>(
-      h->cand_key.as<float>(), h->cand_idx.as<int>(), nullptr, nq, L, kc, kout, h->metric == RDB_METRIC_L2 ? 1 : 0,
-      qnorm, id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l,
-      shard_mode ? d_a : raw_key, run_if);
+  // lists per lane: the per-round work of the merge is proportional to it, so use the smallest that holds L lists
+#define MERGE_LOCAL(LPL)                                                                                         \
+  merge_lists_kernel<int, LPL><<<grid, block, stage * warps, h->stream>>>(                                       \
+      h->cand_key.as<float>(), h->cand_idx.as<int>(), nullptr, nq, L, kc, kout, h->metric == RDB_METRIC_L2 ? 1 : 0, \
+      qnorm, id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l,              \
+      shard_mode ? d_a : raw_key, run_if, int(stage))
+  if (L <= 32) MERGE_LOCAL(1); else if (L <= 64) MERGE_LOCAL(2); else if (L <= 128) MERGE_LOCAL(4); else MERGE_LOCAL(8);
+#undef MERGE_LOCAL
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return RDB_OK;
