@@ -117,3 +117,44 @@ def test_lockstep_membership_arithmetic():
             assert len(set(ms)) == 1 and ms[0] == len(ms), (nqt, S, ngroups, key, ms)
             total += len(ms)
         assert total == num_units
+
+
+def test_reconstruct_cache_logic_without_gpu(pkg):
+    """flat_index._ReconstructCache (host logic only): lazy -- nothing is fetched until reconstruct is called; ONE
+    batched fetch of the unique valid ids of the last search; hits are independent copies; misses, ids of an older
+    search and oversized batches fall through to the single-row path."""
+    import numpy as np
+    from importlib import import_module
+    fi = import_module(pkg.__name__ + ".flat_index")
+
+    class Fake(fi._ReconstructCache):
+        d = 4
+
+        def __init__(self):
+            self.batched, self.single = [], []
+
+        def reconstruct_batch(self, ids):
+            self.batched.append(np.array(ids))
+            return np.stack([np.full(4, float(i), np.float32) for i in ids])
+
+        def reconstruct(self, i):
+            hit = self._rc_lookup(int(i))
+            if hit is not None:
+                return hit
+            self.single.append(int(i))
+            return np.full(4, float(i), np.float32)
+
+    f = Fake()
+    assert f.reconstruct(3)[0] == 3 and f.single == [3] and not f.batched        # no search yet: single-row path
+    f._rc_note_search(np.array([[5, 2, -1], [2, 9, 5]], dtype=np.int64))
+    assert not f.batched                                                            # lazy
+    a = f.reconstruct(9)
+    assert len(f.batched) == 1 and list(f.batched[0]) == [2, 5, 9]                  # unique, valid, sorted
+    a[:] = -1
+    assert f.reconstruct(9)[0] == 9 and f.reconstruct(2)[0] == 2 and len(f.batched) == 1
+    assert f.reconstruct(7)[0] == 7 and f.single == [3, 7]                          # not in the result: miss
+    f._rc_note_search(np.array([[1]], dtype=np.int64))                              # next search drops the cache
+    assert f.reconstruct(5)[0] == 5 and f.single == [3, 7, 5] and len(f.batched) == 2
+    f._RC_MAX_BYTES = 8                                                             # oversized batch: never fetched
+    f._rc_note_search(np.array([[4, 6]], dtype=np.int64))
+    assert f.reconstruct(4)[0] == 4 and len(f.batched) == 2 and f.single[-1] == 4
