@@ -2,6 +2,7 @@
 invariants are pinned here -- exact equality with a float64 lexsort on lattice data (ties -> lowest id), shard
 invariance, k clamping, BLAS-expansion vs direct agreement."""
 import numpy as np
+import pytest
 from hypothesis import given, settings, strategies as st
 
 
@@ -74,3 +75,30 @@ def test_blas_and_direct_paths_agree_within_fp32(oracle, n, seed):
     Db, Ib = idx.search(xq, 5, direct=True)
     st_ = oracle.compare_topk(Da, Ia, Db, Ib, lambda ids: idx.exact_scores(xq, ids), oracle.METRIC_L2, 1e-5, 1e-4)
     assert st_["recall"] >= 0.99
+
+
+def test_oracle_agrees_with_sklearn_bruteforce(oracle):
+    """FAISS (the reference's dependency) is not installable here, so as an INDEPENDENT third-party check of the
+    oracle's flat-kNN semantics: scikit-learn's brute-force NearestNeighbors must return the same neighbours
+    (squared-L2 ascending == euclidean ascending; inner product on normalised rows == cosine similarity descending)."""
+    import numpy as np
+    sk = pytest.importorskip("sklearn.neighbors")
+    rng = np.random.default_rng(2024)
+    xb = rng.standard_normal((4000, 48)).astype(np.float32)
+    xq = rng.standard_normal((60, 48)).astype(np.float32)
+    k = 12
+    ref = oracle.FlatIndexOracle(48, oracle.METRIC_L2)
+    ref.add(xb)
+    D, I = ref.search(xq, k, direct=True)
+    nn = sk.NearestNeighbors(n_neighbors=k, algorithm="brute", metric="euclidean").fit(xb.astype(np.float64))
+    Ds, Is = nn.kneighbors(xq.astype(np.float64))
+    np.testing.assert_array_equal(I, Is)
+    np.testing.assert_allclose(D, Ds ** 2, rtol=2e-5, atol=1e-4)
+    xbn, xqn = oracle.maybe_normalize(xb, True), oracle.maybe_normalize(xq, True)
+    refc = oracle.FlatIndexOracle(48, oracle.METRIC_IP)
+    refc.add(xbn)
+    Dc, Ic = refc.search(xqn, k)
+    nnc = sk.NearestNeighbors(n_neighbors=k, algorithm="brute", metric="cosine").fit(xb.astype(np.float64))
+    Dsc, Isc = nnc.kneighbors(xq.astype(np.float64))
+    np.testing.assert_array_equal(Ic, Isc)
+    np.testing.assert_allclose(Dc, 1.0 - Dsc, rtol=0, atol=2e-6)
