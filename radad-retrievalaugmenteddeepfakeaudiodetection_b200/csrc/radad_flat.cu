@@ -27,6 +27,7 @@
 #include "score_simt.cuh"
 #include "score_stream.cuh"
 #include "score_tc.cuh"
+#include "select_large.cuh"
 
 using namespace rdb;
 
@@ -95,6 +96,7 @@ struct rdb_handle {
   // scratch
   DevBuf add_stage, q_stage, qf, qhi, qlo, qnorm, cand_key, cand_idx, o_dist, o_idx, o_lbl, ids_stage, rec_stage;
   DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l, gthr, tcsync, stream_ctl, fkey, fidx;
+  DevBuf lk_scores;               // large-k path: dense keys of one (query block x row chunk)
   void* pin = nullptr;            // pinned host staging of the small-batch path
   size_t pin_bytes = 0;
   float* d_ynorm_max = nullptr;   // max |y|^2 over the shard (device scalar; feeds the re-rank certificate)
@@ -218,7 +220,7 @@ int launch_simt_t(rdb_handle* h, const T* Q, const T* Y, int nq, int ld, int nqt
   auto kern = score_select_simt_kernel<KT, L2, T, ALIGNED>;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt_smem_bytes()));
   kern<<<dim3(unsigned(nqt) * unsigned(S)), dim3(256), simt_smem_bytes(), h->stream>>>(
-      Q, Y, h->ynorm, nq, int(h->n), h->d, ld, nqt, S, rows_per_chunk, ck, ci, kout);
+      Q, Y, h->ynorm, nq, int(h->n), h->d, ld, nqt, S, rows_per_chunk, ck, ci, kout, nullptr, 0ll, 0);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return RDB_OK;
@@ -378,7 +380,11 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
 }
 
 constexpr int64_t kQueryBatch = 65536;
-constexpr int kMaxK = 128;
+constexpr int kMaxK = 128;          // fused selectors (register list / reservoir / streaming lists)
+constexpr int kMaxKLarge = SELK_MAXK;   // 128 < k <= 2048: dense keys + radix select (run_largek); faiss-gpu's own limit
+constexpr int64_t kQueryBatchLargeK = 4096;
+constexpr int kLargeKQueryBlock = 256;                // queries per dense key block (two SIMT query tiles)
+constexpr int64_t kLargeKRowsDefault = 1 << 20;       // rows per chunk: 256 x 1M x 4 B = 1 GiB of keys
 constexpr int kMaxKTc = 128;       // k <= 32: register-resident list; 32 < k <= 128: local-memory reservoir
 constexpr int kMaxKSplit = 104;    // split-precision path keeps kc = 16 / 32 / 64 / 128 candidates: slack >= 6 / 8 / 16 / 24
 constexpr int64_t kMinRowsTc = 1024;
@@ -608,6 +614,76 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
   return RDB_OK;
 }
 
+// ---- large k (128 < k <= 2048): exact fp32 keys of (query block x row chunk) written to HBM by the CUDA-core scorer's
+// DUMP form, exact radix select per query and chunk (select_large.cuh) -> one sorted list per chunk in
+// h->cand_key / h->cand_idx, laid out [nq][S][k] for merge_lists_kernel.  *L_out = S.
+template <bool L2, typename T, bool ALIGNED>
+int launch_simt_dump_t(rdb_handle* h, const T* Q, const T* Y, int nq, int ld, int nqt, int S, int rows_per_chunk,
+                       int row0, int row_end, float* dump, long long pitch) {
+  auto kern = score_select_simt_kernel<16, L2, T, ALIGNED, true>;
+  CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt_smem_bytes()));
+  kern<<<dim3(unsigned(nqt) * unsigned(S)), dim3(256), simt_smem_bytes(), h->stream>>>(
+      Q, Y, h->ynorm, nq, row_end, h->d, ld, nqt, S, rows_per_chunk, nullptr, nullptr, 0, dump, pitch, row0);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return RDB_OK;
+}
+
+template <bool L2>
+int launch_simt_dump(rdb_handle* h, const QueryView& qv, int q0, int nq, int nqt, int S, int rows_per_chunk, int row0,
+                     int row_end, float* dump, long long pitch) {
+  if (h->store == RDB_STORE_F32) {
+    const float* Q = qv.qf + size_t(q0) * h->d;
+    if (h->d % 4 == 0) return launch_simt_dump_t<L2, float, true>(h, Q, h->master, nq, h->d, nqt, S, rows_per_chunk, row0, row_end, dump, pitch);
+    return launch_simt_dump_t<L2, float, false>(h, Q, h->master, nq, h->d, nqt, S, rows_per_chunk, row0, row_end, dump, pitch);
+  }
+  if (h->f16())
+    return launch_simt_dump_t<L2, __half, true>(h, (const __half*)qv.qhi + size_t(q0) * h->dp, (const __half*)h->hi, nq, h->dp, nqt, S, rows_per_chunk, row0, row_end, dump, pitch);
+  return launch_simt_dump_t<L2, __nv_bfloat16, true>(h, (const __nv_bfloat16*)qv.qhi + size_t(q0) * h->dp, (const __nv_bfloat16*)h->hi, nq, h->dp, nqt, S, rows_per_chunk, row0, row_end, dump, pitch);
+}
+
+int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
+  const int64_t N = h->n;
+  int64_t rows = kLargeKRowsDefault;
+  if (const char* e = getenv("RDB_LARGEK_ROWS")) rows = std::max<int64_t>(1, atoll(e));   // tests: force several chunks
+  rows = std::max<int64_t>(rows, (N + 255) / 256);          // merge_lists_kernel folds at most 256 lists
+  rows = round_up(rows, SIMT_BN);
+  rows = std::min<int64_t>(rows, round_up(N, SIMT_BN));
+  const int S = int((N + rows - 1) / rows);
+  const int qb = std::min(qv.nq, kLargeKQueryBlock);
+  CUDA_TRY(h, h->lk_scores.ensure(size_t(qb) * size_t(rows) * 4));
+  CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * k * 4));
+  CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * k * 4));
+  float* scores = h->lk_scores.as<float>();
+  cudaStream_t s = h->stream;
+  cudaEventRecord(h->ev0, s);
+  int rc;
+  for (int q0 = 0; q0 < qv.nq; q0 += kLargeKQueryBlock) {
+    const int nqs = std::min(kLargeKQueryBlock, qv.nq - q0);
+    const int nqt = (nqs + SIMT_BM - 1) / SIMT_BM;
+    for (int c = 0; c < S; ++c) {
+      const int64_t row0 = int64_t(c) * rows, row_end = std::min<int64_t>(N, row0 + rows);
+      const int len = int(row_end - row0);
+      const int tiles = (len + SIMT_BN - 1) / SIMT_BN;
+      int units = std::min(tiles, std::max(1, 8 * h->num_sms / nqt));
+      const int tpu = (tiles + units - 1) / units;
+      units = (tiles + tpu - 1) / tpu;
+      rc = (h->metric == RDB_METRIC_L2)
+               ? launch_simt_dump<true>(h, qv, q0, nqs, nqt, units, tpu * SIMT_BN, int(row0), int(row_end), scores, rows)
+               : launch_simt_dump<false>(h, qv, q0, nqs, nqt, units, tpu * SIMT_BN, int(row0), int(row_end), scores, rows);
+      if (rc) return rc;
+      select_dense_kernel<<<nqs, SELK_THREADS, 0, s>>>(scores, rows, len, int(row0), k, S, c, q0,
+                                                       h->cand_key.as<float>(), h->cand_idx.as<int>());
+      h->launches++;
+      CUDA_TRY(h, cudaGetLastError());
+    }
+  }
+  cudaEventRecord(h->ev1, s);
+  h->ev_valid = true; h->last_algo = RDB_ALGO_SIMT; h->last_S = S;
+  *L_out = S;
+  return RDB_OK;
+}
+
 // fold the local candidate lists: final form (dist or key, global id, label)
 int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float* qnorm, bool shard_mode, float* d_a,
                     int64_t* d_i, float* d_l, long long id_offset, const float* labels, float* raw_key,
@@ -636,7 +712,10 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   DeviceGuard dg(h->device);
   if (nq < 0 || k < 1 || (!q && nq > 0) || !out_a || !out_idx)
     return fail(h, RDB_ERR_INVALID, "search: bad arguments (nq >= 0, k >= 1, non-null buffers)");
-  if (k > kMaxK) return fail(h, RDB_ERR_UNSUPPORTED, "search: k > 128 is not supported");
+  if (k > kMaxKLarge) return fail(h, RDB_ERR_UNSUPPORTED, "search: k > 2048 is not supported (the limit of faiss-gpu itself)");
+  const bool largek = k > kMaxK;     // dense keys + radix select (exact fp32 keys on CUDA cores)
+  if (largek && algo != RDB_ALGO_AUTO && algo != RDB_ALGO_SIMT)
+    return fail(h, RDB_ERR_UNSUPPORTED, "search: k > 128 runs on the exact CUDA-core scorer only (RDB_ALGO_AUTO / RDB_ALGO_SIMT)");
   if (nq == 0) return RDB_OK;
   const int D = h->d, Dp = h->dp;
   const bool host = mem == RDB_MEM_HOST;
@@ -647,6 +726,7 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   const bool tc_ok = sixteen ? (k <= kMaxKTc && h->n >= TC_BN) : (k <= kMaxKSplit && h->n >= TC_BN);
   // small batches are a pure HBM stream of the stored rows: dedicated streaming scorer (exact fp32 for fp32 stores)
   const bool stream_ok = nq <= 4 && k <= 128 && h->n >= 1 && (sixteen || D % 4 == 0);
+  if (largek) algo = RDB_ALGO_SIMT;
   if (algo == RDB_ALGO_AUTO) {
     algo = (stream_ok && h->n >= 4096) ? RDB_ALGO_STREAM : ((tc_ok && h->n >= kMinRowsTc) ? RDB_ALGO_TC : RDB_ALGO_SIMT);
   }
@@ -662,8 +742,9 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   if (algo == RDB_ALGO_STREAM)
     return search_stream(h, q, int(nq), k, mem, normalize, shard_mode, out_a, out_idx, out_lbl, out_qnorm);
 
-  for (int64_t b0 = 0; b0 < nq; b0 += kQueryBatch) {
-    const int nb = int(std::min<int64_t>(kQueryBatch, nq - b0));
+  const int64_t qbatch = largek ? kQueryBatchLargeK : kQueryBatch;
+  for (int64_t b0 = 0; b0 < nq; b0 += qbatch) {
+    const int nb = int(std::min<int64_t>(qbatch, nq - b0));
     const float* qsrc = q + b0 * D;
     if (host) {
       CUDA_TRY(h, h->q_stage.ensure(size_t(nb) * D * 4));
@@ -702,7 +783,7 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
     if (!split) {
       // ---- score + select, then merge
       h->tc_pivoted = false;
-      if (h->n > 0 && (rc = run_scorer(h, algo, 1, qv, k, &L, true))) return rc;
+      if (h->n > 0 && (rc = largek ? run_largek(h, qv, k, &L) : run_scorer(h, algo, 1, qv, k, &L, true))) return rc;
       if ((rc = run_merge_local(h, nb, L, k, k, qv.qnorm, shard_mode, d_a, d_i, d_l, h->id_offset, labels, nullptr)))
         return rc;
       if (h->tc_pivoted) {
@@ -852,7 +933,7 @@ int rdb_destroy(rdb_handle* h) {
     cudaFree(h->d_ynorm_max);
     for (DevBuf* b : {&h->add_stage, &h->q_stage, &h->qf, &h->qhi, &h->qlo, &h->qnorm, &h->cand_key, &h->cand_idx,
                       &h->o_dist, &h->o_idx, &h->o_lbl, &h->ids_stage, &h->rec_stage, &h->rr_key, &h->rr_idx,
-                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l, &h->gthr, &h->tcsync, &h->stream_ctl, &h->fkey, &h->fidx})
+                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l, &h->gthr, &h->tcsync, &h->stream_ctl, &h->fkey, &h->fidx, &h->lk_scores})
       b->release();
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);

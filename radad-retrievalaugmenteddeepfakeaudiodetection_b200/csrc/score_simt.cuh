@@ -76,14 +76,20 @@ __device__ __forceinline__ float4 simt_load4<__half, true>(const __half* __restr
 // ynorm[N] = |y|^2 of the stored values (L2 only).
 // cand_key / cand_idx : [nq][S * SIMT_LISTS][kout]   (key: larger is better; idx: local row id or -1)
 // grid.x = nqt * S, block = 256.   chunk c covers rows [c*rows_per_chunk, min(N, (c+1)*rows_per_chunk)).
-template <int KT, bool L2, typename T, bool ALIGNED>
+//
+// DUMP form (k > 128, see select_dense_kernel in select_large.cuh): no selection; the keys of rows
+// [dump_row0, N) are written to dump[q][row - dump_row0] (row pitch dump_pitch floats) with exactly the arithmetic of
+// the selecting form, chunk c covering rows [dump_row0 + c*rows_per_chunk, ...).
+template <int KT, bool L2, typename T, bool ALIGNED, bool DUMP = false>
 __global__ void __launch_bounds__(256) score_select_simt_kernel(const T* __restrict__ Q,
                                                                 const T* __restrict__ Y,
                                                                 const float* __restrict__ ynorm, int nq, int N, int D,
                                                                 int ld,
                                                                 int nqt, int S, int rows_per_chunk,
                                                                 float* __restrict__ cand_key,
-                                                                int* __restrict__ cand_idx, int kout) {
+                                                                int* __restrict__ cand_idx, int kout,
+                                                                float* __restrict__ dump = nullptr,
+                                                                long long dump_pitch = 0, int dump_row0 = 0) {
   extern __shared__ __align__(16) float smem[];
   float* As = smem;                                   // [2][BK][LD]
   float* Bs = As + 2 * SIMT_BK * SIMT_LD;             // [2][BK][LD]
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(256) score_select_simt_kernel(const T* __restr
   const int qtile = blockIdx.x % nqt;
   const int chunk = blockIdx.x / nqt;
   const long long q0 = (long long)qtile * SIMT_BM;
-  const int row_begin = chunk * rows_per_chunk;
+  const int row_begin = (DUMP ? dump_row0 : 0) + chunk * rows_per_chunk;
   const int row_end = min(N, row_begin + rows_per_chunk);
 
   const int ty = tid >> 4, tx = tid & 15;
@@ -167,7 +173,20 @@ __global__ void __launch_bounds__(256) score_select_simt_kernel(const T* __restr
       }
     }
     __syncthreads();
-    {
+    if (DUMP) {
+      // one warp per query row of the tile, 4 coalesced 128-byte stores per row
+      const int w = tid >> 5, lane = tid & 31;
+      for (int rr = w; rr < SIMT_BM && q0 + rr < nq; rr += 8) {
+        float* drow = dump + (q0 + rr) * dump_pitch + (n0 - dump_row0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = lane + 32 * i;
+          float v = Ss[rr * SIMT_SLD + c];
+          if (L2) v = fmaf(2.0f, v, -Yn[c]);
+          if (n0 + c < row_end) drow[c] = v;
+        }
+      }
+    } else {
       const float* srow_p = Ss + srow * SIMT_SLD + shalf * 64;
       const int cbase = n0 + shalf * 64;
 #pragma unroll 4
@@ -181,7 +200,7 @@ __global__ void __launch_bounds__(256) score_select_simt_kernel(const T* __restr
   }
 
   const long long q = q0 + srow;
-  if (q < nq) {
+  if (!DUMP && q < nq) {
     const long long base = ((q * S + chunk) * SIMT_LISTS + shalf) * (long long)kout;
 #pragma unroll
     for (int j = 0; j < KT; ++j)

@@ -1,0 +1,164 @@
+"""GPU parity for 128 < k <= 2048 (index.search(q, k) -- vector_database.py:181 -- accepts any k; faiss-gpu up to 2048).
+
+The path: exact CUDA-core scorer in its DUMP form -> dense fp32 keys of (query block x row chunk) -> exact radix
+select per query and chunk (csrc/select_large.cuh) -> merge of the per-chunk lists.  Integer-lattice inputs (exact
+arithmetic, massive ties) must match the oracle BIT-EXACTLY, ties by the lowest id; Gaussian inputs within the
+north-star tolerances (1e-5 relative fp32 store, 1e-3 16-bit stores).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL_F32, TOL_BF16 = 1e-5, 1e-3
+
+
+def _gauss(n, d, seed):
+    return np.random.default_rng(seed).standard_normal((n, d)).astype(np.float32)
+
+
+def _lattice(N, D, Q, seed):
+    rng = np.random.default_rng(seed)
+    xb = rng.integers(-2, 3, size=(N, D)).astype(np.float32)
+    xq = rng.integers(-2, 3, size=(Q, D)).astype(np.float32)
+    if N > 700:
+        xb[N // 2:N // 2 + 300] = xb[10]                        # 300 identical rows: ties far beyond the boundary
+        xq[0] = xb[10]
+    return xb, xq
+
+
+@pytest.mark.parametrize("store", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("metric_s", ["L2", "IP"])
+@pytest.mark.parametrize("k,rows", [(129, None), (200, 1024), (777, None), (2048, 2500)])
+def test_lattice_bit_exact_k_above_128(pkg, oracle, monkeypatch, metric_s, k, rows, store):
+    """rows = forced chunk length (RDB_LARGEK_ROWS): several per-chunk lists, ties straddling chunk borders."""
+    if rows:
+        monkeypatch.setenv("RDB_LARGEK_ROWS", str(rows))
+    xb, xq = _lattice(6001, 64, 70, 11)
+    metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
+    idx = pkg.FlatIndex(64, metric, store)
+    idx.add(xb[:4000])
+    idx.add(xb[4000:])
+    D, I = idx.search(xq, k)
+    ref = oracle.FlatIndexOracle(64, metric)
+    ref.add(xb)
+    Dr, Ir = ref.search(xq, k, direct=False)
+    np.testing.assert_array_equal(I, Ir)
+    np.testing.assert_array_equal(D, Dr)
+    assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (70, k)
+
+
+def test_all_rows_identical(pkg):
+    """Every key equal: the select has to walk all eight radix digits down to the row id."""
+    xb = np.ones((5000, 16), np.float32)
+    idx = pkg.FlatIndex(16, pkg.METRIC_L2, "f32")
+    idx.add(xb)
+    D, I = idx.search(np.ones((3, 16), np.float32), 1500)
+    np.testing.assert_array_equal(I, np.tile(np.arange(1500, dtype=np.int64), (3, 1)))
+    np.testing.assert_array_equal(D, np.zeros((3, 1500), np.float32))
+
+
+@pytest.mark.parametrize("case", [
+    # N      D    Q    k     metric cos    store   rows
+    (20000,  128, 300, 1000, "L2", False, "f32",  None),      # two query blocks of 256
+    (30011,  96,  64,  500,  "IP", True,  "bf16", 8192),      # 4 chunks, ragged last chunk
+    (5003,   101, 33,  256,  "IP", False, "f32",  None),      # D % 4 != 0
+    (9000,   768, 1,   150,  "L2", False, "bf16", None),      # batch-1 (beyond the streaming scorer's k)
+    (4100,   40,  5,   2048, "L2", False, "f16",  None),
+], ids=["l2_f32_k1000", "cos_bf16_k500_chunks", "ip_f32_oddD_k256", "l2_bf16_q1_k150", "l2_f16_k2048"])
+def test_gaussian_vs_oracle_k_above_128(pkg, oracle, monkeypatch, case):
+    N, Dm, Q, k, metric_s, cos, store, rows = case
+    if rows:
+        monkeypatch.setenv("RDB_LARGEK_ROWS", str(rows))
+    metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
+    xb, xq = _gauss(N, Dm, 1234), _gauss(Q, Dm, 5678)
+    xq[0] = xb[5]
+    idx = pkg.FlatIndex(Dm, metric, store)
+    idx.add(xb, normalize=cos)
+    D, I = idx.search(xq, k, normalize=cos)
+    ref = oracle.FlatIndexOracle(Dm, metric, store=store)
+    ref.add(oracle.maybe_normalize(xb, cos))
+    qn = oracle.maybe_normalize(xq, cos)
+    Dr, Ir = ref.search(qn, min(k + 8, N), direct=False)
+    tol = TOL_F32 if store == "f32" else TOL_BF16
+    if metric == pkg.METRIC_L2:
+        scale = float((qn * qn).sum(1).max() + (ref._base() ** 2).sum(1).max())
+        floor = 2e-6 * scale
+    else:
+        floor = 1e-6
+    st = oracle.compare_topk(D, I, Dr, Ir, lambda ids: ref.exact_scores(qn, ids), metric, tol=tol, abs_floor=floor)
+    assert st["recall"] >= 0.999, st
+    # sorted best-first, no duplicate ids
+    assert np.all(np.diff(D, axis=1) >= 0) if metric == pkg.METRIC_L2 else np.all(np.diff(D, axis=1) <= 0)
+    assert all(len(set(r.tolist())) == k for r in I)
+
+
+def test_k_beyond_ntotal_and_limits(pkg, tmp_path):
+    """k > ntotal at the index level: faiss fills id -1 / +inf; the wrapper clamps k to ntotal (vector_database.py:169);
+    k > 2048 is refused loudly (faiss-gpu's own limit)."""
+    from conftest import Cfg
+    xb = _gauss(200, 32, 3)
+    idx = pkg.FlatIndex(32, pkg.METRIC_L2, "f32")
+    idx.add(xb)
+    D, I = idx.search(xb[:4], 300)
+    assert np.all(I[:, 200:] == -1) and np.all(np.isinf(D[:, 200:]))
+    assert all(sorted(r[:200].tolist()) == list(range(200)) for r in I)
+    np.testing.assert_array_equal(I[:, 0], np.arange(4))
+    with pytest.raises(RuntimeError):
+        idx.search(xb[:4], 2049)
+    vdb = pkg.VectorDatabase(Cfg(tmp_path / "lk", "L2"))
+    vdb.add_vectors(xb, [f"/d/u{i}.wav" for i in range(200)], [i % 2 for i in range(200)], {})
+    Dw, Iw = vdb.search_batch(xb[:4], k=1000)
+    assert Dw.shape == (4, 200) and Iw.shape == (4, 200)
+    np.testing.assert_array_equal(Iw, I[:, :200])
+
+
+def test_sharded_and_labels_k_above_128(pkg, oracle):
+    """Row shards (4 emulated on one GPU) + merge kernel == unsharded search at k = 400, labels gathered on device."""
+    import torch
+    N, Dm, Q, k = 10007, 64, 37, 400
+    xb, xq = _lattice(N, Dm, Q, 5)
+    labels = (np.arange(N) % 2).astype(np.float32)
+    full = pkg.FlatIndex(Dm, pkg.METRIC_L2, "bf16")
+    full.add(xb)
+    full.set_labels(labels)
+    Df, If, Lf = full.search(xq, k, return_labels=True)
+    ref = oracle.FlatIndexOracle(Dm, pkg.METRIC_L2)
+    ref.add(xb)
+    Dr, Ir = ref.search(xq, k, direct=False)
+    np.testing.assert_array_equal(If, Ir)
+    np.testing.assert_array_equal(Df, Dr)
+    np.testing.assert_array_equal(Lf, labels[If])
+    G = 4
+    q = torch.from_numpy(xq).cuda()
+    keys, gids, labs, shards = [], [], [], []
+    for r in range(G):
+        s, e = pkg.shard_bounds(N, G, r)
+        sh = pkg.FlatIndex(Dm, pkg.METRIC_L2, "bf16")
+        sh.set_id_offset(s)
+        sh.add(xb[s:e])
+        sh.set_labels(labels[s:e])
+        kk, gg, ll, qn = sh.search_shard(q, k)
+        keys.append(kk), gids.append(gg), labs.append(ll)
+        shards.append(sh)
+    D, I, L = shards[0].merge_shards(torch.stack(keys, 1), torch.stack(gids, 1), torch.stack(labs, 1), qn)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(I.cpu().numpy(), If)
+    np.testing.assert_array_equal(D.cpu().numpy(), Df)
+    np.testing.assert_array_equal(L.cpu().numpy(), Lf)
+
+
+def test_multi_gpu_index_k_above_128(pkg):
+    """MultiGpuFlatIndex (peer-memory merge kernel) at k = 300 == one FlatIndex."""
+    import torch
+    n = torch.cuda.device_count()
+    devices = list(range(min(n, 4))) if n >= 2 else [0, 0, 0]
+    xb, xq = _lattice(9001, 64, 20, 17)
+    one = pkg.FlatIndex(64, pkg.METRIC_IP, "bf16")
+    one.add(xb)
+    D1, I1 = one.search(xq, 300)
+    multi = pkg.MultiGpuFlatIndex(64, pkg.METRIC_IP, "bf16", devices=devices)
+    multi.add(xb[:5000])
+    multi.add(xb[5000:])
+    Dm_, Im_ = multi.search(xq, 300)
+    np.testing.assert_array_equal(Im_, I1)
+    np.testing.assert_array_equal(Dm_, D1)
