@@ -179,13 +179,19 @@ int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int n
   int64_t blocks = std::min<int64_t>((n + warps_per_block - 1) / warps_per_block, int64_t(h->num_sms) * 16);
   dim3 grid((unsigned)blocks), block(256);
   cudaStream_t s = h->stream;
-  if (h->f16()) {
-    if (vec4) ingest_rows_kernel<__half, true><<<grid, block, 0, s>>>(x, n, D, Dp, normalize, norm_of_hi, master, (__half*)hi, (__half*)lo, norm2);
-    else      ingest_rows_kernel<__half, false><<<grid, block, 0, s>>>(x, n, D, Dp, normalize, norm_of_hi, master, (__half*)hi, (__half*)lo, norm2);
-  } else {
-    if (vec4) ingest_rows_kernel<__nv_bfloat16, true><<<grid, block, 0, s>>>(x, n, D, Dp, normalize, norm_of_hi, master, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, norm2);
-    else      ingest_rows_kernel<__nv_bfloat16, false><<<grid, block, 0, s>>>(x, n, D, Dp, normalize, norm_of_hi, master, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, norm2);
-  }
+  // rows of up to 1024 floats are held in registers (one read, NC independent 128-bit loads per lane)
+  const int nc = !vec4 ? 0 : (Dp <= 256 ? 2 : (Dp <= 512 ? 4 : (Dp <= 1024 ? 8 : 0)));
+#define INGEST_LAUNCH(T16, V4, NC) \
+  ingest_rows_kernel<T16, V4, NC><<<grid, block, 0, s>>>(x, n, D, Dp, normalize, norm_of_hi, master, (T16*)hi, (T16*)lo, norm2)
+#define INGEST_T(T16)                                                                                     \
+  do {                                                                                                    \
+    if (nc == 2) INGEST_LAUNCH(T16, true, 2); else if (nc == 4) INGEST_LAUNCH(T16, true, 4);              \
+    else if (nc == 8) INGEST_LAUNCH(T16, true, 8); else if (vec4) INGEST_LAUNCH(T16, true, 0);            \
+    else INGEST_LAUNCH(T16, false, 0);                                                                    \
+  } while (0)
+  if (h->f16()) INGEST_T(__half); else INGEST_T(__nv_bfloat16);
+#undef INGEST_T
+#undef INGEST_LAUNCH
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return RDB_OK;
