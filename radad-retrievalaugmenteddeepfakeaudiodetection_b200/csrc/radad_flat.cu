@@ -96,6 +96,9 @@ struct rdb_handle {
   // scratch
   DevBuf add_stage, q_stage, qf, qhi, qlo, qnorm, cand_key, cand_idx, o_dist, o_idx, o_lbl, ids_stage, rec_stage;
   DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l, gthr, tcsync, stream_ctl, fkey, fidx;
+  DevBuf uncert1, t2_qf, t2_qhi, t2_qlo, t2_qnorm, t2_a, t2_i, t2_l;   // fp32 stores: tier-1 list + tier-2 sub-batch
+  int t1_skip = 0;                // batches left during which tier 1 is skipped (it failed for most queries)
+  int64_t last_tier1_queries = 0, last_tier1_uncertified = 0;
   DevBuf lk_scores;               // large-k path: dense keys of one (query block x row chunk)
   void* pin = nullptr;            // pinned host staging of the small-batch path
   size_t pin_bytes = 0;
@@ -710,6 +713,147 @@ int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float*
   return RDB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- fp32 stores
+// Exact-fp32 neighbours at tensor-core speed.  A *certified pass* scores the queries approximately on the tensor cores
+// keeping kc > k candidates per query, re-scores the candidates exactly in fp32 (kernel 6) and certifies query q iff
+//     exact_key[k-1] > approx_key_of_the_worst_candidate + B,     B = eps * |q| * max|y| (x 2 for the L2 key)
+// -- then no row outside the candidate set can belong to the exact top-k.  Two approximations are used, cheapest first:
+//   tier 1   q_hi.y_hi (ONE MMA term, bf16 roundings of both operands: eps = 2^-8 + 2^-18 + accumulation), kc = 128.
+//            A third of the tensor work and half of the database bytes of tier 2; certifies whenever the exact k-th
+//            key clears the 128-th approximate key by ~0.4 % of |q||y| (k <= 32, N >= 262144 rows: the sampled
+//            admission bound keeps the kc = 128 epilogue cheap).
+//   tier 2   q_lo.y_hi + q_hi.y_lo + q_hi.y_hi (three terms, eps = 3.02 * 2^-18 + accumulation), kc = 16 .. 128.
+// Queries tier 1 cannot certify are compacted and go through tier 2; what tier 2 cannot certify (adversarial ties) is
+// searched by the exact CUDA-core kernel.  Every tier ends in exact fp32 keys, so the result does not depend on which
+// tier certified a query.
+int certified_pass(rdb_handle* h, const QueryView& v, int k, int kc, int nterms, bool shard_mode, float* o_a,
+                   int64_t* o_i, float* o_l, const float* labels, int* ucount, int* ulist, bool timed) {
+  const int nb = v.nq, D = h->d;
+  const bool l2 = h->metric == RDB_METRIC_L2;
+  cudaStream_t s = h->stream;
+  int rc, L = 0;
+  if ((rc = run_scorer(h, RDB_ALGO_TC, nterms, v, kc, &L, timed))) return rc;
+  CUDA_TRY(h, h->rr_key.ensure(size_t(nb) * kc * 4));
+  CUDA_TRY(h, h->rr_idx.ensure(size_t(nb) * kc * 8));
+  CUDA_TRY(h, h->rr_key2.ensure(size_t(nb) * kc * 4));
+  CUDA_TRY(h, h->rr_idx2.ensure(size_t(nb) * kc * 8));
+  // approximate top-kc per query (local ids, raw keys)
+  if ((rc = run_merge_local(h, nb, L, kc, kc, v.qnorm, false, nullptr, h->rr_idx.as<int64_t>(), nullptr, 0, nullptr,
+                            h->rr_key.as<float>()))) return rc;
+  CUDA_TRY(h, cudaMemsetAsync(ucount, 0, 4, s));
+  const int nks = (D + TC_BK - 1) / TC_BK;
+  const float n_mma = float(nks * (TC_BK / 16) * nterms);
+  const float accum = 2.0f * (n_mma + 16.f) * 1.1920928955078125e-07f /*2^-23*/;
+  const float eps = (nterms == 3 ? 3.02f * 3.814697265625e-06f /*2^-18*/
+                                 : 0.00390625f /*2 * 2^-9*/ + 3.814697265625e-06f /*2^-18*/) + accum;
+  const int warps = 4;
+  dim3 grid((nb + warps - 1) / warps), block(32 * warps);
+  dim3 rgrid(nb), rblock(RERANK_THREADS);                       // re-rank: one block per query
+  if (l2) rerank_exact_kernel<true><<<rgrid, rblock, 0, s>>>(
+      h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, v.qf, h->master, h->ynorm, D, eps, v.qnorm,
+      h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount);
+  else rerank_exact_kernel<false><<<rgrid, rblock, 0, s>>>(
+      h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, v.qf, h->master, h->ynorm, D, eps, v.qnorm,
+      h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  // exact list (L = 1, already sorted) -> final form
+  merge_lists_kernel<long long><<<grid, block, 0, s>>>(
+      h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), nullptr, nb, 1, kc, k, l2 ? 1 : 0, v.qnorm, h->id_offset,
+      labels, shard_mode ? nullptr : o_a, reinterpret_cast<long long*>(o_i), o_l, shard_mode ? o_a : nullptr);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return RDB_OK;
+}
+
+// tier 2 (+ exact CUDA-core search of what it cannot certify) over the queries of `v`; results [v.nq][k] into o_*
+int split3_search(rdb_handle* h, const QueryView& v, int k, bool shard_mode, float* o_a, int64_t* o_i, float* o_l,
+                  const float* labels, bool timed) {
+  const int nb = v.nq, D = h->d;
+  cudaStream_t s = h->stream;
+  int rc;
+  const int kc = (k <= 10) ? 16 : (k <= 24 ? 32 : (k <= 48 ? 64 : 128));
+  CUDA_TRY(h, h->uncert.ensure(size_t(nb + 1) * 4));
+  int* ucount = h->uncert.as<int>();
+  int* ulist = ucount + 1;
+  if ((rc = certified_pass(h, v, k, kc, 3, shard_mode, o_a, o_i, o_l, labels, ucount, ulist, timed))) return rc;
+  int m = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&m, ucount, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  h->last_uncertified += m;
+  if (m > 0) {
+    CUDA_TRY(h, h->fb_qf.ensure(size_t(m) * D * 4));
+    CUDA_TRY(h, h->fb_qnorm.ensure(size_t(m) * 4));
+    CUDA_TRY(h, h->fb_a.ensure(size_t(m) * k * 4));
+    CUDA_TRY(h, h->fb_i.ensure(size_t(m) * k * 8));
+    CUDA_TRY(h, h->fb_l.ensure(size_t(m) * k * 4));
+    gather_f32_rows_kernel<<<(m + 7) / 8, 256, 0, s>>>(v.qf, ulist, m, D, h->fb_qf.as<float>());
+    h->launches++;
+    if ((rc = launch_ingest(h, h->fb_qf.as<float>(), m, 0, 0, nullptr, nullptr, nullptr, h->fb_qnorm.as<float>())))
+      return rc;
+    QueryView fv{h->fb_qf.as<float>(), nullptr, nullptr, h->fb_qnorm.as<float>(), m};
+    int Lf = 0;
+    if ((rc = run_scorer(h, RDB_ALGO_SIMT, 1, fv, k, &Lf, false))) return rc;
+    if ((rc = run_merge_local(h, m, Lf, k, k, fv.qnorm, shard_mode, h->fb_a.as<float>(), h->fb_i.as<int64_t>(),
+                              h->fb_l.as<float>(), h->id_offset, labels, nullptr))) return rc;
+    scatter_results_kernel<<<(m * k + 255) / 256, 256, 0, s>>>(ulist, m, k, h->fb_a.as<float>(),
+                                                               h->fb_i.as<long long>(), h->fb_l.as<float>(), o_a,
+                                                               reinterpret_cast<long long*>(o_i), o_l);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  return RDB_OK;
+}
+
+constexpr int kTier1MaxK = 32;      // kc = 128 candidates: >= 4x slack
+constexpr int kTier1Candidates = 128;
+
+int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mode, float* d_a, int64_t* d_i, float* d_l,
+                       const float* labels) {
+  const int nb = qv.nq, D = h->d, Dp = h->dp;
+  cudaStream_t s = h->stream;
+  int rc;
+  const int64_t ntiles = (h->n + TC_BN - 1) / TC_BN;
+  bool tier1 = k <= kTier1MaxK && ntiles >= kTcPivotMinTiles && !getenv("RDB_NO_TIER1");
+  if (tier1 && h->t1_skip > 0) { h->t1_skip--; tier1 = false; }     // recent batches mostly failed tier 1: do not pay for it
+  if (!tier1) return split3_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels, true);
+
+  CUDA_TRY(h, h->uncert1.ensure(size_t(nb + 1) * 4));
+  int* ucount = h->uncert1.as<int>();
+  int* ulist = ucount + 1;
+  if ((rc = certified_pass(h, qv, k, kTier1Candidates, 1, shard_mode, d_a, d_i, d_l, labels, ucount, ulist, true)))
+    return rc;
+  int m = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&m, ucount, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  h->last_tier1_queries += nb;
+  h->last_tier1_uncertified += m;
+  if (2 * m > nb) h->t1_skip = 8;
+  if (m == 0) return RDB_OK;
+  // compact the uncertified queries and run tier 2 on them
+  CUDA_TRY(h, h->t2_qf.ensure(size_t(m) * D * 4));
+  CUDA_TRY(h, h->t2_qhi.ensure(size_t(m) * Dp * 2));
+  CUDA_TRY(h, h->t2_qlo.ensure(size_t(m) * Dp * 2));
+  CUDA_TRY(h, h->t2_qnorm.ensure(size_t(m) * 4));
+  CUDA_TRY(h, h->t2_a.ensure(size_t(m) * k * 4));
+  CUDA_TRY(h, h->t2_i.ensure(size_t(m) * k * 8));
+  CUDA_TRY(h, h->t2_l.ensure(size_t(m) * k * 4));
+  gather_f32_rows_kernel<<<(m + 7) / 8, 256, 0, s>>>(qv.qf, ulist, m, D, h->t2_qf.as<float>());
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  if ((rc = launch_ingest(h, h->t2_qf.as<float>(), m, 0, 0, nullptr, h->t2_qhi.p, h->t2_qlo.p, h->t2_qnorm.as<float>())))
+    return rc;
+  QueryView sub{h->t2_qf.as<float>(), h->t2_qhi.p, h->t2_qlo.p, h->t2_qnorm.as<float>(), m};
+  if ((rc = split3_search(h, sub, k, shard_mode, h->t2_a.as<float>(), h->t2_i.as<int64_t>(), h->t2_l.as<float>(), labels,
+                          false))) return rc;
+  scatter_results_kernel<<<(m * k + 255) / 256, 256, 0, s>>>(ulist, m, k, h->t2_a.as<float>(), h->t2_i.as<long long>(),
+                                                             h->t2_l.as<float>(), d_a, reinterpret_cast<long long*>(d_i),
+                                                             d_l);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return RDB_OK;
+}
+
 // One search over the local shard.  shard_mode: out_a receives merge keys instead of distances.
 int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int normalize, int algo, bool shard_mode,
                 float* out_a, int64_t* out_idx, float* out_lbl, float* out_qnorm) {
@@ -744,7 +888,7 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   const bool split = (algo == RDB_ALGO_TC) && !sixteen;
   const float* labels = (h->labels && h->nlabels == h->n) ? h->labels : nullptr;
   cudaStream_t s = h->stream;
-  h->last_uncertified = 0;
+  h->last_uncertified = 0; h->last_tier1_queries = 0; h->last_tier1_uncertified = 0;
   if (algo == RDB_ALGO_STREAM)
     return search_stream(h, q, int(nq), k, mem, normalize, shard_mode, out_a, out_idx, out_lbl, out_qnorm);
 
@@ -807,70 +951,8 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
                                   flag))) return rc;
       }
     } else {
-      // ---- split-precision tensor-core pass keeping kc > k candidates
-      const int kc = (k <= 10) ? 16 : (k <= 24 ? 32 : (k <= 48 ? 64 : 128));
-      if ((rc = run_scorer(h, RDB_ALGO_TC, 3, qv, kc, &L, true))) return rc;
-      CUDA_TRY(h, h->rr_key.ensure(size_t(nb) * kc * 4));
-      CUDA_TRY(h, h->rr_idx.ensure(size_t(nb) * kc * 8));
-      CUDA_TRY(h, h->rr_key2.ensure(size_t(nb) * kc * 4));
-      CUDA_TRY(h, h->rr_idx2.ensure(size_t(nb) * kc * 8));
-      CUDA_TRY(h, h->uncert.ensure(size_t(nb + 1) * 4));
-      // approximate top-kc per query (local ids, raw keys)
-      if ((rc = run_merge_local(h, nb, L, kc, kc, qv.qnorm, false, nullptr, h->rr_idx.as<int64_t>(), nullptr, 0,
-                                nullptr, h->rr_key.as<float>()))) return rc;
-      // exact fp32 re-rank + certificate
-      int* ucount = h->uncert.as<int>();
-      int* ulist = ucount + 1;
-      CUDA_TRY(h, cudaMemsetAsync(ucount, 0, 4, s));
-      const int nks = (D + TC_BK - 1) / TC_BK;
-      const float n_mma = float(nks * (TC_BK / 16) * 3);
-      const float eps = 3.02f * 3.814697265625e-06f /*2^-18*/ + 2.0f * (n_mma + 16.f) * 1.1920928955078125e-07f /*2^-23*/;
-      {
-        const int warps = 4;
-        dim3 grid((nb + warps - 1) / warps), block(32 * warps);
-        dim3 rgrid(nb), rblock(RERANK_THREADS);                       // re-rank: one block per query
-        if (l2) rerank_exact_kernel<true><<<rgrid, rblock, 0, s>>>(
-            h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, qv.qf, h->master, h->ynorm, D, eps, qv.qnorm,
-            h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount);
-        else rerank_exact_kernel<false><<<rgrid, rblock, 0, s>>>(
-            h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, qv.qf, h->master, h->ynorm, D, eps, qv.qnorm,
-            h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount);
-        h->launches++;
-        CUDA_TRY(h, cudaGetLastError());
-        // exact list (L = 1, already sorted) -> final form
-        merge_lists_kernel<long long><<<grid, block, 0, s>>>(
-            h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), nullptr, nb, 1, kc, k, l2 ? 1 : 0, qv.qnorm,
-            h->id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l,
-            shard_mode ? d_a : nullptr);
-        h->launches++;
-        CUDA_TRY(h, cudaGetLastError());
-      }
-      // ---- queries whose candidate set could not be certified: exact CUDA-core search
-      int m = 0;
-      CUDA_TRY(h, cudaMemcpyAsync(&m, ucount, 4, cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(h, cudaStreamSynchronize(s));
-      h->last_uncertified += m;
-      if (m > 0) {
-        CUDA_TRY(h, h->fb_qf.ensure(size_t(m) * D * 4));
-        CUDA_TRY(h, h->fb_qnorm.ensure(size_t(m) * 4));
-        CUDA_TRY(h, h->fb_a.ensure(size_t(m) * k * 4));
-        CUDA_TRY(h, h->fb_i.ensure(size_t(m) * k * 8));
-        CUDA_TRY(h, h->fb_l.ensure(size_t(m) * k * 4));
-        gather_f32_rows_kernel<<<(m + 7) / 8, 256, 0, s>>>(qv.qf, ulist, m, D, h->fb_qf.as<float>());
-        h->launches++;
-        if ((rc = launch_ingest(h, h->fb_qf.as<float>(), m, 0, 0, nullptr, nullptr, nullptr, h->fb_qnorm.as<float>())))
-          return rc;
-        QueryView fv{h->fb_qf.as<float>(), nullptr, nullptr, h->fb_qnorm.as<float>(), m};
-        int Lf = 0;
-        if ((rc = run_scorer(h, RDB_ALGO_SIMT, 1, fv, k, &Lf, false))) return rc;
-        if ((rc = run_merge_local(h, m, Lf, k, k, fv.qnorm, shard_mode, h->fb_a.as<float>(), h->fb_i.as<int64_t>(),
-                                  h->fb_l.as<float>(), h->id_offset, labels, nullptr))) return rc;
-        scatter_results_kernel<<<(m * k + 255) / 256, 256, 0, s>>>(ulist, m, k, h->fb_a.as<float>(),
-                                                                   h->fb_i.as<long long>(), h->fb_l.as<float>(), d_a,
-                                                                   reinterpret_cast<long long*>(d_i), d_l);
-        h->launches++;
-        CUDA_TRY(h, cudaGetLastError());
-      }
+      // ---- fp32 store on the tensor cores: certified approximate pass(es) + exact fp32 re-rank (exact_split_search)
+      if ((rc = exact_split_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels))) return rc;
     }
     if (out_qnorm)
       CUDA_TRY(h, cudaMemcpyAsync(out_qnorm + b0, h->qnorm.p, size_t(nb) * 4,
@@ -939,7 +1021,8 @@ int rdb_destroy(rdb_handle* h) {
     cudaFree(h->d_ynorm_max);
     for (DevBuf* b : {&h->add_stage, &h->q_stage, &h->qf, &h->qhi, &h->qlo, &h->qnorm, &h->cand_key, &h->cand_idx,
                       &h->o_dist, &h->o_idx, &h->o_lbl, &h->ids_stage, &h->rec_stage, &h->rr_key, &h->rr_idx,
-                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l, &h->gthr, &h->tcsync, &h->stream_ctl, &h->fkey, &h->fidx, &h->lk_scores})
+                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l, &h->gthr, &h->tcsync, &h->stream_ctl, &h->fkey, &h->fidx, &h->lk_scores,
+                      &h->uncert1, &h->t2_qf, &h->t2_qhi, &h->t2_qlo, &h->t2_qnorm, &h->t2_a, &h->t2_i, &h->t2_l})
       b->release();
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1246,6 +1329,13 @@ int rdb_last_kernel_ms(rdb_handle* h, float* ms, int* algo, int* nsplits) {
 }
 
 int64_t rdb_last_uncertified(rdb_handle* h) { return h ? h->last_uncertified : 0; }
+
+int rdb_last_tier1(rdb_handle* h, int64_t* queries, int64_t* uncertified) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  if (queries) *queries = h->last_tier1_queries;
+  if (uncertified) *uncertified = h->last_tier1_uncertified;
+  return RDB_OK;
+}
 
 int rdb_mem_info(rdb_handle* h, size_t* index_bytes, size_t* free_bytes, size_t* total_bytes) {
   if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");

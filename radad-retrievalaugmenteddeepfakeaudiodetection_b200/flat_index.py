@@ -343,6 +343,13 @@ class FlatIndex(_ReconstructCache):
         """Queries of the last search that fell back from the certified tensor-core path to the exact kernel."""
         return int(self._lib.rdb_last_uncertified(self._h))
 
+    @property
+    def last_tier1(self) -> Tuple[int, int]:
+        """(queries that entered the one-term certified pass, queries it could not certify) of the last search."""
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self._lib.rdb_last_tier1(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
+
     def mem_info(self):
         a, b, c = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
         self._check(self._lib.rdb_mem_info(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))

@@ -111,6 +111,8 @@ def test_c2_full_size_fp32_certified(pkg):
     Dt, It = idx.search(q, k)                                     # auto -> split tcgen05 + re-rank + certificate
     assert idx.last_kernel_ms()[1] == "tc"
     unc = idx.last_uncertified
+    t1q, t1u = idx.last_tier1                                     # one-term certified pass first (k <= 32, N >= 262144)
+    assert t1q == Q and t1u <= Q // 20, (t1q, t1u)
     torch.cuda.synchronize()
     assert torch.equal(It[:64, 0], torch.arange(1000, 1064, device=dev))
     assert float(Dt[:64, 0].abs().max()) < 2e-2                   # |q|^2 + |y|^2 - 2 q.y cancels at scale 1536

@@ -10,6 +10,8 @@ g = torch.Generator(device=dev); g.manual_seed(1)
 which = sys.argv[1]
 if which == "c2":
     N, D, Q, k, store, met = 1000000, 768, 10000, 10, "f32", pkg.METRIC_L2
+elif which == "c2cos":
+    N, D, Q, k, store, met = 1000000, 768, 10000, 10, "f32", pkg.METRIC_IP
 elif which == "c1":
     N, D, Q, k, store, met = 20000, 768, 1000, 10, "f32", pkg.METRIC_IP
 else:
