@@ -97,7 +97,8 @@ struct rdb_handle {
   DevBuf add_stage, q_stage, qf, qhi, qlo, qnorm, cand_key, cand_idx, o_dist, o_idx, o_lbl, ids_stage, rec_stage;
   DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l, gthr, tcsync, stream_ctl, fkey, fidx;
   DevBuf uncert1, t2_qf, t2_qhi, t2_qlo, t2_qnorm, t2_a, t2_i, t2_l;   // fp32 stores: tier-1 list + tier-2 sub-batch
-  int t1_skip = 0;                // batches left during which tier 1 is skipped (it failed for most queries)
+  int t1_level = 0, t1_hold = 0;  // adaptive tier-1 level (exact_split_search) and batches until it decays
+  int last_tier1_kc = 0;
   int64_t last_tier1_queries = 0, last_tier1_uncertified = 0;
   DevBuf lk_scores;               // large-k path: dense keys of one (query block x row chunk)
   void* pin = nullptr;            // pinned host staging of the small-batch path
@@ -718,10 +719,10 @@ int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float*
 // keeping kc > k candidates per query, re-scores the candidates exactly in fp32 (kernel 6) and certifies query q iff
 //     exact_key[k-1] > approx_key_of_the_worst_candidate + B,     B = eps * |q| * max|y| (x 2 for the L2 key)
 // -- then no row outside the candidate set can belong to the exact top-k.  Two approximations are used, cheapest first:
-//   tier 1   q_hi.y_hi (ONE MMA term, bf16 roundings of both operands: eps = 2^-8 + 2^-18 + accumulation), kc = 128.
+//   tier 1   q_hi.y_hi (ONE MMA term, bf16 roundings of both operands: eps = 2^-8 + 2^-18 + accumulation), kc = 32
+//            (k <= 12; register-list epilogue) or 128 (k <= 32; reservoir epilogue + sampled admission bound).
 //            A third of the tensor work and half of the database bytes of tier 2; certifies whenever the exact k-th
-//            key clears the 128-th approximate key by ~0.4 % of |q||y| (k <= 32, N >= 262144 rows: the sampled
-//            admission bound keeps the kc = 128 epilogue cheap).
+//            key clears the kc-th approximate key by ~0.4 % of |q||y| (N >= 262144 rows).
 //   tier 2   q_lo.y_hi + q_hi.y_lo + q_hi.y_hi (three terms, eps = 3.02 * 2^-18 + accumulation), kc = 16 .. 128.
 // Queries tier 1 cannot certify are compacted and go through tier 2; what tier 2 cannot certify (adversarial ties) is
 // searched by the exact CUDA-core kernel.  Every tier ends in exact fp32 keys, so the result does not depend on which
@@ -805,8 +806,9 @@ int split3_search(rdb_handle* h, const QueryView& v, int k, bool shard_mode, flo
   return RDB_OK;
 }
 
-constexpr int kTier1MaxK = 32;      // kc = 128 candidates: >= 4x slack
-constexpr int kTier1Candidates = 128;
+constexpr int kTier1MaxK = 32;        // kc = 128 candidates: >= 4x slack
+constexpr int kTier1SmallK = 12;      // k <= 12: 32 candidates (register-list epilogue, no sample pass) usually suffice
+constexpr int kTier1Hold = 8;         // batches a raised level is kept before it decays by one
 
 int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mode, float* d_a, int64_t* d_i, float* d_l,
                        const float* labels) {
@@ -814,21 +816,31 @@ int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mod
   cudaStream_t s = h->stream;
   int rc;
   const int64_t ntiles = (h->n + TC_BN - 1) / TC_BN;
-  bool tier1 = k <= kTier1MaxK && ntiles >= kTcPivotMinTiles && !getenv("RDB_NO_TIER1");
-  if (tier1 && h->t1_skip > 0) { h->t1_skip--; tier1 = false; }     // recent batches mostly failed tier 1: do not pay for it
+  // Tier-1 level, adapted to how the data certifies: 0 = 32 candidates when k <= 12 (on iid Gaussian data the exact
+  // k-th key clears the 32nd approximate key by ~2.7 standard deviations of that gap: ~0.3 % of the queries fail),
+  // 1 = 128 candidates (more than 5 % failed with 32), 2 = no tier 1 (more than half failed with 128).  A raised level
+  // decays by one after kTier1Hold batches, so a change of the data is picked up again.
+  if (h->t1_hold > 0 && --h->t1_hold == 0 && h->t1_level > 0) { h->t1_level--; h->t1_hold = h->t1_level > 0 ? kTier1Hold : 0; }
+  const bool tier1 = k <= kTier1MaxK && ntiles >= kTcPivotMinTiles && h->t1_level < 2 && !getenv("RDB_NO_TIER1");
   if (!tier1) return split3_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels, true);
+  int kc1 = (h->t1_level == 0 && k <= kTier1SmallK) ? 32 : 128;
+  if (const char* e = getenv("RDB_TIER1_KC")) { const int f = atoi(e); if (f == 32 || f == 64 || f == 128) kc1 = std::max(f, k <= 12 ? 32 : 128); }
 
   CUDA_TRY(h, h->uncert1.ensure(size_t(nb + 1) * 4));
   int* ucount = h->uncert1.as<int>();
   int* ulist = ucount + 1;
-  if ((rc = certified_pass(h, qv, k, kTier1Candidates, 1, shard_mode, d_a, d_i, d_l, labels, ucount, ulist, true)))
+  if ((rc = certified_pass(h, qv, k, kc1, 1, shard_mode, d_a, d_i, d_l, labels, ucount, ulist, true)))
     return rc;
   int m = 0;
   CUDA_TRY(h, cudaMemcpyAsync(&m, ucount, 4, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(h, cudaStreamSynchronize(s));
   h->last_tier1_queries += nb;
   h->last_tier1_uncertified += m;
-  if (2 * m > nb) h->t1_skip = 8;
+  h->last_tier1_kc = kc1;
+  if (kc1 < 128 ? (20 * int64_t(m) > nb) : (2 * int64_t(m) > nb)) {
+    h->t1_level = kc1 < 128 ? 1 : 2;
+    h->t1_hold = kTier1Hold;
+  }
   if (m == 0) return RDB_OK;
   // compact the uncertified queries and run tier 2 on them
   CUDA_TRY(h, h->t2_qf.ensure(size_t(m) * D * 4));
@@ -1330,10 +1342,11 @@ int rdb_last_kernel_ms(rdb_handle* h, float* ms, int* algo, int* nsplits) {
 
 int64_t rdb_last_uncertified(rdb_handle* h) { return h ? h->last_uncertified : 0; }
 
-int rdb_last_tier1(rdb_handle* h, int64_t* queries, int64_t* uncertified) {
+int rdb_last_tier1(rdb_handle* h, int64_t* queries, int64_t* uncertified, int* candidates) {
   if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
   if (queries) *queries = h->last_tier1_queries;
   if (uncertified) *uncertified = h->last_tier1_uncertified;
+  if (candidates) *candidates = h->last_tier1_queries > 0 ? h->last_tier1_kc : 0;
   return RDB_OK;
 }
 

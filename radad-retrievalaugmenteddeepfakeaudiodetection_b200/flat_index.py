@@ -346,9 +346,16 @@ class FlatIndex(_ReconstructCache):
     @property
     def last_tier1(self) -> Tuple[int, int]:
         """(queries that entered the one-term certified pass, queries it could not certify) of the last search."""
-        a, b = ctypes.c_int64(), ctypes.c_int64()
-        self._check(self._lib.rdb_last_tier1(self._h, ctypes.byref(a), ctypes.byref(b)))
+        a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+        self._check(self._lib.rdb_last_tier1(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return int(a.value), int(b.value)
+
+    @property
+    def last_tier1_candidates(self) -> int:
+        """Candidates per query the one-term certified pass of the last search kept (0 = it did not run)."""
+        a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+        self._check(self._lib.rdb_last_tier1(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return int(c.value)
 
     def mem_info(self):
         a, b, c = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()

@@ -42,6 +42,7 @@ def test_tier1_certifies_gaussian(pkg, oracle, monkeypatch, metric_s, cos, k):
     D, I = idx.search(xq, k, normalize=cos)
     t1q, t1u = idx.last_tier1
     assert t1q == Q and t1u <= Q // 10, (t1q, t1u)
+    assert idx.last_tier1_candidates == (32 if k <= 12 else 128)
     assert idx.last_kernel_ms()[1] == "tc"
     _check_vs_oracle(pkg, oracle, idx, xb, xq, D, I, k, metric, cos)
     monkeypatch.setenv("RDB_NO_TIER1", "1")
@@ -71,13 +72,17 @@ def test_tier_chain_when_nothing_certifies(pkg, oracle):
     D, I = idx.search(xq, k)
     t1q, t1u = idx.last_tier1
     assert t1q == Q and t1u == Q, (t1q, t1u)
-    assert idx.last_uncertified == Q
+    assert idx.last_tier1_candidates == 32 and idx.last_uncertified == Q
     np.testing.assert_array_equal(I, Ir)
     np.testing.assert_array_equal(D, Dr)
-    D2, I2 = idx.search(xq, k)
-    assert idx.last_tier1 == (0, 0)                    # skipped: recent failure rate
+    D2, I2 = idx.search(xq, k)                         # 32 candidates failed for > 5 %: 128 candidates now
+    assert idx.last_tier1 == (Q, Q) and idx.last_tier1_candidates == 128
     np.testing.assert_array_equal(I2, Ir)
     np.testing.assert_array_equal(D2, Dr)
+    D3, I3 = idx.search(xq, k)                         # 128 failed for > 50 %: tier 1 is skipped for a while
+    assert idx.last_tier1 == (0, 0) and idx.last_tier1_candidates == 0
+    np.testing.assert_array_equal(I3, Ir)
+    np.testing.assert_array_equal(D3, Dr)
 
 
 def test_lattice_with_ties_inside_the_candidates(pkg, oracle):
