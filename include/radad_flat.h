@@ -170,7 +170,7 @@ int rdb_last_kernel_ms(rdb_handle* h, float* ms, int* algo, int* nsplits);
  * Returns how many queries of the last search took that fallback. */
 int64_t rdb_last_uncertified(rdb_handle* h);
 
-/* fp32 stores, k <= 32, >= 262144 rows: a cheaper certified pass runs first (tier 1: ONE tensor-core term on the bf16
+/* fp32 stores, k <= 64, >= 262144 rows: a cheaper certified pass runs first (tier 1: ONE tensor-core term on the bf16
  * roundings, 32 or 128 candidates, exact fp32 re-rank, certificate against the bf16 error bound); only the queries it
  * cannot certify go through the three-term pass above.  Returns, for the last search, how many queries entered tier 1,
  * how many of them it could not certify, and the candidates kept per query (0 / 0 / 0 when tier 1 did not run).

@@ -720,7 +720,7 @@ int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float*
 //     exact_key[k-1] > approx_key_of_the_worst_candidate + B,     B = eps * |q| * max|y| (x 2 for the L2 key)
 // -- then no row outside the candidate set can belong to the exact top-k.  Two approximations are used, cheapest first:
 //   tier 1   q_hi.y_hi (ONE MMA term, bf16 roundings of both operands: eps = 2^-8 + 2^-18 + accumulation), kc = 32
-//            (k <= 12; register-list epilogue) or 128 (k <= 32; reservoir epilogue + sampled admission bound).
+//            (k <= 12; register-list epilogue) or 128 (k <= 64; reservoir epilogue + sampled admission bound).
 //            A third of the tensor work and half of the database bytes of tier 2; certifies whenever the exact k-th
 //            key clears the kc-th approximate key by ~0.4 % of |q||y| (N >= 262144 rows).
 //   tier 2   q_lo.y_hi + q_hi.y_lo + q_hi.y_hi (three terms, eps = 3.02 * 2^-18 + accumulation), kc = 16 .. 128.
@@ -806,7 +806,7 @@ int split3_search(rdb_handle* h, const QueryView& v, int k, bool shard_mode, flo
   return RDB_OK;
 }
 
-constexpr int kTier1MaxK = 32;        // kc = 128 candidates: >= 4x slack
+constexpr int kTier1MaxK = 64;        // kc = 128 candidates: >= 2x slack (k = 64 vs 128: the gap is ~2.6 sd above the bound on Gaussian data)
 constexpr int kTier1SmallK = 12;      // k <= 12: 32 candidates (register-list epilogue, no sample pass) usually suffice
 constexpr int kTier1Hold = 8;         // batches a raised level is kept before it decays by one
 

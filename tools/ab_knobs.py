@@ -11,6 +11,7 @@ import json
 import os
 import statistics
 import sys
+import time
 
 import torch
 
@@ -37,6 +38,7 @@ def main():
     q = torch.randn((Q, D), generator=g, device=dev)
     knobs = sorted({kv.split("=")[0] for v in variants for kv in v.split(",") if kv})
     ms = {v: [] for v in variants}
+    wall = {v: [] for v in variants}
     ref = None
     for r in range(rounds + 1):
         for v in variants:
@@ -47,10 +49,13 @@ def main():
                     a, b = kv.split("=")
                     os.environ[a] = b
             for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
                 Dv, Iv = idx.search(q, k, normalize=(metric_s.upper() == "IP"))[:2]
                 torch.cuda.synchronize()
                 if r > 0:
                     ms[v].append(idx.last_kernel_ms()[0])
+                    wall[v].append((time.perf_counter() - t0) * 1e3)
             if ref is None:
                 ref = Iv.clone()
             elif not torch.equal(ref, Iv):
@@ -62,6 +67,7 @@ def main():
         print(json.dumps({"config": f"{N}x{D} {store} {metric_s} Q={Q} k={k}", "variant": v or "(default)",
                           "kernel_ms_median": round(med, 3), "kernel_ms_min": round(best, 3),
                           "tflops_median": round(flops / med / 1e9, 1), "samples": len(ms[v]),
+                          "search_ms_median": round(statistics.median(wall[v]), 3),
                           "scorer": idx.last_kernel_ms()[1], "splits": idx.last_kernel_ms()[2]}), flush=True)
 
 
