@@ -720,7 +720,7 @@ int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float*
 //     exact_key[k-1] > approx_key_of_the_worst_candidate + B,     B = eps * |q| * max|y| (x 2 for the L2 key)
 // -- then no row outside the candidate set can belong to the exact top-k.  Two approximations are used, cheapest first:
 //   tier 1   q_hi.y_hi (ONE MMA term, bf16 roundings of both operands: eps = 2^-8 + 2^-18 + accumulation), kc = 32
-//            (k <= 12; register-list epilogue) or 128 (k <= 64; reservoir epilogue + sampled admission bound).
+//            (k <= 16; register-list epilogue) or 128 (k <= 64; reservoir epilogue + sampled admission bound).
 //            A third of the tensor work and half of the database bytes of tier 2; certifies whenever the exact k-th
 //            key clears the kc-th approximate key by ~0.4 % of |q||y| (N >= 262144 rows).
 //   tier 2   q_lo.y_hi + q_hi.y_lo + q_hi.y_hi (three terms, eps = 3.02 * 2^-18 + accumulation), kc = 16 .. 128.
@@ -807,7 +807,8 @@ int split3_search(rdb_handle* h, const QueryView& v, int k, bool shard_mode, flo
 }
 
 constexpr int kTier1MaxK = 64;        // kc = 128 candidates: >= 2x slack (k = 64 vs 128: the gap is ~2.6 sd above the bound on Gaussian data)
-constexpr int kTier1SmallK = 12;      // k <= 12: 32 candidates (register-list epilogue, no sample pass) usually suffice
+constexpr int kTier1SmallK = 16;      // k <= 16 (the reference asks for top_k + 10 = 15): 32 candidates (register-list epilogue, no
+                                      // sample pass); a failed query only costs its share of a three-term pass
 constexpr int kTier1Hold = 8;         // batches a raised level is kept before it decays by one
 
 int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mode, float* d_a, int64_t* d_i, float* d_l,
@@ -816,15 +817,16 @@ int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mod
   cudaStream_t s = h->stream;
   int rc;
   const int64_t ntiles = (h->n + TC_BN - 1) / TC_BN;
-  // Tier-1 level, adapted to how the data certifies: 0 = 32 candidates when k <= 12 (on iid Gaussian data the exact
-  // k-th key clears the 32nd approximate key by ~2.7 standard deviations of that gap: ~0.3 % of the queries fail),
-  // 1 = 128 candidates (more than 5 % failed with 32), 2 = no tier 1 (more than half failed with 128).  A raised level
+  // Tier-1 level, adapted to how the data certifies: 0 = 32 candidates when k <= 16 (on iid Gaussian data at D = 768
+  // the exact 10th key clears the 32nd approximate key by ~2.7 standard deviations of that gap: ~0.3 % of the queries
+  // fail; k = 15: ~5 %), 1 = 128 candidates (more than a quarter failed with 32: beyond that the three-term pass over
+  // the failures costs more than the larger epilogue), 2 = no tier 1 (more than half failed with 128).  A raised level
   // decays by one after kTier1Hold batches, so a change of the data is picked up again.
   if (h->t1_hold > 0 && --h->t1_hold == 0 && h->t1_level > 0) { h->t1_level--; h->t1_hold = h->t1_level > 0 ? kTier1Hold : 0; }
   const bool tier1 = k <= kTier1MaxK && ntiles >= kTcPivotMinTiles && h->t1_level < 2 && !getenv("RDB_NO_TIER1");
   if (!tier1) return split3_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels, true);
   int kc1 = (h->t1_level == 0 && k <= kTier1SmallK) ? 32 : 128;
-  if (const char* e = getenv("RDB_TIER1_KC")) { const int f = atoi(e); if (f == 32 || f == 64 || f == 128) kc1 = std::max(f, k <= 12 ? 32 : 128); }
+  if (const char* e = getenv("RDB_TIER1_KC")) { const int f = atoi(e); if (f == 32 || f == 64 || f == 128) kc1 = std::max(f, k <= kTier1SmallK ? 32 : 128); }
 
   CUDA_TRY(h, h->uncert1.ensure(size_t(nb + 1) * 4));
   int* ucount = h->uncert1.as<int>();
@@ -837,7 +839,7 @@ int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mod
   h->last_tier1_queries += nb;
   h->last_tier1_uncertified += m;
   h->last_tier1_kc = kc1;
-  if (kc1 < 128 ? (20 * int64_t(m) > nb) : (2 * int64_t(m) > nb)) {
+  if (kc1 < 128 ? (4 * int64_t(m) > nb) : (2 * int64_t(m) > nb)) {
     h->t1_level = kc1 < 128 ? 1 : 2;
     h->t1_hold = kTier1Hold;
   }
