@@ -67,6 +67,7 @@ __device__ __forceinline__ float floor_from_gthr(uint32_t g) {
 
 template <int KT>
 struct SelectSmall {
+  static constexpr bool kDump = false;
   TopK<KT> top;
   float floor_;
   uint32_t* gq;
@@ -96,6 +97,7 @@ struct SelectSmall {
 // Appends are ~k*ln(n/k) per thread per unit and cost one scattered local store each.
 template <int CAP>
 struct SelectReservoir {
+  static constexpr bool kDump = false;
   static constexpr int B = 16;   // entries loaded per batch: independent local-memory loads in flight per thread
   uint32_t okey[CAP];   // ordered_f32(key); 0 = never a valid key of a finite score
   int idx[CAP];
@@ -197,6 +199,19 @@ struct SelectReservoir {
       if (rank < kout) { ck[rank] = unordered_f32(oa); ci[rank] = ia; }
     }
   }
+};
+
+// "Selector" of the k > 128 path on 16-bit stores: no selection at all -- the tensor-core epilogue writes every key of
+// its query row to a dense [queries][rows] buffer in HBM (row = this query's line of it, or null for padding rows of
+// the query tile) and select_dense_kernel (select_large.cuh) picks the best k afterwards.
+struct SelectDump {
+  static constexpr bool kDump = true;
+  float* row;          // &dump[q][0] - row_base, so row[global row id] is this query's slot for that row
+  __device__ __forceinline__ void init(int, uint32_t*) { row = nullptr; }
+  __device__ __forceinline__ float threshold() const { return -CUDART_INF_F; }
+  __device__ __forceinline__ void offer(float, int) {}
+  __device__ __forceinline__ void end_group(int) {}
+  __device__ __forceinline__ void finalize(int, float*, int*) {}
 };
 
 // ----------------------------------------------------------------------------------------------

@@ -329,6 +329,7 @@ int launch_tc_cg(rdb_handle* h, TcParams& p, int k) {
   p.idesc = make_idesc_f16(TC_BM * CG, TC_BN, h->f16() ? 0 : 1);
   const int groups = std::min(p.num_units, h->num_sms / CG);
   const bool l2 = h->metric == RDB_METRIC_L2;
+  if (p.dump)       return l2 ? launch_tc_kernel<SelectDump, true, CG>(h, p, groups) : launch_tc_kernel<SelectDump, false, CG>(h, p, groups);
   if (k <= 16)      return l2 ? launch_tc_kernel<SelectSmall<16>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<16>, false, CG>(h, p, groups);
   else if (k <= 32) return l2 ? launch_tc_kernel<SelectSmall<32>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<32>, false, CG>(h, p, groups);
   return l2 ? launch_tc_kernel<SelectReservoir<kReservoirCap>, true, CG>(h, p, groups)
@@ -338,7 +339,8 @@ int launch_tc_cg(rdb_handle* h, TcParams& p, int k) {
 // nqg = query-tile GROUPS (128 * cg queries each); S chunks of tiles_per_chunk 256-row database tiles
 int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, int cg, int nqg, int S, int tiles_per_chunk,
               int ntiles, int nterms, float* ck, int* ci, int tile_step = 1, bool keep_gthr = false,
-              const int* run_if = nullptr) {
+              const int* run_if = nullptr, float* dump = nullptr, long long dump_pitch = 0, int row_base = 0,
+              int row_end = 0) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -354,6 +356,7 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
   p.astat = (nterms == 1 && h->d <= TcCfg<1>::ASTAT_MAX_KS * TC_BK && !getenv("RDB_TC_NO_ASTAT")) ? 1 : 0;
   p.gthr = (S > 1 || TC_LISTS > 1) ? h->gthr.as<uint32_t>() : nullptr;
   p.nq = nq; p.N = int(h->n); p.D = h->d;
+  if (dump) { p.dump = dump; p.dump_pitch = dump_pitch; p.row_base = row_base; p.N = row_end; }   // k > 128: rows [row_base, row_end)
   p.nqt = nqg; p.S = S; p.tiles_per_chunk = tiles_per_chunk; p.ntiles = ntiles; p.kout = k;
   p.num_units = nqg * S; p.nterms = nterms;
   { const char* v = getenv("RDB_TC_DEBUG"); p.dbg = v ? atoi(v) : 0; }
@@ -654,11 +657,19 @@ int launch_simt_dump(rdb_handle* h, const QueryView& qv, int q0, int nq, int nqt
 
 int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
   const int64_t N = h->n;
+  // 16-bit stores: the keys come from the tensor cores (SelectDump epilogue of kernel 2); fp32 stores need exact fp32
+  // keys -> CUDA-core scorer.  RDB_LARGEK_SCORER=simt|tc overrides (tests).
+  bool use_tc = h->store != RDB_STORE_F32 && N >= kMinRowsTc;
+  if (const char* e = getenv("RDB_LARGEK_SCORER")) {
+    if (!strcmp(e, "simt")) use_tc = false;
+    else if (!strcmp(e, "tc") && h->store != RDB_STORE_F32 && N >= TC_BN) use_tc = true;
+  }
+  const int64_t align = use_tc ? TC_BN : SIMT_BN;
   int64_t rows = kLargeKRowsDefault;
   if (const char* e = getenv("RDB_LARGEK_ROWS")) rows = std::max<int64_t>(1, atoll(e));   // tests: force several chunks
   rows = std::max<int64_t>(rows, (N + 255) / 256);          // merge_lists_kernel folds at most 256 lists
-  rows = round_up(rows, SIMT_BN);
-  rows = std::min<int64_t>(rows, round_up(N, SIMT_BN));
+  rows = round_up(rows, align);
+  rows = std::min<int64_t>(rows, round_up(N, align));
   const int S = int((N + rows - 1) / rows);
   const int qb = std::min(qv.nq, kLargeKQueryBlock);
   CUDA_TRY(h, h->lk_scores.ensure(size_t(qb) * size_t(rows) * 4));
@@ -674,14 +685,25 @@ int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
     for (int c = 0; c < S; ++c) {
       const int64_t row0 = int64_t(c) * rows, row_end = std::min<int64_t>(N, row0 + rows);
       const int len = int(row_end - row0);
-      const int tiles = (len + SIMT_BN - 1) / SIMT_BN;
-      int units = std::min(tiles, std::max(1, 8 * h->num_sms / nqt));
-      const int tpu = (tiles + units - 1) / units;
-      units = (tiles + tpu - 1) / tpu;
-      rc = (h->metric == RDB_METRIC_L2)
-               ? launch_simt_dump<true>(h, qv, q0, nqs, nqt, units, tpu * SIMT_BN, int(row0), int(row_end), scores, rows)
-               : launch_simt_dump<false>(h, qv, q0, nqs, nqt, units, tpu * SIMT_BN, int(row0), int(row_end), scores, rows);
-      if (rc) return rc;
+      if (use_tc) {
+        const int cg = tc_cta_group(nqs, 1, h->d);
+        const int nqg = (nqs + TC_BM * cg - 1) / (TC_BM * cg);
+        const int tiles = (len + TC_BN - 1) / TC_BN;
+        int tpc;
+        const int units = choose_splits(nqg, tiles, h->num_sms / cg, 256, 4, &tpc);
+        const char* qhi = static_cast<const char*>(qv.qhi) + size_t(q0) * h->dp * 2;
+        if ((rc = launch_tc(h, qhi, nullptr, nqs, k, cg, nqg, units, tpc, tiles, 1, nullptr, nullptr, 1, false, nullptr,
+                            scores, rows, int(row0), int(row_end)))) return rc;
+      } else {
+        const int tiles = (len + SIMT_BN - 1) / SIMT_BN;
+        int units = std::min(tiles, std::max(1, 8 * h->num_sms / nqt));
+        const int tpu = (tiles + units - 1) / units;
+        units = (tiles + tpu - 1) / tpu;
+        rc = (h->metric == RDB_METRIC_L2)
+                 ? launch_simt_dump<true>(h, qv, q0, nqs, nqt, units, tpu * SIMT_BN, int(row0), int(row_end), scores, rows)
+                 : launch_simt_dump<false>(h, qv, q0, nqs, nqt, units, tpu * SIMT_BN, int(row0), int(row_end), scores, rows);
+        if (rc) return rc;
+      }
       select_dense_kernel<<<nqs, SELK_THREADS, 0, s>>>(scores, rows, len, int(row0), k, S, c, q0,
                                                        h->cand_key.as<float>(), h->cand_idx.as<int>());
       h->launches++;
@@ -689,7 +711,7 @@ int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
     }
   }
   cudaEventRecord(h->ev1, s);
-  h->ev_valid = true; h->last_algo = RDB_ALGO_SIMT; h->last_S = S;
+  h->ev_valid = true; h->last_algo = use_tc ? RDB_ALGO_TC : RDB_ALGO_SIMT; h->last_S = S;
   *L_out = S;
   return RDB_OK;
 }
@@ -878,8 +900,8 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
     return fail(h, RDB_ERR_INVALID, "search: bad arguments (nq >= 0, k >= 1, non-null buffers)");
   if (k > kMaxKLarge) return fail(h, RDB_ERR_UNSUPPORTED, "search: k > 2048 is not supported (the limit of faiss-gpu itself)");
   const bool largek = k > kMaxK;     // dense keys + radix select (exact fp32 keys on CUDA cores)
-  if (largek && algo != RDB_ALGO_AUTO && algo != RDB_ALGO_SIMT)
-    return fail(h, RDB_ERR_UNSUPPORTED, "search: k > 128 runs on the exact CUDA-core scorer only (RDB_ALGO_AUTO / RDB_ALGO_SIMT)");
+  if (largek && algo == RDB_ALGO_STREAM)
+    return fail(h, RDB_ERR_UNSUPPORTED, "search: the streaming scorer holds k <= 128 (use RDB_ALGO_AUTO for larger k)");
   if (nq == 0) return RDB_OK;
   const int D = h->d, Dp = h->dp;
   const bool host = mem == RDB_MEM_HOST;

@@ -77,6 +77,11 @@ struct TcParams {
   int nstages;              // ring slots used (<= TcCfg::STAGES; profiling knob RDB_TC_STAGES)
   int astat;                // query-stationary form (host: nterms == 1 && D <= 256)
   const int* run_if;        // fallback launch: all CTAs exit at once unless *run_if != 0 (null = always run)
+  // k > 128 path (SelectDump): the launch covers rows [row_base, N) only (row_base a multiple of 256; tile t stands
+  // for rows row_base + 256 t ...) and writes key(q, row) to dump[q * dump_pitch + row - row_base]
+  int row_base;
+  float* dump;
+  long long dump_pitch;
 };
 
 // ---- lock-step window ----------------------------------------------------------------------------------------------
@@ -130,6 +135,33 @@ __device__ __forceinline__ void tc_process32(uint32_t (&r)[32], Sel& sel, const 
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if constexpr (Sel::kDump) {
+    // k > 128: no selection -- this thread's 32 keys go to its query's line of the dense key buffer (128 bytes)
+    if (sel.row != nullptr && nvalid > 0) {
+      if (L2) {
+        float4 y[8];
+        tc_load_yn(y, ynorm, col0);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          v[4 * g + 0] = fmaf(2.0f, v[4 * g + 0], -y[g].x);
+          v[4 * g + 1] = fmaf(2.0f, v[4 * g + 1], -y[g].y);
+          v[4 * g + 2] = fmaf(2.0f, v[4 * g + 2], -y[g].z);
+          v[4 * g + 3] = fmaf(2.0f, v[4 * g + 3], -y[g].w);
+        }
+      }
+      float* dst = sel.row + col0;
+      if (nvalid >= 32) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          __stcs(reinterpret_cast<float4*>(dst) + g, make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) dst[j] = v[j];
+      }
+    }
+    return;
+  }
   const float worst = sel.threshold();
   // fast path: a depth-5 max tree (31 independent FMNMX) decides whether ANY of the 32 columns can survive;
   // in steady state almost no group does, so the per-element compare/mask work below is skipped entirely.
@@ -324,11 +356,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
                 if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * slot_bytes);
                 if (!astat) tma_load_2d_pair(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
                 tma_load_2d_pair(sa + b_off, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK,
-                                 t * p.tile_step * TC_BN + rank * Cfg::B_ROWS, p.hint_y);
+                                 p.row_base + t * p.tile_step * TC_BN + rank * Cfg::B_ROWS, p.hint_y);
               } else {
                 mbar_expect_tx(&full_bar[stage], slot_bytes);
                 if (!astat) tma_load_2d(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
-                tma_load_2d(sa + b_off, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK, t * p.tile_step * TC_BN, p.hint_y);
+                tma_load_2d(sa + b_off, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK, p.row_base + t * p.tile_step * TC_BN,
+                            p.hint_y);
               }
               if (++stage == nst) { stage = 0; phase ^= 1; }
             }
@@ -389,11 +422,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
       const long long q = (long long)qtile * TC_BM + row;
       Sel sel;
       sel.init(p.kout, (p.gthr && q < p.nq) ? p.gthr + q : nullptr);
+      if constexpr (Sel::kDump) sel.row = (q < p.nq) ? p.dump + q * p.dump_pitch - p.row_base : nullptr;
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * TC_BN + half * (TC_BN / 2));
-        const int n0 = t * p.tile_step * TC_BN + half * (TC_BN / 2);
+        const int n0 = p.row_base + t * p.tile_step * TC_BN + half * (TC_BN / 2);
         const int nvalid = p.N - n0;         // >= 128 for full tiles
         if (p.dbg & 1) {
           tc_fence_before();
