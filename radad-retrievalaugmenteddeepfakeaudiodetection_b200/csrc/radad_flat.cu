@@ -677,6 +677,9 @@ int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
   CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * k * 4));
   float* scores = h->lk_scores.as<float>();
   cudaStream_t s = h->stream;
+  CUDA_TRY(h, cudaFuncSetAttribute(select_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)selk_smem_bytes()));
+  const int use_sample = getenv("RDB_LARGEK_NO_SAMPLE") ? 0 : 1;      // sampled-pivot fast path of the select (A/B knob)
   cudaEventRecord(h->ev0, s);
   int rc;
   for (int q0 = 0; q0 < qv.nq; q0 += kLargeKQueryBlock) {
@@ -704,8 +707,9 @@ int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
                  : launch_simt_dump<false>(h, qv, q0, nqs, nqt, units, tpu * SIMT_BN, int(row0), int(row_end), scores, rows);
         if (rc) return rc;
       }
-      select_dense_kernel<<<nqs, SELK_THREADS, 0, s>>>(scores, rows, len, int(row0), k, S, c, q0,
-                                                       h->cand_key.as<float>(), h->cand_idx.as<int>());
+      select_dense_kernel<<<nqs, SELK_THREADS, selk_smem_bytes(), s>>>(scores, rows, len, int(row0), k, S, c, q0,
+                                                                       use_sample, h->cand_key.as<float>(),
+                                                                       h->cand_idx.as<int>());
       h->launches++;
       CUDA_TRY(h, cudaGetLastError());
     }

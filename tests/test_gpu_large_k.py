@@ -97,6 +97,40 @@ def test_gaussian_vs_oracle_k_above_128(pkg, oracle, monkeypatch, case):
     assert all(len(set(r.tolist())) == k for r in I)
 
 
+@pytest.mark.parametrize("sample", [True, False])
+@pytest.mark.parametrize("kind", ["gauss", "lattice", "on_stride"])
+def test_long_rows_sampled_pivot_select(pkg, oracle, monkeypatch, kind, sample):
+    """Chunks of >= 32768 rows take the select's fast path (pivot from a strided sample + one collect pass); it must be
+    exact on Gaussian keys, on lattice keys (ties ordered by id), and when the sample misleads (the best rows sit
+    exactly on the sample stride -> too few rows reach the pivot -> exact path).  Same answers with the fast path off."""
+    if not sample:
+        monkeypatch.setenv("RDB_LARGEK_NO_SAMPLE", "1")
+    N, Dm, Q, k = 163_840, 32, 12, 700
+    rng = np.random.default_rng(8)
+    if kind == "gauss":
+        xb, xq = _gauss(N, Dm, 1), _gauss(Q, Dm, 2)
+    else:
+        xb = rng.integers(-2, 3, size=(N, Dm)).astype(np.float32)
+        xq = rng.integers(-2, 3, size=(Q, Dm)).astype(np.float32)
+        if kind == "on_stride":
+            xb[::10] = xq[0]                                      # stride of the sample = N // 16384 = 10
+    idx = pkg.FlatIndex(Dm, pkg.METRIC_L2, "bf16" if kind != "gauss" else "f32")
+    idx.add(xb)
+    D, I = idx.search(xq, k)
+    ref = oracle.FlatIndexOracle(Dm, pkg.METRIC_L2)
+    ref.add(xb)
+    if kind == "gauss":
+        Dr, Ir = ref.search(xq, k + 8, direct=False)
+        scale = float((xq * xq).sum(1).max() + (xb * xb).sum(1).max())
+        st = oracle.compare_topk(D, I, Dr, Ir, lambda ids: ref.exact_scores(xq, ids), pkg.METRIC_L2, tol=TOL_F32,
+                                 abs_floor=2e-6 * scale)
+        assert st["recall"] == 1.0, st
+    else:
+        Dr, Ir = ref.search(xq, k, direct=False)
+        np.testing.assert_array_equal(I, Ir)
+        np.testing.assert_array_equal(D, Dr)
+
+
 def test_k_beyond_ntotal_and_limits(pkg, tmp_path):
     """k > ntotal at the index level: faiss fills id -1 / +inf; the wrapper clamps k to ntotal (vector_database.py:169);
     k > 2048 is refused loudly (faiss-gpu's own limit)."""

@@ -67,3 +67,54 @@ def test_radix_select_mirror_matches_sort(seed):
     np.testing.assert_array_equal(rows, order)
     if kind == 2 and n > k:
         assert passes >= 5
+
+
+def sampled_select_mirror(keys, row0, k, cap=8192, sample=16384, min_len=32768):
+    """Fast path of select_dense_kernel: pivot from a strided sample, one collect pass, exact iff k <= count <= cap.
+    Returns (selected or None when the kernel would fall back, count)."""
+    n = len(keys)
+    kk = min(k, n)
+    if n < min_len or n <= k:
+        return None, 0
+    st = n // sample
+    ns = (n + st - 1) // st
+    r = max(32, (5 * kk // 2 + st - 1) // st)
+    if r >= ns:
+        return None, 0
+    v = _pack(keys, row0)
+    vs = v[::st]
+    assert len(vs) == ns
+    T = np.sort(vs)[::-1][r - 1]                       # what the radix select on the sample returns
+    sel = v[v >= T]
+    if kk <= len(sel) <= cap:
+        return np.sort(sel)[::-1][:kk], len(sel)
+    return None, len(sel)
+
+
+@pytest.mark.parametrize("n,k", [(40_000, 129), (300_000, 1000), (1_000_000, 2048), (70_001, 500)])
+def test_sampled_pivot_fast_path_is_exact_and_usually_taken(n, k):
+    keys = np.random.default_rng(n + k).standard_normal(n).astype(np.float32)
+    got, count = sampled_select_mirror(keys, 12345, k)
+    assert got is not None, count                      # Gaussian keys: the pivot lands between k and the buffer size
+    assert k <= count <= 8192
+    np.testing.assert_array_equal(got, np.sort(_pack(keys, 12345))[::-1][:k])
+
+
+def test_sampled_pivot_with_heavy_ties():
+    """(key, id) pairs are distinct, so ties on the key do not pile up at the pivot: the fast path stays exact and is
+    still taken (ids order the ~28 K elements per key value)."""
+    keys = np.random.default_rng(5).integers(-3, 4, 200_000).astype(np.float32)
+    got, count = sampled_select_mirror(keys, 0, 300)
+    assert got is not None and 300 <= count <= 8192
+    np.testing.assert_array_equal(got, np.sort(_pack(keys, 0))[::-1][:300])
+
+
+def test_sampled_pivot_falls_back_when_the_sample_misleads():
+    """Adversarial layout: the large keys sit exactly on the sample stride, so the pivot is far too high for the row
+    -> fewer than k elements reach it -> the kernel takes the exact path."""
+    n, k = 163_840, 1000
+    keys = np.zeros(n, np.float32)
+    keys[::10] = 5.0                                   # stride = n // 16384 = 10: every sampled element is a 5.0
+    keys[1::10] = np.linspace(1.0, 4.0, len(keys[1::10]), dtype=np.float32)
+    got, count = sampled_select_mirror(keys, 0, k)
+    assert got is None and count < k
