@@ -164,6 +164,35 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
                                      out_idx, out_lbl, out_key, lane, nullptr);
 }
 
+// A single, already sorted list per query (the k > 128 path with one row chunk): nothing to merge -- convert keys to
+// distances, local to global ids and gather the labels, one thread per output slot.  Same output conventions as
+// merge_lists_warp (missing results: id -1, +inf / -inf, label 0, key -inf).
+__global__ void __launch_bounds__(256) finalize_sorted_list_kernel(const float* __restrict__ key_in,
+                                                                   const int* __restrict__ idx_in, int Q, int k,
+                                                                   int metric_l2, const float* __restrict__ qnorm,
+                                                                   long long id_offset, const float* __restrict__ labels,
+                                                                   float* __restrict__ out_dist,
+                                                                   long long* __restrict__ out_idx,
+                                                                   float* __restrict__ out_lbl,
+                                                                   float* __restrict__ out_key) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)Q * k) return;
+  const int q = int(t / k);
+  const int id = idx_in[t];
+  const float kv = key_in[t];
+  if (id < 0) {
+    if (out_dist) out_dist[t] = metric_l2 ? CUDART_INF_F : -CUDART_INF_F;
+    if (out_idx) out_idx[t] = -1;
+    if (out_lbl) out_lbl[t] = 0.f;
+    if (out_key) out_key[t] = -CUDART_INF_F;
+    return;
+  }
+  if (out_dist) out_dist[t] = metric_l2 ? fmaxf(0.f, qnorm[q] - kv) : kv;
+  if (out_idx) out_idx[t] = (long long)id + id_offset;
+  if (out_key) out_key[t] = kv;
+  if (out_lbl) out_lbl[t] = labels ? __ldg(labels + id) : 0.f;
+}
+
 // host helper: bytes of dynamic shared memory per warp for the staged form, or 0 when staging does not pay / fit
 template <typename IdxT>
 inline size_t merge_stage_bytes(int L, int kc, int kout) {

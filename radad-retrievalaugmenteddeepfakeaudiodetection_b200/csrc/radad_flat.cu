@@ -724,6 +724,16 @@ int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
 int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float* qnorm, bool shard_mode, float* d_a,
                     int64_t* d_i, float* d_l, long long id_offset, const float* labels, float* raw_key,
                     const int* run_if = nullptr) {
+  if (L == 1 && kc == kout && !run_if) {
+    // one sorted list per query (k > 128 with a single row chunk): elementwise conversion instead of k merge rounds
+    const long long total = (long long)nq * kout;
+    finalize_sorted_list_kernel<<<unsigned((total + 255) / 256), 256, 0, h->stream>>>(
+        h->cand_key.as<float>(), h->cand_idx.as<int>(), nq, kout, h->metric == RDB_METRIC_L2 ? 1 : 0, qnorm, id_offset,
+        labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l, shard_mode ? d_a : raw_key);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return RDB_OK;
+  }
   const size_t stage = merge_stage_bytes<int>(L, kc, kout);
   const int warps = stage > 12 * 1024 ? 2 : 4;             // <= 48 KB of dynamic shared memory per block
   dim3 grid((nq + warps - 1) / warps), block(32 * warps);

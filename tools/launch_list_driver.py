@@ -12,6 +12,8 @@ if which == "c2":
     N, D, Q, k, store, met = 1000000, 768, 10000, 10, "f32", pkg.METRIC_L2
 elif which == "c2cos":
     N, D, Q, k, store, met = 1000000, 768, 10000, 10, "f32", pkg.METRIC_IP
+elif which == "largek":
+    N, D, Q, k, store, met = 1000000, 768, 1000, 1000, "bf16", pkg.METRIC_IP
 elif which == "c1":
     N, D, Q, k, store, met = 20000, 768, 1000, 10, "f32", pkg.METRIC_IP
 else:
