@@ -151,9 +151,13 @@ __device__ __forceinline__ void tc_process32(uint32_t (&r)[32], Sel& sel, const 
       }
       float* dst = sel.row + col0;
       if (nvalid >= 32) {
+        // four 256-bit stores (sm_100: STG.256): every store fills whole 32-byte sectors of this query's line
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          __stcs(reinterpret_cast<float4*>(dst) + g, make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
+        for (int g = 0; g < 4; ++g)
+          asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * g), "f"(v[8 * g]),
+                       "f"(v[8 * g + 1]), "f"(v[8 * g + 2]), "f"(v[8 * g + 3]), "f"(v[8 * g + 4]), "f"(v[8 * g + 5]),
+                       "f"(v[8 * g + 6]), "f"(v[8 * g + 7])
+                       : "memory");
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
