@@ -3,7 +3,8 @@
 
 Run in the build container only (needs /root/reference, which the GPU box lacks):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py                       # everything
+    python tests/golden/make_golden.py --only NAME [NAME ...]   # only these search fixtures (e.g. lattice_l2_k200)
 
 What runs unmodified from /root/reference: ``vector_database.py::VectorDatabase`` (all
 wrapper logic: normalisation, batching, metadata bookkeeping, k clamping, return types),
@@ -156,10 +157,16 @@ def main():
         ("gauss_l2_small", gaussian, 1500, 96,  5,  15, "L2"),   # nq < 20: FAISS direct path
         ("kclamp_l2",      gaussian, 7,    32,  4,  15, "L2"),   # k > ntotal -> clamped
         ("ref_shape_l2",   gaussian, 640,  448, 16, 15, "L2"),   # D = 7*64 (TPP 1-2-4 layout)
+        ("lattice_l2_k200", lattice, 700,  64,  24, 200, "L2"),  # k beyond the fused selectors (dense keys + radix select)
+        ("lattice_ip_k300", lattice, 700,  64,  24, 300, "IP"),
     ]
+    only = set(sys.argv[sys.argv.index("--only") + 1:]) if "--only" in sys.argv else None
     for name, gen, N, D, Q, k, itype in search_cases:
+        if only is not None and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
-            cfg = make_cfg(Config, tmp, itype, normalize_for_ip=(name != "lattice_ip" and name != "kat_tiny_ip"))
+            cfg = make_cfg(Config, tmp, itype,
+                           normalize_for_ip=(not name.startswith("lattice_ip") and name != "kat_tiny_ip"))
             xb = gen(N, D, seed=1234)
             xq = gen(Q, D, seed=5678)
             if gen is lattice:
@@ -186,6 +193,9 @@ def main():
                 n_paths=np.int64(len(vdb.vector_paths)),
                 n_meta=np.int64(len(vdb.vector_metadata["speaker_id"])))
             print(f"search_{name}: dist{dist.shape} idx{idx.shape} cosine={vdb._cosine}")
+
+    if only is not None:
+        return
 
     # ---------------- wrapper-behaviour fixtures --------------------------------------
     with tempfile.TemporaryDirectory() as tmp:
