@@ -862,7 +862,10 @@ int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mod
   const bool tier1 = k <= kTier1MaxK && ntiles >= kTcPivotMinTiles && h->t1_level < 2 && !getenv("RDB_NO_TIER1");
   if (!tier1) return split3_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels, true);
   int kc1 = (h->t1_level == 0 && k <= kTier1SmallK) ? 32 : 128;
-  if (const char* e = getenv("RDB_TIER1_KC")) { const int f = atoi(e); if (f == 32 || f == 64 || f == 128) kc1 = std::max(f, k <= kTier1SmallK ? 32 : 128); }
+  if (const char* e = getenv("RDB_TIER1_KC")) {           // A/B knob: force the candidate count (never below what k needs)
+    const int f = atoi(e);
+    if (f == 32 || f == 64 || f == 128) kc1 = (k <= kTier1SmallK) ? f : 128;
+  }
 
   CUDA_TRY(h, h->uncert1.ensure(size_t(nb + 1) * 4));
   int* ucount = h->uncert1.as<int>();
@@ -919,10 +922,10 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   if (nq == 0) return RDB_OK;
   const int D = h->d, Dp = h->dp;
   const bool host = mem == RDB_MEM_HOST;
-  const bool l2 = h->metric == RDB_METRIC_L2;
   const bool sixteen = h->store != RDB_STORE_F32;
-  // scorer selection.  16-bit stores: tcgen05 (1 term).  fp32 stores: split-precision tcgen05 (3 terms) + exact
-  // fp32 re-rank + certificate, exact CUDA-core kernel for whatever cannot be certified (and for small cases).
+  // scorer selection.  16-bit stores: tcgen05 (1 term).  fp32 stores: tiered certified search on tcgen05 (one bf16
+  // term first, then split precision with 3 terms) + exact fp32 re-rank + certificate, exact CUDA-core kernel for
+  // whatever cannot be certified (and for small cases).  k > 128: dense keys + radix select (run_largek).
   const bool tc_ok = sixteen ? (k <= kMaxKTc && h->n >= TC_BN) : (k <= kMaxKSplit && h->n >= TC_BN);
   // small batches are a pure HBM stream of the stored rows: dedicated streaming scorer (exact fp32 for fp32 stores)
   const bool stream_ok = nq <= 4 && k <= 128 && h->n >= 1 && (sixteen || D % 4 == 0);
