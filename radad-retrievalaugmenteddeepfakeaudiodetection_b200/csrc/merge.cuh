@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
 // A single, already sorted list per query (the k > 128 path with one row chunk): nothing to merge -- convert keys to
 // distances, local to global ids and gather the labels, one thread per output slot.  Same output conventions as
 // merge_lists_warp (missing results: id -1, +inf / -inf, label 0, key -inf).
-__global__ void __launch_bounds__(256) finalize_sorted_list_kernel(const float* __restrict__ key_in,
+static __global__ void __launch_bounds__(256) finalize_sorted_list_kernel(const float* __restrict__ key_in,
                                                                    const int* __restrict__ idx_in, int Q, int k,
                                                                    int metric_l2, const float* __restrict__ qnorm,
                                                                    long long id_offset, const float* __restrict__ labels,
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_exact_kernel(const long
 
 // ---- sampled pivot for the large-k tensor-core path (see launch_tc_pivoted in radad_flat.cu) ---------------------------
 // gthr[q] <- ordered(key of rank `rank` of the sample's merged list), 0 (= no bound) when the sample holds fewer rows
-__global__ void gthr_from_pivot_kernel(const float* __restrict__ sample_key, int Q, int kc, int rank,
+static __global__ void gthr_from_pivot_kernel(const float* __restrict__ sample_key, int Q, int kc, int rank,
                                        uint32_t* __restrict__ gthr) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
@@ -321,7 +321,7 @@ __global__ void gthr_from_pivot_kernel(const float* __restrict__ sample_key, int
 }
 // flag <- 1 if any query ended with fewer than min(k, N) neighbours (the pivot was too high for it); gthr <- 0 so the
 // fallback launch starts without any bound
-__global__ void check_complete_kernel(const long long* __restrict__ out_idx, int Q, int k, int need,
+static __global__ void check_complete_kernel(const long long* __restrict__ out_idx, int Q, int k, int need,
                                       uint32_t* __restrict__ gthr, int* __restrict__ flag) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
@@ -331,7 +331,7 @@ __global__ void check_complete_kernel(const long long* __restrict__ out_idx, int
 
 // min |y|^2 over aligned groups of 32 rows: out[g0 + i] for i < ngroups (one warp per group).  Lets the tcgen05
 // epilogue reject a whole 32-column group in the L2 metric with one compare: key_j = 2 s_j - |y_j|^2 <= 2 max(s) - min.
-__global__ void ynorm_min32_kernel(const float* __restrict__ ynorm, long long g0, long long ngroups,
+static __global__ void ynorm_min32_kernel(const float* __restrict__ ynorm, long long g0, long long ngroups,
                                    float* __restrict__ out) {
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= ngroups) return;
@@ -342,7 +342,7 @@ __global__ void ynorm_min32_kernel(const float* __restrict__ ynorm, long long g0
 }
 
 // max over rows of |y|^2 (positive floats order like their bit patterns) -- feeds the re-rank certificate
-__global__ void ynorm_max_kernel(const float* __restrict__ ynorm, long long n, float* __restrict__ out) {
+static __global__ void ynorm_max_kernel(const float* __restrict__ ynorm, long long n, float* __restrict__ out) {
   float m = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     m = fmaxf(m, ynorm[i]);
@@ -352,7 +352,7 @@ __global__ void ynorm_max_kernel(const float* __restrict__ ynorm, long long n, f
 }
 
 // rows list[i] of src [*, D] -> dst [m, D]   (compact the uncertified queries)
-__global__ void gather_f32_rows_kernel(const float* __restrict__ src, const int* __restrict__ list, int m, int D,
+static __global__ void gather_f32_rows_kernel(const float* __restrict__ src, const int* __restrict__ list, int m, int D,
                                        float* __restrict__ dst) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= m) return;
@@ -362,7 +362,7 @@ __global__ void gather_f32_rows_kernel(const float* __restrict__ src, const int*
 }
 
 // scatter rows of the fallback results back to their query slots
-__global__ void scatter_results_kernel(const int* __restrict__ list, int m, int k, const float* __restrict__ s_a,
+static __global__ void scatter_results_kernel(const int* __restrict__ list, int m, int k, const float* __restrict__ s_a,
                                        const long long* __restrict__ s_i, const float* __restrict__ s_l,
                                        float* __restrict__ d_a, long long* __restrict__ d_i,
                                        float* __restrict__ d_l) {
@@ -384,7 +384,7 @@ struct PeerLists {
   const long long* idx[32];
   const float* lbl[32];
 };
-__global__ void __launch_bounds__(128) merge_peer_lists_kernel(const PeerLists P, int G, int Q, int k, int metric_l2,
+static __global__ void __launch_bounds__(128) merge_peer_lists_kernel(const PeerLists P, int G, int Q, int k, int metric_l2,
                                                                const float* __restrict__ qnorm,
                                                                float* __restrict__ out_dist,
                                                                long long* __restrict__ out_idx,
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(128) merge_peer_lists_kernel(const PeerLists P
 //   idx/dist/lbl [B][ks] best-first search results; row_code[ntotal] = int code of each row's file basename;
 //   excl [ne] sorted ascending = codes to skip.  One thread per query walks its ks results in rank order, skips
 //   excluded rows (binary search), keeps the first K; pads with id -1 / label 0 / distance NaN.
-__global__ void filter_first_k_kernel(const long long* __restrict__ idx, const float* __restrict__ dist,
+static __global__ void filter_first_k_kernel(const long long* __restrict__ idx, const float* __restrict__ dist,
                                       const float* __restrict__ lbl, int B, int ks,
                                       const long long* __restrict__ row_code, long long ntotal,
                                       const long long* __restrict__ excl, int ne, int K,
@@ -476,7 +476,7 @@ __global__ void filter_first_k_kernel(const long long* __restrict__ idx, const f
 }
 
 // sum of neighbour labels per query over the first kvote results (the "kNN label vote" evidence)
-__global__ void label_vote_kernel(const float* __restrict__ lbl, int Q, int k, int kvote, float* __restrict__ vote) {
+static __global__ void label_vote_kernel(const float* __restrict__ lbl, int Q, int k, int kvote, float* __restrict__ vote) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
   float s = 0.f;

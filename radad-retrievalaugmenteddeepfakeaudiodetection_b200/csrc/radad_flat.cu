@@ -8,10 +8,7 @@
 //   labels f32 [n]          neighbour labels for the kNN vote
 // Everything a search needs beyond that lives in grow-only scratch owned by the handle, so a steady-state
 // search performs no allocation.
-#include "../../include/radad_flat.h"
-
-#include <cuda.h>
-#include <cuda_runtime.h>
+#include "handle.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -31,110 +28,9 @@
 
 using namespace rdb;
 
-namespace {
-
-thread_local std::string g_err;
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  cudaError_t ensure(size_t need) {
-    if (need <= bytes) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; bytes = 0;
-    size_t want = need + need / 8;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) { cudaGetLastError(); want = need; e = cudaMalloc(&p, want); }
-    if (e == cudaSuccess) bytes = want;
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
-  template <typename T> T* as() { return reinterpret_cast<T*>(p); }
-};
-
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-    else
-      cudaGetLastError();
-  });
-  return fn;
-}
-
-}  // namespace
-
-struct rdb_handle {
-  int d = 0, dp = 0, metric = 0, store = 0, device = 0;
-  unsigned flags = 0;
-  int64_t n = 0, cap = 0, id_offset = 0, nlabels = 0;
-  float* master = nullptr;
-  void* hi = nullptr;
-  void* lo = nullptr;
-  float* ynorm = nullptr;
-  float* ynmin32 = nullptr;       // [cap / 32] min |y|^2 over each aligned group of 32 rows (L2 coarse filter of the tcgen05 epilogue)
-  float* labels = nullptr;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool ev_valid = false;
-  int last_algo = 0, last_S = 0;
-  bool tc_pivoted = false;        // last tensor-core search used the sampled pivot (needs the completeness check)
-  int tc_cg = 1, tc_nqg = 0, tc_S = 0, tc_tpc = 0, tc_ntiles = 0;
-  int num_sms = 148;
-  int64_t launches = 0;
-  std::string err;
-  std::mutex mu;
-  // scratch
-  DevBuf add_stage, q_stage, qf, qhi, qlo, qnorm, cand_key, cand_idx, o_dist, o_idx, o_lbl, ids_stage, rec_stage;
-  DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l, gthr, tcsync, stream_ctl, fkey, fidx;
-  DevBuf uncert1, t2_qf, t2_qhi, t2_qlo, t2_qnorm, t2_a, t2_i, t2_l;   // fp32 stores: tier-1 list + tier-2 sub-batch
-  int t1_level = 0, t1_hold = 0;  // adaptive tier-1 level (exact_split_search) and batches until it decays
-  int last_tier1_kc = 0;
-  int64_t last_tier1_queries = 0, last_tier1_uncertified = 0;
-  DevBuf lk_scores;               // large-k path: dense keys of one (query block x row chunk)
-  void* pin = nullptr;            // pinned host staging of the small-batch path
-  size_t pin_bytes = 0;
-  float* d_ynorm_max = nullptr;   // max |y|^2 over the shard (device scalar; feeds the re-rank certificate)
-  int64_t last_uncertified = 0;
-  bool has_master() const { return store == RDB_STORE_F32 || (flags & RDB_FLAG_KEEP_F32_MASTER); }
-  bool has_hi() const { return true; }
-  bool has_lo() const { return store == RDB_STORE_F32; }
-  bool f16() const { return store == RDB_STORE_F16; }
-};
+namespace rdb { thread_local std::string g_err; }
 
 namespace {
-
-int fail(rdb_handle* h, int code, const std::string& msg) {
-  if (h) h->err = msg;
-  g_err = msg;
-  return code;
-}
-#define CUDA_TRY(h, expr)                                                                              \
-  do {                                                                                                 \
-    cudaError_t e_ = (expr);                                                                           \
-    if (e_ != cudaSuccess) {                                                                           \
-      cudaGetLastError();                                                                              \
-      return fail(h, e_ == cudaErrorMemoryAllocation ? RDB_ERR_NOMEM : RDB_ERR_CUDA,                   \
-                  std::string(#expr) + ": " + cudaGetErrorString(e_));                                 \
-    }                                                                                                  \
-  } while (0)
-
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
-  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
-int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // ---------------------------------------------------------------------------------------------- storage
 int grow_to(rdb_handle* h, int64_t need, bool exact = false) {
@@ -223,45 +119,6 @@ int choose_splits(int64_t nqt, int64_t ntiles, int slots, int max_lists, int min
   return bestS;
 }
 
-// ---------------------------------------------------------------------------------------------- scorers
-template <int KT, bool L2, typename T, bool ALIGNED>
-int launch_simt_t(rdb_handle* h, const T* Q, const T* Y, int nq, int ld, int nqt, int S, int rows_per_chunk,
-                  float* ck, int* ci, int kout) {
-  auto kern = score_select_simt_kernel<KT, L2, T, ALIGNED>;
-  CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt_smem_bytes()));
-  kern<<<dim3(unsigned(nqt) * unsigned(S)), dim3(256), simt_smem_bytes(), h->stream>>>(
-      Q, Y, h->ynorm, nq, int(h->n), h->d, ld, nqt, S, rows_per_chunk, ck, ci, kout, nullptr, 0ll, 0);
-  h->launches++;
-  CUDA_TRY(h, cudaGetLastError());
-  return RDB_OK;
-}
-
-template <int KT, bool L2>
-int launch_simt_k(rdb_handle* h, const float* qf, const void* qhi, int nq, int nqt, int S, int rows_per_chunk,
-                  float* ck, int* ci, int kout) {
-  if (h->store == RDB_STORE_F32) {
-    const float* Q = qf;
-    if (h->d % 4 == 0) return launch_simt_t<KT, L2, float, true>(h, Q, h->master, nq, h->d, nqt, S, rows_per_chunk, ck, ci, kout);
-    return launch_simt_t<KT, L2, float, false>(h, Q, h->master, nq, h->d, nqt, S, rows_per_chunk, ck, ci, kout);
-  }
-  if (h->f16())
-    return launch_simt_t<KT, L2, __half, true>(h, (const __half*)qhi, (const __half*)h->hi, nq, h->dp, nqt, S, rows_per_chunk, ck, ci, kout);
-  return launch_simt_t<KT, L2, __nv_bfloat16, true>(h, (const __nv_bfloat16*)qhi, (const __nv_bfloat16*)h->hi, nq, h->dp, nqt, S, rows_per_chunk, ck, ci, kout);
-}
-
-int launch_simt(rdb_handle* h, const float* qf, const void* qhi, int nq, int k, int nqt, int S, int rows_per_chunk,
-                float* ck, int* ci) {
-  const bool l2 = h->metric == RDB_METRIC_L2;
-#define SIMT_CASE(KT)                                                                          \
-  return l2 ? launch_simt_k<KT, true>(h, qf, qhi, nq, nqt, S, rows_per_chunk, ck, ci, k)       \
-            : launch_simt_k<KT, false>(h, qf, qhi, nq, nqt, S, rows_per_chunk, ck, ci, k)
-  if (k <= 16) { SIMT_CASE(16); }
-  if (k <= 32) { SIMT_CASE(32); }
-  if (k <= 64) { SIMT_CASE(64); }
-  SIMT_CASE(128);
-#undef SIMT_CASE
-}
-
 // tuning knob (profiling only): RDB_TC_HINT_{Q,Y} = first | normal | last
 uint64_t l2_hint_from_env(const char* name, uint64_t dflt) {
   const char* v = getenv(name);
@@ -270,23 +127,6 @@ uint64_t l2_hint_from_env(const char* name, uint64_t dflt) {
   if (!strcmp(v, "last")) return kEvictLast;
   if (!strcmp(v, "normal")) return kEvictNormal;
   return dflt;
-}
-
-constexpr int kReservoirCap = 320;   // large-k epilogue: room for 128 kept + >= 160 appended between prunes
-
-int encode_2d(rdb_handle* h, CUtensorMap* m, const void* base, int64_t rows, int D, int Dp, int box_rows) {
-  PFN_encodeTiled enc = get_encode_fn();
-  if (!enc) return fail(h, RDB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {cuuint64_t(D), cuuint64_t(rows)};
-  cuuint64_t strides[1] = {cuuint64_t(Dp) * 2};
-  cuuint32_t box[2] = {cuuint32_t(TC_BK), cuuint32_t(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, h->f16() ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(h, RDB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
-  return RDB_OK;
 }
 
 // CTAs per MMA group.  Both forms are built and parity-tested: cta_group::1 (one CTA = one 128-query tile, M = 128)
@@ -300,40 +140,6 @@ int tc_cta_group(int nq, int nterms, int d) {
   if (const char* v = getenv("RDB_TC_CG")) { const int f = atoi(v); if (f == 1 || f == 2) return f; }
   if (nterms == 3) return 2;
   return d > TcCfg<1>::ASTAT_MAX_KS * TC_BK ? 2 : 1;
-}
-
-template <class SEL, bool L2V, int CG>
-int launch_tc_kernel(rdb_handle* h, const TcParams& p, int groups) {
-  auto kern = score_select_tc_kernel<SEL, L2V, CG>;
-  CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<CG>()));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(unsigned(groups * CG));
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = tc_smem_bytes<CG>();
-  cfg.stream = h->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CUDA_TRY(h, cudaLaunchKernelEx(&cfg, kern, p));
-  return RDB_OK;
-}
-
-template <int CG>
-int launch_tc_cg(rdb_handle* h, TcParams& p, int k) {
-  int rc;
-  if ((rc = encode_2d(h, &p.tmap_y[0], h->hi, h->n, h->d, h->dp, TC_BN / CG))) return rc;
-  if (p.nterms == 3) { if ((rc = encode_2d(h, &p.tmap_y[1], h->lo, h->n, h->d, h->dp, TC_BN / CG))) return rc; }
-  else p.tmap_y[1] = p.tmap_y[0];
-  p.idesc = make_idesc_f16(TC_BM * CG, TC_BN, h->f16() ? 0 : 1);
-  const int groups = std::min(p.num_units, h->num_sms / CG);
-  const bool l2 = h->metric == RDB_METRIC_L2;
-  if (p.dump)       return l2 ? launch_tc_kernel<SelectDump, true, CG>(h, p, groups) : launch_tc_kernel<SelectDump, false, CG>(h, p, groups);
-  if (k <= 16)      return l2 ? launch_tc_kernel<SelectSmall<16>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<16>, false, CG>(h, p, groups);
-  else if (k <= 32) return l2 ? launch_tc_kernel<SelectSmall<32>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<32>, false, CG>(h, p, groups);
-  return l2 ? launch_tc_kernel<SelectReservoir<kReservoirCap>, true, CG>(h, p, groups)
-            : launch_tc_kernel<SelectReservoir<kReservoirCap>, false, CG>(h, p, groups);
 }
 
 // nqg = query-tile GROUPS (128 * cg queries each); S chunks of tiles_per_chunk 256-row database tiles
@@ -385,7 +191,7 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
       if (const char* v = getenv("RDB_TC_LOCKSTEP_SPINS")) p.sync_spins = atoi(v);
     }
   }
-  rc = (cg == 2) ? launch_tc_cg<2>(h, p, k) : launch_tc_cg<1>(h, p, k);
+  rc = launch_tc_cg(h, p, k, cg);
   if (rc) return rc;
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
@@ -405,53 +211,7 @@ constexpr int kTcSample = 64;          // large-k pivot: every 64th DB tile
 constexpr int kTcPivotRank = 16;       // ... and the sample's 16th best key
 constexpr int kTcPivotMinTiles = 1024; // >= 16 sampled tiles (N >= 262144)
 
-struct QueryView {
-  const float* qf;    // fp32 [nq, D] (fp32 stores)
-  const void* qhi;    // 16-bit [nq, Dp]
-  const void* qlo;    // 16-bit [nq, Dp] (split-precision)
-  const float* qnorm; // [nq]
-  int nq;
-};
-
 // ---- small-batch streaming search (nq <= 4): ONE launch per pass does query prep + stream + final merge
-template <typename T, int NQ, bool L2, int MODE>
-int launch_stream_kernel(rdb_handle* h, const StreamParams& p, int blocks, size_t smem) {
-  auto kern = score_select_stream_kernel<T, NQ, L2, MODE>;
-  CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3(blocks), dim3(STREAM_THREADS), smem, h->stream>>>(p);
-  h->launches++;
-  CUDA_TRY(h, cudaGetLastError());
-  return RDB_OK;
-}
-template <typename T, bool L2>
-int launch_stream_mode(rdb_handle* h, const StreamParams& p, int blocks, int mode) {
-  const int nqt = p.nq <= 1 ? 1 : (p.nq <= 2 ? 2 : 4);
-  const size_t smem = stream_smem_bytes(nqt, p.ld, mode);
-#define STREAM_NQ(MODE)                                                                         \
-  (nqt == 1 ? launch_stream_kernel<T, 1, L2, MODE>(h, p, blocks, smem)                          \
-            : (nqt == 2 ? launch_stream_kernel<T, 2, L2, MODE>(h, p, blocks, smem)              \
-                        : launch_stream_kernel<T, 4, L2, MODE>(h, p, blocks, smem)))
-  if (mode == STREAM_LIST1) return STREAM_NQ(STREAM_LIST1);
-  if (mode == STREAM_LIST4) return STREAM_NQ(STREAM_LIST4);
-  return STREAM_NQ(STREAM_FILTER);
-#undef STREAM_NQ
-}
-int launch_stream(rdb_handle* h, StreamParams& p, int blocks, int mode) {
-  const bool l2 = h->metric == RDB_METRIC_L2;
-  p.metric_l2 = l2 ? 1 : 0;
-  int nvec;
-  if (h->store == RDB_STORE_F32) { p.Y = h->master; p.ld = h->d; nvec = p.ld / 4; }
-  else { p.Y = h->hi; p.ld = h->dp; nvec = p.ld / 8; }
-  // lanes per row: whole warp for long rows, 16 / 8 lanes when a row is only a few 128-bit vectors
-  p.lpr_log2 = nvec >= 96 ? 5 : (nvec >= 48 ? 4 : 3);
-  if (h->store == RDB_STORE_F32)
-    return l2 ? launch_stream_mode<float, true>(h, p, blocks, mode) : launch_stream_mode<float, false>(h, p, blocks, mode);
-  if (h->f16())
-    return l2 ? launch_stream_mode<__half, true>(h, p, blocks, mode) : launch_stream_mode<__half, false>(h, p, blocks, mode);
-  return l2 ? launch_stream_mode<__nv_bfloat16, true>(h, p, blocks, mode)
-            : launch_stream_mode<__nv_bfloat16, false>(h, p, blocks, mode);
-}
-
 
 // FILTER (sampled pivot) needs a sample that is a known fraction of the rows: the pivot pass takes every
 // `sample_mul`-th warp step (each warp must own at least that many steps) and its rank-r key becomes the pivot.
@@ -630,31 +390,6 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
 // ---- large k (128 < k <= 2048): exact fp32 keys of (query block x row chunk) written to HBM by the CUDA-core scorer's
 // DUMP form, exact radix select per query and chunk (select_large.cuh) -> one sorted list per chunk in
 // h->cand_key / h->cand_idx, laid out [nq][S][k] for merge_lists_kernel.  *L_out = S.
-template <bool L2, typename T, bool ALIGNED>
-int launch_simt_dump_t(rdb_handle* h, const T* Q, const T* Y, int nq, int ld, int nqt, int S, int rows_per_chunk,
-                       int row0, int row_end, float* dump, long long pitch) {
-  auto kern = score_select_simt_kernel<16, L2, T, ALIGNED, true>;
-  CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt_smem_bytes()));
-  kern<<<dim3(unsigned(nqt) * unsigned(S)), dim3(256), simt_smem_bytes(), h->stream>>>(
-      Q, Y, h->ynorm, nq, row_end, h->d, ld, nqt, S, rows_per_chunk, nullptr, nullptr, 0, dump, pitch, row0);
-  h->launches++;
-  CUDA_TRY(h, cudaGetLastError());
-  return RDB_OK;
-}
-
-template <bool L2>
-int launch_simt_dump(rdb_handle* h, const QueryView& qv, int q0, int nq, int nqt, int S, int rows_per_chunk, int row0,
-                     int row_end, float* dump, long long pitch) {
-  if (h->store == RDB_STORE_F32) {
-    const float* Q = qv.qf + size_t(q0) * h->d;
-    if (h->d % 4 == 0) return launch_simt_dump_t<L2, float, true>(h, Q, h->master, nq, h->d, nqt, S, rows_per_chunk, row0, row_end, dump, pitch);
-    return launch_simt_dump_t<L2, float, false>(h, Q, h->master, nq, h->d, nqt, S, rows_per_chunk, row0, row_end, dump, pitch);
-  }
-  if (h->f16())
-    return launch_simt_dump_t<L2, __half, true>(h, (const __half*)qv.qhi + size_t(q0) * h->dp, (const __half*)h->hi, nq, h->dp, nqt, S, rows_per_chunk, row0, row_end, dump, pitch);
-  return launch_simt_dump_t<L2, __nv_bfloat16, true>(h, (const __nv_bfloat16*)qv.qhi + size_t(q0) * h->dp, (const __nv_bfloat16*)h->hi, nq, h->dp, nqt, S, rows_per_chunk, row0, row_end, dump, pitch);
-}
-
 int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
   const int64_t N = h->n;
   // 16-bit stores: the keys come from the tensor cores (SelectDump epilogue of kernel 2); fp32 stores need exact fp32
@@ -702,9 +437,7 @@ int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
         int units = std::min(tiles, std::max(1, 8 * h->num_sms / nqt));
         const int tpu = (tiles + units - 1) / units;
         units = (tiles + tpu - 1) / tpu;
-        rc = (h->metric == RDB_METRIC_L2)
-                 ? launch_simt_dump<true>(h, qv, q0, nqs, nqt, units, tpu * SIMT_BN, int(row0), int(row_end), scores, rows)
-                 : launch_simt_dump<false>(h, qv, q0, nqs, nqt, units, tpu * SIMT_BN, int(row0), int(row_end), scores, rows);
+        rc = launch_simt_dump(h, qv, q0, nqs, nqt, units, tpu * SIMT_BN, int(row0), int(row_end), scores, rows);
         if (rc) return rc;
       }
       select_dense_kernel<<<nqs, SELK_THREADS, selk_smem_bytes(), s>>>(scores, rows, len, int(row0), k, S, c, q0,

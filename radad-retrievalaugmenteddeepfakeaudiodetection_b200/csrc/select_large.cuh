@@ -137,7 +137,7 @@ __device__ __forceinline__ int selk_collect(const float* __restrict__ row, int l
 // scores [nq_blk][pitch]: keys (larger is better) of rows row0 .. row0 + len - 1 of the shard, one row per query of
 // this block of queries.  Output: list `chunk` of query (q_first + blockIdx.x) in cand_key / cand_idx laid out
 // [q][S][k]: best-first, local row ids, tail slots (when len < k) = (-inf, -1).   Dynamic smem: selk_smem_bytes().
-__global__ void __launch_bounds__(SELK_THREADS) select_dense_kernel(const float* __restrict__ scores, long long pitch,
+static __global__ void __launch_bounds__(SELK_THREADS) select_dense_kernel(const float* __restrict__ scores, long long pitch,
                                                                     int len, int row0, int k, int S, int chunk,
                                                                     int q_first, int use_sample,
                                                                     float* __restrict__ cand_key,
