@@ -14,9 +14,14 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from . import _cabi
-from ._cabi import (ALGO_AUTO, ALGO_SIMT, ALGO_STREAM, ALGO_TC, FLAG_KEEP_F32_MASTER, MEM_DEVICE, MEM_HOST, METRIC_IP,
-                    METRIC_L2, STORE_BF16, STORE_F16, STORE_F32)
+if __package__:
+    from . import _cabi
+else:           # flat layout: this directory itself is on sys.path, as the reference's `from vector_database import ...`
+    import _cabi
+(ALGO_AUTO, ALGO_SIMT, ALGO_STREAM, ALGO_TC, FLAG_KEEP_F32_MASTER, MEM_DEVICE, MEM_HOST, METRIC_IP, METRIC_L2, STORE_BF16,
+ STORE_F16, STORE_F32) = (_cabi.ALGO_AUTO, _cabi.ALGO_SIMT, _cabi.ALGO_STREAM, _cabi.ALGO_TC, _cabi.FLAG_KEEP_F32_MASTER,
+                          _cabi.MEM_DEVICE, _cabi.MEM_HOST, _cabi.METRIC_IP, _cabi.METRIC_L2, _cabi.STORE_BF16,
+                          _cabi.STORE_F16, _cabi.STORE_F32)
 
 _STORE_BY_NAME = {"f32": STORE_F32, "fp32": STORE_F32, "float32": STORE_F32,
                   "bf16": STORE_BF16, "bfloat16": STORE_BF16,

@@ -26,8 +26,12 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from ._cabi import ALGO_AUTO, METRIC_IP, METRIC_L2
-from .flat_index import FlatIndex, _ReconstructCache, _is_cuda_tensor
+if __package__:
+    from ._cabi import ALGO_AUTO, METRIC_IP, METRIC_L2
+    from .flat_index import FlatIndex, _ReconstructCache, _is_cuda_tensor
+else:           # flat layout (see flat_index.py)
+    from _cabi import ALGO_AUTO, METRIC_IP, METRIC_L2
+    from flat_index import FlatIndex, _ReconstructCache, _is_cuda_tensor
 
 _MIN_SPLIT_ROWS = 4096          # smaller add() calls go whole to the least-loaded shard (fewer segments)
 

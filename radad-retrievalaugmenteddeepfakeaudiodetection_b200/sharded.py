@@ -64,7 +64,10 @@ class ShardedFlatIndex:
     def __init__(self, d: int, metric: int, store="bf16", group=None, device: Optional[int] = None,
                  keep_f32_master: bool = False, exchange: str = "peer"):
         import torch.distributed as dist
-        from .flat_index import FlatIndex
+        if __package__:
+            from .flat_index import FlatIndex
+        else:
+            from flat_index import FlatIndex
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0

@@ -27,10 +27,18 @@ from typing import Dict, List, Tuple
 
 import numpy as np
 
-from . import _cabi
-from .flat_index import FlatIndex, _is_cuda_tensor
-from .multi_gpu import MultiGpuFlatIndex
-from ._cabi import METRIC_IP, METRIC_L2
+if __package__:
+    from . import _cabi
+    from .flat_index import FlatIndex, _is_cuda_tensor
+    from .multi_gpu import MultiGpuFlatIndex
+    from ._cabi import METRIC_IP, METRIC_L2
+else:
+    # Flat layout, exactly how the reference imports this module (`from vector_database import VectorDatabase`,
+    # pipeline.py:11): this directory is on sys.path and there is no parent package.
+    import _cabi
+    from flat_index import FlatIndex, _is_cuda_tensor
+    from multi_gpu import MultiGpuFlatIndex
+    from _cabi import METRIC_IP, METRIC_L2
 
 
 class VectorDatabase:

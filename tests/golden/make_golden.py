@@ -160,7 +160,8 @@ def main():
         ("lattice_l2_k200", lattice, 700,  64,  24, 200, "L2"),  # k beyond the fused selectors (dense keys + radix select)
         ("lattice_ip_k300", lattice, 700,  64,  24, 300, "IP"),
     ]
-    only = set(sys.argv[sys.argv.index("--only") + 1:]) if "--only" in sys.argv else None
+    models_only = "--models-only" in sys.argv      # only (re)write the traced consumer models next to the fixtures
+    only = set(sys.argv[sys.argv.index("--only") + 1:]) if "--only" in sys.argv else (set() if models_only else None)
     for name, gen, N, D, Q, k, itype in search_cases:
         if only is not None and name not in only:
             continue
@@ -194,64 +195,65 @@ def main():
                 n_meta=np.int64(len(vdb.vector_metadata["speaker_id"])))
             print(f"search_{name}: dist{dist.shape} idx{idx.shape} cosine={vdb._cosine}")
 
-    if only is not None:
+    if only is not None and not models_only:
         return
 
-    # ---------------- wrapper-behaviour fixtures --------------------------------------
-    with tempfile.TemporaryDirectory() as tmp:
-        cfg = make_cfg(Config, tmp, "L2")
-        vdb = VectorDatabase(cfg)
-        beh = {}
-        try:
-            vdb.search_batch(np.zeros((1, 8), np.float32))
-        except ValueError as e:
-            beh["empty_search_error"] = str(e)
-        vdb.add_vectors(np.zeros((0, 8), np.float32), [], [], {})
-        beh["index_none_after_empty_add"] = vdb.index is None
-        xb = gaussian(10, 8, 1)
-        # scalar (non-indexable) metadata value is replicated per row (:145)
-        vdb.add_vectors_batch(xb, [f"p{i}" for i in range(10)], list(range(10)),
-                              {"split": 7, "speaker_id": [f"s{i}" for i in range(10)]}, batch_size=4)
-        beh["meta_split"] = vdb.vector_metadata["split"]
-        beh["meta_speaker"] = vdb.vector_metadata["speaker_id"]
-        beh["labels"] = vdb.vector_labels
-        d0, i0 = vdb.search_batch(xb[:2], k=0)     # k=0 -> falsy? no: `k if k is not None` -> 0 -> empty
-        beh["k0_shapes"] = [list(d0.shape), list(i0.shape)]
-        beh["k0_dtypes"] = [str(d0.dtype), str(i0.dtype)]
-        vdb.save()
-        vdb2 = VectorDatabase(cfg)
-        vdb2.load()
-        beh["loaded_ntotal"] = int(vdb2.index.ntotal)
-        beh["loaded_has_cosine_attr"] = hasattr(vdb2, "_cosine")
-        beh["loaded_labels"] = vdb2.vector_labels
-        with open(vdb.metadata_path, "rb") as f:
-            import pickle
-            beh["pickle_keys"] = sorted(pickle.load(f).keys())
-        cfg_bad = make_cfg(Config, tmp, "HNSW")
-        try:
-            VectorDatabase(cfg_bad).create_index(8)
-        except ValueError as e:
-            beh["bad_type_error"] = str(e)
-        import json
-        with open(os.path.join(OUT, "wrapper_behaviour.json"), "w") as f:
-            json.dump(beh, f, indent=1, sort_keys=True)
-        print("wrapper_behaviour:", beh)
+    if not models_only:
+        # ---------------- wrapper-behaviour fixtures --------------------------------------
+        with tempfile.TemporaryDirectory() as tmp:
+            cfg = make_cfg(Config, tmp, "L2")
+            vdb = VectorDatabase(cfg)
+            beh = {}
+            try:
+                vdb.search_batch(np.zeros((1, 8), np.float32))
+            except ValueError as e:
+                beh["empty_search_error"] = str(e)
+            vdb.add_vectors(np.zeros((0, 8), np.float32), [], [], {})
+            beh["index_none_after_empty_add"] = vdb.index is None
+            xb = gaussian(10, 8, 1)
+            # scalar (non-indexable) metadata value is replicated per row (:145)
+            vdb.add_vectors_batch(xb, [f"p{i}" for i in range(10)], list(range(10)),
+                                  {"split": 7, "speaker_id": [f"s{i}" for i in range(10)]}, batch_size=4)
+            beh["meta_split"] = vdb.vector_metadata["split"]
+            beh["meta_speaker"] = vdb.vector_metadata["speaker_id"]
+            beh["labels"] = vdb.vector_labels
+            d0, i0 = vdb.search_batch(xb[:2], k=0)     # k=0 -> falsy? no: `k if k is not None` -> 0 -> empty
+            beh["k0_shapes"] = [list(d0.shape), list(i0.shape)]
+            beh["k0_dtypes"] = [str(d0.dtype), str(i0.dtype)]
+            vdb.save()
+            vdb2 = VectorDatabase(cfg)
+            vdb2.load()
+            beh["loaded_ntotal"] = int(vdb2.index.ntotal)
+            beh["loaded_has_cosine_attr"] = hasattr(vdb2, "_cosine")
+            beh["loaded_labels"] = vdb2.vector_labels
+            with open(vdb.metadata_path, "rb") as f:
+                import pickle
+                beh["pickle_keys"] = sorted(pickle.load(f).keys())
+            cfg_bad = make_cfg(Config, tmp, "HNSW")
+            try:
+                VectorDatabase(cfg_bad).create_index(8)
+            except ValueError as e:
+                beh["bad_type_error"] = str(e)
+            import json
+            with open(os.path.join(OUT, "wrapper_behaviour.json"), "w") as f:
+                json.dump(beh, f, indent=1, sort_keys=True)
+            print("wrapper_behaviour:", beh)
 
-    # cosine-after-load quirk: IP index, queries NOT normalised after load()
-    with tempfile.TemporaryDirectory() as tmp:
-        cfg = make_cfg(Config, tmp, "IP")
-        xb = gaussian(200, 32, 7)
-        xq = gaussian(6, 32, 8) * 3.0
-        vdb = VectorDatabase(cfg)
-        vdb.add_vectors(xb, [f"p{i}" for i in range(200)], [0] * 200, {})
-        d_before, i_before = vdb.search_batch(xq, k=5)
-        vdb.save()
-        vdb2 = VectorDatabase(cfg)
-        vdb2.load()
-        d_after, i_after = vdb2.search_batch(xq, k=5)
-        np.savez_compressed(os.path.join(OUT, "quirk_cosine_after_load.npz"), xb=xb, xq=xq,
-                            d_before=d_before, i_before=i_before, d_after=d_after, i_after=i_after)
-        print("quirk: max |d_after/d_before| =", float(np.abs(d_after / d_before).max()))
+        # cosine-after-load quirk: IP index, queries NOT normalised after load()
+        with tempfile.TemporaryDirectory() as tmp:
+            cfg = make_cfg(Config, tmp, "IP")
+            xb = gaussian(200, 32, 7)
+            xq = gaussian(6, 32, 8) * 3.0
+            vdb = VectorDatabase(cfg)
+            vdb.add_vectors(xb, [f"p{i}" for i in range(200)], [0] * 200, {})
+            d_before, i_before = vdb.search_batch(xq, k=5)
+            vdb.save()
+            vdb2 = VectorDatabase(cfg)
+            vdb2.load()
+            d_after, i_after = vdb2.search_batch(xq, k=5)
+            np.savez_compressed(os.path.join(OUT, "quirk_cosine_after_load.npz"), xb=xb, xq=xq,
+                                d_before=d_before, i_before=i_before, d_after=d_after, i_after=i_after)
+            print("quirk: max |d_after/d_before| =", float(np.abs(d_after / d_before).max()))
 
     # ---------------- caller fixtures: retrieve_similar_vectors + RADADModel -----------
     for name, itype in (("retrieve_l2", "L2"), ("retrieve_cos", "IP")):
@@ -295,6 +297,19 @@ def main():
             with torch.no_grad():
                 logits = model(torch.from_numpy(out["excl_paths_vec"]), torch.from_numpy(q))
             out["logits_excl_paths"] = logits.numpy()
+            # The consumer itself as a fixture: a torch.jit trace of the seeded reference model (a graph of aten ops with
+            # its weights, not source), so the GPU box -- where /root/reference does not exist -- can run the unmodified
+            # RADADModel arithmetic on the neighbours OUR retrieval returns and compare the logits with the ones above.
+            traced = torch.jit.trace(model, (torch.from_numpy(out["excl_paths_vec"]), torch.from_numpy(q)))
+            with torch.no_grad():
+                assert torch.equal(traced(torch.from_numpy(out["excl_paths_vec"]), torch.from_numpy(q)), logits)
+            torch.jit.save(traced, os.path.join(OUT, f"radad_model_{name}.pt"))
+            if "--models-only" in sys.argv:
+                old = np.load(os.path.join(OUT, f"{name}.npz"), allow_pickle=True)
+                assert np.array_equal(old["logits_excl_paths"], out["logits_excl_paths"]), "fixture drifted"
+                assert np.array_equal(old["excl_paths_vec"], out["excl_paths_vec"]), "fixture drifted"
+                print(name, "traced model written; logits equal the committed fixture")
+                continue
             np.savez_compressed(os.path.join(OUT, f"{name}.npz"), xb=xb, q=q,
                                 paths=np.array(paths), qpaths=np.array(qpaths),
                                 labels=np.array([int(l) for l in labels], np.int64),
