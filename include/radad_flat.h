@@ -125,11 +125,13 @@ int rdb_reconstruct_batch(rdb_handle* h, const int64_t* ids, int64_t n, int mem,
 
 /* The caller's rank-ordered self-exclusion + "first K survivors of K+10" compaction -- pipeline.py:491-520 -- on the
  * device.  idx/dist/labels [nq][ks] are search results (device), row_code[ntotal] an integer code per row (the file
- * basename the reference compares), excl_sorted[n_excl] the ascending codes to skip.  Outputs [nq][K]; missing slots
- * get id -1, label 0, distance NaN (the reference's padding).  All pointers are device pointers. */
+ * basename the reference compares), excl_sorted[n_excl] the ascending codes to skip.  `ntotal` is the number of rows of
+ * the WHOLE database (= the length of row_code): ids outside [0, ntotal) are skipped -- with row shards that is the global
+ * row count, not this handle's.  Outputs [nq][K]; missing slots get id -1, label 0, distance NaN (the reference's
+ * padding).  All pointers are device pointers. */
 int rdb_filter_first_k(rdb_handle* h, const int64_t* idx, const float* dist, const float* labels, int64_t nq, int ks,
-                       const int64_t* row_code, const int64_t* excl_sorted, int n_excl, int K, int64_t* out_idx,
-                       float* out_dist, float* out_labels);
+                       const int64_t* row_code, int64_t ntotal, const int64_t* excl_sorted, int n_excl, int K,
+                       int64_t* out_idx, float* out_dist, float* out_labels);
 
 /* Neighbour labels for the kNN label vote: labels float32[n] (host), n must equal ntotal at search time.
  * Mirrors VectorDatabase.vector_labels -- vector_database.py:16,142. */
@@ -154,9 +156,26 @@ int rdb_serialize(rdb_handle* h, const char* path);
 /* Replaces faiss.read_index + faiss.index_cpu_to_gpu -- vector_database.py:230,233. */
 int rdb_deserialize(const char* path, int store_dtype, int device, unsigned flags, rdb_handle** out);
 
-/* Device memory: bytes owned by this index, and free/total of the device (get_gpu_memory_usage --
- * vector_database.py:245-256). */
-int rdb_mem_info(rdb_handle* h, size_t* index_bytes, size_t* free_bytes, size_t* total_bytes);
+/* Device memory: bytes of row storage owned by this index, bytes of its grow-only search scratch (the counterpart of
+ * faiss.StandardGpuResources' temporary memory, vector_database.py:39-45), and free/total of the device
+ * (get_gpu_memory_usage -- vector_database.py:245-256).  h == NULL reports 0 / 0 and the current device. */
+int rdb_mem_info(rdb_handle* h, size_t* index_bytes, size_t* scratch_bytes, size_t* free_bytes, size_t* total_bytes);
+
+/* Free the search scratch (staging buffers, candidate lists, pinned host staging); the index stays searchable and the
+ * scratch regrows on demand.  With rdb_destroy this is what cleanup_gpu_resources (vector_database.py:259-268) maps to. */
+int rdb_release_scratch(rdb_handle* h);
+
+/* Forget the rows beyond the first n_keep (n_keep <= ntotal; storage is kept for re-use).  Used to roll a partially
+ * applied multi-shard add back so that index.add stays all-or-nothing as in faiss (vector_database.py:138,147-149). */
+int rdb_truncate(rdb_handle* h, int64_t n_keep);
+
+/* Per-handle tuning / test options; every default is the production path and the library never reads the process
+ * environment.  Names: "tc_cta_group" (0 auto | 1 | 2), "tc_lockstep" (window in groups of 8 tiles, 0 = off),
+ * "tc_lockstep_spins", "tc_stages", "tc_query_stationary" (0 | 1), "tc_pivot" (0 | 1), "tier1" (0 | 1), "tier1_kc"
+ * (0 auto | 32 | 64 | 128), "largek_scorer" (0 auto | 1 CUDA cores | 2 tensor cores), "largek_rows" (rows per dense key
+ * chunk, 0 = default), "largek_sample" (0 | 1), "largek_split" (0 | 1: split-precision tensor-core keys for fp32 stores).
+ * Unknown names fail with RDB_ERR_INVALID.  No reference counterpart. */
+int rdb_set_option(rdb_handle* h, const char* name, int64_t value);
 
 /* Number of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
 int64_t rdb_launch_count(rdb_handle* h);

@@ -18,7 +18,7 @@ STORE_F32, STORE_BF16, STORE_F16 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_STREAM = 0, 1, 2, 3
 FLAG_KEEP_F32_MASTER = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _fp = POINTER(c_float)
 _ip = POINTER(c_int64)
@@ -49,8 +49,8 @@ SIGNATURES = {
     "rdb_enable_peer_access": (c_int, [_h, c_int]),
     "rdb_reconstruct": (c_int, [_h, c_int64, c_void_p]),
     "rdb_reconstruct_batch": (c_int, [_h, c_void_p, c_int64, c_int, c_void_p]),
-    "rdb_filter_first_k": (c_int, [_h, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int,
-                                   c_void_p, c_void_p, c_void_p]),
+    "rdb_filter_first_k": (c_int, [_h, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int,
+                                   c_int, c_void_p, c_void_p, c_void_p]),
     "rdb_set_labels": (c_int, [_h, c_void_p, c_int64]),
     "rdb_label_vote": (c_int, [_h, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "rdb_ntotal": (c_int64, [_h]),
@@ -60,7 +60,10 @@ SIGNATURES = {
     "rdb_set_id_offset": (c_int, [_h, c_int64]),
     "rdb_serialize": (c_int, [_h, c_char_p]),
     "rdb_deserialize": (c_int, [c_char_p, c_int, c_int, c_uint, POINTER(_h)]),
-    "rdb_mem_info": (c_int, [_h, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]),
+    "rdb_mem_info": (c_int, [_h, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]),
+    "rdb_release_scratch": (c_int, [_h]),
+    "rdb_truncate": (c_int, [_h, c_int64]),
+    "rdb_set_option": (c_int, [_h, c_char_p, c_int64]),
     "rdb_launch_count": (c_int64, [_h]),
     "rdb_last_kernel_ms": (c_int, [_h, POINTER(c_float), POINTER(c_int), POINTER(c_int)]),
     "rdb_last_uncertified": (c_int64, [_h]),

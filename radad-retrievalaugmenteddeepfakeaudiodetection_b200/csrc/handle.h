@@ -34,7 +34,25 @@ struct DevBuf {
 
 }  // namespace rdb
 
+// Per-handle tuning / test options (rdb_set_option); the defaults are the production path.
+struct rdb_options {
+  int tc_cta_group = 0;          // 0 = auto, 1 | 2 = force cta_group
+  int tc_lockstep = 8;           // lock-step window of the TMA producers, in groups of 8 tiles (0 = off)
+  int tc_lockstep_spins = 4096;  // polls before a producer gives lock-step up (~5 ms)
+  int tc_stages = 64;            // ring slots used (clamped to what the kernel has)
+  int tc_query_stationary = 1;   // D <= 256 one-term searches keep the query tile resident
+  int tc_pivot = 1;              // sampled admission bound for 32 < k <= 128
+  int tc_debug = 0;              // RDB_PROFILING builds only: 1 = skip the selection work (results invalid)
+  int tier1 = 1;                 // fp32 stores: one-term certified pass first
+  int tier1_kc = 0;              // 0 = auto, else force 32 | 64 | 128 candidates
+  int largek_scorer = 0;         // 0 = auto, 1 = CUDA-core keys, 2 = tensor-core keys
+  int64_t largek_rows = 0;       // rows per dense key chunk (0 = default 1M)
+  int largek_sample = 1;         // sampled-pivot fast path of the radix select
+  int largek_split = 1;          // fp32 stores: split-precision tensor-core keys + certificate for k > 128
+};
+
 struct rdb_handle {
+  rdb_options opt;
   int d = 0, dp = 0, metric = 0, store = 0, device = 0;
   unsigned flags = 0;
   int64_t n = 0, cap = 0, id_offset = 0, nlabels = 0;
@@ -62,9 +80,12 @@ struct rdb_handle {
   int last_tier1_kc = 0;
   int64_t last_tier1_queries = 0, last_tier1_uncertified = 0;
   rdb::DevBuf lk_scores;          // large-k path: dense keys of one (query block x row chunk)
+  rdb::DevBuf dev_ctl;            // device-side control words of the stream-ordered certified search (counts, flags)
   void* pin = nullptr;            // pinned host staging of the small-batch path
   size_t pin_bytes = 0;
   float* d_ynorm_max = nullptr;   // max |y|^2 over the shard (device scalar; feeds the re-rank certificate)
+  rdb::DevBuf np_tab;             // piece table of numpy's pairwise summation for rows of d floats (ingest.cuh: NpPlan)
+  int np_nleaves = 0, np_nops = 0;
   int64_t last_uncertified = 0;
   bool has_master() const { return store == RDB_STORE_F32 || (flags & RDB_FLAG_KEEP_F32_MASTER); }
   bool has_hi() const { return true; }

@@ -69,6 +69,30 @@ int grow_to(rdb_handle* h, int64_t need, bool exact = false) {
   return RDB_OK;
 }
 
+// numpy's pairwise_sum recursion for a row of n floats (numpy/_core/src/umath/loops_utils.h.src: PW_BLOCKSIZE = 128,
+// left part = n / 2 rounded down to a multiple of 8): leaves in left-to-right order + the post-order fold program.
+int np_plan_rec(int off, int n, std::vector<int>& offs, std::vector<int>& lens, std::vector<int>& ops) {
+  if (n <= 128) { offs.push_back(off); lens.push_back(n); return int(offs.size()) - 1; }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  const int a = np_plan_rec(off, n2, offs, lens, ops);
+  const int b = np_plan_rec(off + n2, n - n2, offs, lens, ops);
+  ops.push_back(a); ops.push_back(b);
+  return a;
+}
+int np_plan_build(rdb_handle* h) {
+  std::vector<int> offs, lens, ops;
+  np_plan_rec(0, h->d, offs, lens, ops);
+  std::vector<int> tab(offs);
+  tab.insert(tab.end(), lens.begin(), lens.end());
+  tab.insert(tab.end(), ops.begin(), ops.end());
+  CUDA_TRY(h, h->np_tab.ensure(tab.size() * 4));
+  CUDA_TRY(h, cudaMemcpy(h->np_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+  h->np_nleaves = int(offs.size()); h->np_nops = int(ops.size() / 2);
+  return RDB_OK;
+}
+NpPlan np_plan(rdb_handle* h) { return NpPlan{h->np_tab.as<int>(), h->np_nleaves, h->np_nops}; }
+
 // launch the fused ingest kernel (also used to prepare queries)
 int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int norm_of_hi, float* master, void* hi,
                   void* lo, float* norm2) {
@@ -81,8 +105,17 @@ int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int n
   cudaStream_t s = h->stream;
   // rows of up to 1024 floats are held in registers (one read, NC independent 128-bit loads per lane)
   const int nc = !vec4 ? 0 : (Dp <= 256 ? 2 : (Dp <= 512 ? 4 : (Dp <= 1024 ? 8 : 0)));
-#define INGEST_LAUNCH(T16, V4, NC) \
-  ingest_rows_kernel<T16, V4, NC><<<grid, block, 0, s>>>(x, n, D, Dp, normalize, norm_of_hi, master, (T16*)hi, (T16*)lo, norm2)
+  // normalising launches stage the row's squares / leaf sums of numpy's summation order in shared memory (ingest.cuh)
+  const size_t smem = normalize ? size_t(warps_per_block) * ingest_warp_floats(h->np_nleaves, D, nc > 0) * 4 : 0;
+  if (smem > 200 * 1024) return fail(h, RDB_ERR_UNSUPPORTED, "normalisation of rows this long is not supported");
+  const NpPlan np = np_plan(h);
+#define INGEST_LAUNCH(T16, V4, NC)                                                                                        \
+  do {                                                                                                                    \
+    if (smem > 48 * 1024)                                                                                                 \
+      CUDA_TRY(h, cudaFuncSetAttribute(ingest_rows_kernel<T16, V4, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
+    ingest_rows_kernel<T16, V4, NC><<<grid, block, smem, s>>>(x, n, D, Dp, normalize, norm_of_hi, master, (T16*)hi,       \
+                                                              (T16*)lo, norm2, np);                                       \
+  } while (0)
 #define INGEST_T(T16)                                                                                     \
   do {                                                                                                    \
     if (nc == 2) INGEST_LAUNCH(T16, true, 2); else if (nc == 4) INGEST_LAUNCH(T16, true, 4);              \
@@ -119,25 +152,15 @@ int choose_splits(int64_t nqt, int64_t ntiles, int slots, int max_lists, int min
   return bestS;
 }
 
-// tuning knob (profiling only): RDB_TC_HINT_{Q,Y} = first | normal | last
-uint64_t l2_hint_from_env(const char* name, uint64_t dflt) {
-  const char* v = getenv(name);
-  if (!v) return dflt;
-  if (!strcmp(v, "first")) return kEvictFirst;
-  if (!strcmp(v, "last")) return kEvictLast;
-  if (!strcmp(v, "normal")) return kEvictNormal;
-  return dflt;
-}
-
 // CTAs per MMA group.  Both forms are built and parity-tested: cta_group::1 (one CTA = one 128-query tile, M = 128)
 // and cta_group::2 (a CTA pair runs M = 256 MMAs, each SM staging half of the database tile: a third less L2->SM
 // operand traffic, 6-deep ring).  Interleaved A/Bs on B200 (profiles/r01_session2_notes.md): with the lock-step
 // window holding the wave together the pair form is 2-3.5 % faster for D = 768 one-term searches (C3: 1421-1442 vs
 // 1385-1393 TFLOP/s) and ~10 % faster for the three-term split-precision search (C2); the query-stationary form
-// (D <= 256) already stages database slices only and is faster as a single CTA.  RDB_TC_CG=1|2 overrides.
-int tc_cta_group(int nq, int nterms, int d) {
+// (D <= 256) already stages database slices only and is faster as a single CTA.  Option "tc_cta_group" overrides.
+int tc_cta_group(const rdb_handle* h, int nq, int nterms, int d) {
   if (nq <= TC_BM) return 1;
-  if (const char* v = getenv("RDB_TC_CG")) { const int f = atoi(v); if (f == 1 || f == 2) return f; }
+  if (h->opt.tc_cta_group == 1 || h->opt.tc_cta_group == 2) return h->opt.tc_cta_group;
   if (nterms == 3) return 2;
   return d > TcCfg<1>::ASTAT_MAX_KS * TC_BK ? 2 : 1;
 }
@@ -157,24 +180,24 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
   CUDA_TRY(h, h->gthr.ensure(size_t(nq) * 4));
   if (!keep_gthr) CUDA_TRY(h, cudaMemsetAsync(h->gthr.p, 0, size_t(nq) * 4, h->stream));
   p.tile_step = tile_step; p.run_if = run_if;
-  p.nstages = 64;
-  if (const char* v = getenv("RDB_TC_STAGES")) p.nstages = std::max(2, atoi(v));
-  p.astat = (nterms == 1 && h->d <= TcCfg<1>::ASTAT_MAX_KS * TC_BK && !getenv("RDB_TC_NO_ASTAT")) ? 1 : 0;
+  p.nstages = std::max(2, h->opt.tc_stages);
+  p.astat = (nterms == 1 && h->d <= TcCfg<1>::ASTAT_MAX_KS * TC_BK && h->opt.tc_query_stationary) ? 1 : 0;
   p.gthr = (S > 1 || TC_LISTS > 1) ? h->gthr.as<uint32_t>() : nullptr;
   p.nq = nq; p.N = int(h->n); p.D = h->d;
   if (dump) { p.dump = dump; p.dump_pitch = dump_pitch; p.row_base = row_base; p.N = row_end; }   // k > 128: rows [row_base, row_end)
   p.nqt = nqg; p.S = S; p.tiles_per_chunk = tiles_per_chunk; p.ntiles = ntiles; p.kout = k;
   p.num_units = nqg * S; p.nterms = nterms;
-  { const char* v = getenv("RDB_TC_DEBUG"); p.dbg = v ? atoi(v) : 0; }
-  p.hint_q = l2_hint_from_env("RDB_TC_HINT_Q", kEvictLast);     // queries: re-read for every DB tile -> keep
-  p.hint_y = l2_hint_from_env("RDB_TC_HINT_Y", kEvictNormal);   // database tiles: shared by the CTAs of a wave
+#ifdef RDB_PROFILING
+  p.dbg = h->opt.tc_debug;      // profiling builds only: skips the selection work, results invalid
+#endif
+  p.hint_q = kEvictLast;        // queries: re-read for every DB tile -> keep
+  p.hint_y = kEvictNormal;      // database tiles: shared by the CTAs of a wave
   // lock-step window of the TMA producers (score_tc.cuh): on when there is more than one wave of units, at least a
-  // quarter of a wave shares each chunk, and units are long enough to drift; RDB_TC_LOCKSTEP=<window in groups of 8
-  // tiles> (0 = off) overrides.
+  // quarter of a wave shares each chunk, and units are long enough to drift; option "tc_lockstep" = window in groups
+  // of 8 tiles (0 = off).
   {
     const int ngroups = std::min(p.num_units, h->num_sms / cg);
-    int window = 8;
-    if (const char* v = getenv("RDB_TC_LOCKSTEP")) window = atoi(v);
+    const int window = h->opt.tc_lockstep;
     const int sync_groups = (tiles_per_chunk + TC_SYNC_GS - 1) / TC_SYNC_GS;
     const int span = (ngroups + nqg - 1) / nqg + 1;                        // chunks one slot of ngroups units can touch
     // (measured: +6 % at C3, +4 % at the C5 shard, -4 % for the three-term split search -> one-term searches only)
@@ -187,8 +210,7 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
       p.sync = h->tcsync.as<uint32_t>(); p.sync_groups = sync_groups; p.sync_window = window;
       p.sync_span = span;
       p.sync_broken = p.sync + slots * span * size_t(sync_groups);
-      p.sync_spins = 4096;                                                // ~5 ms of patience
-      if (const char* v = getenv("RDB_TC_LOCKSTEP_SPINS")) p.sync_spins = atoi(v);
+      p.sync_spins = h->opt.tc_lockstep_spins;                            // default 4096: ~5 ms of patience
     }
   }
   rc = launch_tc_cg(h, p, k, cg);
@@ -284,7 +306,7 @@ int search_stream(rdb_handle* h, const float* q, int nq, int k, int mem, int nor
   StreamParams p;
   memset(&p, 0, sizeof(p));
   p.ynorm = h->ynorm; p.N = int(h->n);
-  p.q_raw = qsrc; p.nq = nq; p.D = D; p.normalize = normalize;
+  p.q_raw = qsrc; p.nq = nq; p.D = D; p.normalize = normalize; p.np = np_plan(h);
   p.rows_per_block = rpb; p.kout = k; p.step_mul = 1;
   p.cand_key = h->cand_key.as<float>(); p.cand_idx = h->cand_idx.as<int>();
   p.ctl = h->stream_ctl.as<StreamCtl>();
@@ -329,7 +351,7 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
   cudaStream_t s = h->stream;
   if (algo == RDB_ALGO_TC) {
     const int ntiles = int((h->n + TC_BN - 1) / TC_BN);
-    const int cg = tc_cta_group(qv.nq, nterms, h->d);
+    const int cg = tc_cta_group(h, qv.nq, nterms, h->d);
     const int nqg = (qv.nq + TC_BM * cg - 1) / (TC_BM * cg);
     // large k: per-unit selection overhead (reservoir warm-up, final sort) is worth ~64 tiles -> fewer, longer units.
     // The minimum unit length is expressed in tiles of the C3 shape (12 K-slices, one term): long rows / three terms
@@ -342,7 +364,7 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
     CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * TC_LISTS * kc * 4));
     CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * TC_LISTS * kc * 4));
     if (timed) cudaEventRecord(h->ev0, s);
-    const bool pivoted = kc > 32 && nterms == 1 && ntiles >= kTcPivotMinTiles && !getenv("RDB_TC_NO_PIVOT");
+    const bool pivoted = kc > 32 && nterms == 1 && ntiles >= kTcPivotMinTiles && h->opt.tc_pivot;
     if (pivoted) {
       // Large k: seed every query's admission bound from a strided 1/64 sample of the DB tiles (rank-16 key of the
       // sample: ~1000 rows of the shard beat it), so the reservoirs admit ~1000 rows per query in total instead of
@@ -393,15 +415,13 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
 int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
   const int64_t N = h->n;
   // 16-bit stores: the keys come from the tensor cores (SelectDump epilogue of kernel 2); fp32 stores need exact fp32
-  // keys -> CUDA-core scorer.  RDB_LARGEK_SCORER=simt|tc overrides (tests).
+  // keys -> CUDA-core scorer.  Option "largek_scorer" = 1 (CUDA cores) | 2 (tensor cores) overrides (tests).
   bool use_tc = h->store != RDB_STORE_F32 && N >= kMinRowsTc;
-  if (const char* e = getenv("RDB_LARGEK_SCORER")) {
-    if (!strcmp(e, "simt")) use_tc = false;
-    else if (!strcmp(e, "tc") && h->store != RDB_STORE_F32 && N >= TC_BN) use_tc = true;
-  }
+  if (h->opt.largek_scorer == 1) use_tc = false;
+  else if (h->opt.largek_scorer == 2 && h->store != RDB_STORE_F32 && N >= TC_BN) use_tc = true;
   const int64_t align = use_tc ? TC_BN : SIMT_BN;
   int64_t rows = kLargeKRowsDefault;
-  if (const char* e = getenv("RDB_LARGEK_ROWS")) rows = std::max<int64_t>(1, atoll(e));   // tests: force several chunks
+  if (h->opt.largek_rows > 0) rows = h->opt.largek_rows;       // tests: force several chunks
   rows = std::max<int64_t>(rows, (N + 255) / 256);          // merge_lists_kernel folds at most 256 lists
   rows = round_up(rows, align);
   rows = std::min<int64_t>(rows, round_up(N, align));
@@ -414,7 +434,7 @@ int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
   cudaStream_t s = h->stream;
   CUDA_TRY(h, cudaFuncSetAttribute(select_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)selk_smem_bytes()));
-  const int use_sample = getenv("RDB_LARGEK_NO_SAMPLE") ? 0 : 1;      // sampled-pivot fast path of the select (A/B knob)
+  const int use_sample = h->opt.largek_sample ? 1 : 0;      // sampled-pivot fast path of the select (A/B option)
   cudaEventRecord(h->ev0, s);
   int rc;
   for (int q0 = 0; q0 < qv.nq; q0 += kLargeKQueryBlock) {
@@ -424,7 +444,7 @@ int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
       const int64_t row0 = int64_t(c) * rows, row_end = std::min<int64_t>(N, row0 + rows);
       const int len = int(row_end - row0);
       if (use_tc) {
-        const int cg = tc_cta_group(nqs, 1, h->d);
+        const int cg = tc_cta_group(h, nqs, 1, h->d);
         const int nqg = (nqs + TC_BM * cg - 1) / (TC_BM * cg);
         const int tiles = (len + TC_BN - 1) / TC_BN;
         int tpc;
@@ -592,13 +612,11 @@ int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mod
   // the failures costs more than the larger epilogue), 2 = no tier 1 (more than half failed with 128).  A raised level
   // decays by one after kTier1Hold batches, so a change of the data is picked up again.
   if (h->t1_hold > 0 && --h->t1_hold == 0 && h->t1_level > 0) { h->t1_level--; h->t1_hold = h->t1_level > 0 ? kTier1Hold : 0; }
-  const bool tier1 = k <= kTier1MaxK && ntiles >= kTcPivotMinTiles && h->t1_level < 2 && !getenv("RDB_NO_TIER1");
+  const bool tier1 = k <= kTier1MaxK && ntiles >= kTcPivotMinTiles && h->t1_level < 2 && h->opt.tier1;
   if (!tier1) return split3_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels, true);
   int kc1 = (h->t1_level == 0 && k <= kTier1SmallK) ? 32 : 128;
-  if (const char* e = getenv("RDB_TIER1_KC")) {           // A/B knob: force the candidate count (never below what k needs)
-    const int f = atoi(e);
+  if (const int f = h->opt.tier1_kc)                      // A/B option: force the candidate count (never below what k needs)
     if (f == 32 || f == 64 || f == 128) kc1 = (k <= kTier1SmallK) ? f : 128;
-  }
 
   CUDA_TRY(h, h->uncert1.ensure(size_t(nb + 1) * 4));
   int* ucount = h->uncert1.as<int>();
@@ -753,12 +771,24 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   return RDB_OK;
 }
 
+// every grow-only search scratch buffer of a handle (released by rdb_release_scratch / rdb_destroy, counted by rdb_mem_info)
+using DevBufMember = DevBuf rdb_handle::*;
+const DevBufMember kScratch[] = {
+    &rdb_handle::add_stage, &rdb_handle::q_stage, &rdb_handle::qf, &rdb_handle::qhi, &rdb_handle::qlo, &rdb_handle::qnorm,
+    &rdb_handle::cand_key, &rdb_handle::cand_idx, &rdb_handle::o_dist, &rdb_handle::o_idx, &rdb_handle::o_lbl,
+    &rdb_handle::ids_stage, &rdb_handle::rec_stage, &rdb_handle::rr_key, &rdb_handle::rr_idx, &rdb_handle::rr_key2,
+    &rdb_handle::rr_idx2, &rdb_handle::uncert, &rdb_handle::fb_qf, &rdb_handle::fb_qnorm, &rdb_handle::fb_a,
+    &rdb_handle::fb_i, &rdb_handle::fb_l, &rdb_handle::gthr, &rdb_handle::tcsync, &rdb_handle::stream_ctl,
+    &rdb_handle::fkey, &rdb_handle::fidx, &rdb_handle::lk_scores, &rdb_handle::uncert1, &rdb_handle::t2_qf,
+    &rdb_handle::t2_qhi, &rdb_handle::t2_qlo, &rdb_handle::t2_qnorm, &rdb_handle::t2_a, &rdb_handle::t2_i,
+    &rdb_handle::t2_l, &rdb_handle::dev_ctl};
+
 }  // namespace
 
 // ================================================================================================ C ABI
 extern "C" {
 
-int rdb_abi_version(void) { return 1; }
+int rdb_abi_version(void) { return 2; }
 
 const char* rdb_last_error(rdb_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
 
@@ -794,6 +824,7 @@ int rdb_create(int d, int metric, int store_dtype, int device, unsigned flags, r
     rdb_destroy(h);
     return fail(nullptr, RDB_ERR_NOMEM, "rdb_create: device allocation failed");
   }
+  if (np_plan_build(h) != RDB_OK) { rdb_destroy(h); return fail(nullptr, RDB_ERR_NOMEM, "rdb_create: device allocation failed"); }
   *out = h;
   return RDB_OK;
 }
@@ -805,11 +836,8 @@ int rdb_destroy(rdb_handle* h) {
     cudaStreamSynchronize(h->stream);
     cudaFree(h->master); cudaFree(h->hi); cudaFree(h->lo); cudaFree(h->ynorm); cudaFree(h->ynmin32); cudaFree(h->labels);
     cudaFree(h->d_ynorm_max);
-    for (DevBuf* b : {&h->add_stage, &h->q_stage, &h->qf, &h->qhi, &h->qlo, &h->qnorm, &h->cand_key, &h->cand_idx,
-                      &h->o_dist, &h->o_idx, &h->o_lbl, &h->ids_stage, &h->rec_stage, &h->rr_key, &h->rr_idx,
-                      &h->rr_key2, &h->rr_idx2, &h->uncert, &h->fb_qf, &h->fb_qnorm, &h->fb_a, &h->fb_i, &h->fb_l, &h->gthr, &h->tcsync, &h->stream_ctl, &h->fkey, &h->fidx, &h->lk_scores,
-                      &h->uncert1, &h->t2_qf, &h->t2_qhi, &h->t2_qlo, &h->t2_qnorm, &h->t2_a, &h->t2_i, &h->t2_l})
-      b->release();
+    for (auto m : kScratch) (h->*m).release();
+    h->np_tab.release();
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1048,18 +1076,18 @@ int rdb_set_labels(rdb_handle* h, const float* labels, int64_t n) {
 }
 
 int rdb_filter_first_k(rdb_handle* h, const int64_t* idx, const float* dist, const float* labels, int64_t nq, int ks,
-                       const int64_t* row_code, const int64_t* excl_sorted, int n_excl, int K, int64_t* out_idx,
-                       float* out_dist, float* out_labels) {
+                       const int64_t* row_code, int64_t ntotal, const int64_t* excl_sorted, int n_excl, int K,
+                       int64_t* out_idx, float* out_dist, float* out_labels) {
   if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
   std::lock_guard<std::mutex> lock(h->mu);
   DeviceGuard dg(h->device);
-  if (nq < 0 || ks < 0 || K < 1 || !out_idx || !out_dist || !out_labels || (ks > 0 && (!idx || !dist)) ||
+  if (nq < 0 || ks < 0 || K < 1 || ntotal < 0 || !out_idx || !out_dist || !out_labels || (ks > 0 && (!idx || !dist)) ||
       (n_excl > 0 && (!row_code || !excl_sorted)))
     return fail(h, RDB_ERR_INVALID, "filter_first_k: bad arguments");
   if (nq == 0) return RDB_OK;
   filter_first_k_kernel<<<unsigned((nq + 127) / 128), 128, 0, h->stream>>>(
       reinterpret_cast<const long long*>(idx), dist, labels, int(nq), ks, reinterpret_cast<const long long*>(row_code),
-      h->n + h->id_offset, reinterpret_cast<const long long*>(excl_sorted), n_excl, K,
+      (long long)ntotal, reinterpret_cast<const long long*>(excl_sorted), n_excl, K,
       reinterpret_cast<long long*>(out_idx), out_dist, out_labels);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
@@ -1124,18 +1152,79 @@ int rdb_last_tier1(rdb_handle* h, int64_t* queries, int64_t* uncertified, int* c
   return RDB_OK;
 }
 
-int rdb_mem_info(rdb_handle* h, size_t* index_bytes, size_t* free_bytes, size_t* total_bytes) {
-  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
-  DeviceGuard dg(h->device);
-  size_t fr = 0, tot = 0;
-  CUDA_TRY(h, cudaMemGetInfo(&fr, &tot));
-  size_t ib = 0;
-  if (h->has_master()) ib += size_t(h->cap) * h->d * 4;
-  ib += size_t(h->cap) * h->dp * 2 * (h->has_lo() ? 2 : 1);
-  ib += size_t(h->cap) * 4 + size_t(h->nlabels) * 4;
+int rdb_mem_info(rdb_handle* h, size_t* index_bytes, size_t* scratch_bytes, size_t* free_bytes, size_t* total_bytes) {
+  size_t fr = 0, tot = 0, ib = 0, sb = 0;
+  if (h) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard dg(h->device);
+    CUDA_TRY(h, cudaMemGetInfo(&fr, &tot));
+    if (h->has_master()) ib += size_t(h->cap) * h->d * 4;
+    ib += size_t(h->cap) * h->dp * 2 * (h->has_lo() ? 2 : 1);
+    ib += size_t(h->cap) * 4 + size_t(h->cap / 32) * 4 + size_t(h->nlabels) * 4;
+    for (auto m : kScratch) sb += (h->*m).bytes;
+    sb += h->pin_bytes;
+  } else {
+    CUDA_TRY(nullptr, cudaMemGetInfo(&fr, &tot));
+  }
   if (index_bytes) *index_bytes = ib;
+  if (scratch_bytes) *scratch_bytes = sb;
   if (free_bytes) *free_bytes = fr;
   if (total_bytes) *total_bytes = tot;
+  return RDB_OK;
+}
+
+int rdb_release_scratch(rdb_handle* h) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (auto m : kScratch) (h->*m).release();
+  if (h->pin) cudaFreeHost(h->pin);
+  h->pin = nullptr; h->pin_bytes = 0;
+  h->ev_valid = false;
+  cudaGetLastError();
+  return RDB_OK;
+}
+
+int rdb_truncate(rdb_handle* h, int64_t n_keep) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  if (n_keep < 0 || n_keep > h->n) return fail(h, RDB_ERR_INVALID, "truncate: n_keep must be in [0, ntotal]");
+  if (n_keep == h->n) return RDB_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  // forgotten rows must look like never-filled ones: |y|^2 = 0 keeps the group minima a valid (loose) lower bound
+  CUDA_TRY(h, cudaMemsetAsync(h->ynorm + n_keep, 0, size_t(h->n - n_keep) * 4, h->stream));
+  const int64_t g0 = n_keep / 32, g1 = (h->n - 1) / 32;
+  ynorm_min32_kernel<<<unsigned((g1 - g0 + 1 + 7) / 8), 256, 0, h->stream>>>(h->ynorm, g0, g1 - g0 + 1, h->ynmin32);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->n = n_keep;                       // labels (if any) no longer match ntotal -> ignored until set again
+  return RDB_OK;
+}
+
+int rdb_set_option(rdb_handle* h, const char* name, int64_t value) {
+  if (!h || !name) return fail(h, RDB_ERR_INVALID, "set_option: bad arguments");
+  std::lock_guard<std::mutex> lock(h->mu);
+  const std::string n(name);
+  rdb_options& o = h->opt;
+  if (n == "tc_cta_group") o.tc_cta_group = int(value);
+  else if (n == "tc_lockstep") o.tc_lockstep = int(value);
+  else if (n == "tc_lockstep_spins") o.tc_lockstep_spins = int(value);
+  else if (n == "tc_stages") o.tc_stages = int(value);
+  else if (n == "tc_query_stationary") o.tc_query_stationary = int(value);
+  else if (n == "tc_pivot") o.tc_pivot = int(value);
+  else if (n == "tier1") o.tier1 = int(value);
+  else if (n == "tier1_kc") o.tier1_kc = int(value);
+  else if (n == "largek_scorer") o.largek_scorer = int(value);
+  else if (n == "largek_rows") o.largek_rows = value;
+  else if (n == "largek_sample") o.largek_sample = int(value);
+  else if (n == "largek_split") o.largek_split = int(value);
+#ifdef RDB_PROFILING
+  else if (n == "tc_debug") o.tc_debug = int(value);
+#endif
+  else return fail(h, RDB_ERR_INVALID, "set_option: unknown option '" + n + "'");
   return RDB_OK;
 }
 

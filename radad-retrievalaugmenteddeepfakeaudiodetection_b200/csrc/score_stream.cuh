@@ -118,6 +118,7 @@ struct StreamCtl {                      // device control block owned by the han
 struct StreamParams {
   const void* Y; int ld; const float* ynorm; int N;       // stored rows [N, ld] (T), |y|^2
   const float* q_raw; int nq, D, normalize;               // raw fp32 queries [nq, D] (device)
+  NpPlan np;                                              // numpy summation order of the row norm (ingest.cuh)
   int rows_per_block, kout, lpr_log2, step_mul;           // step_mul > 1: strided sample pass
   float* cand_key; int* cand_idx;                         // LIST: block lists [nq][gridDim.x][kout]
   float* fkey; int* fidx;                                 // FILTER: candidates [nq][STREAM_FCAP]
@@ -136,23 +137,10 @@ template <> __device__ __forceinline__ float from16<float>(float v) { return v; 
 // squares of the STORED values.  dst is fp32 [ld], pad columns [D, ld) zero.
 template <typename T>
 __device__ __forceinline__ float stream_prep_query(const float* __restrict__ xr, int D, int ld, int normalize,
-                                                   float* __restrict__ dst, int lane) {
+                                                   float* __restrict__ dst, int lane, const NpPlan& np, float* lv) {
   const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(xr) & 15) == 0);
   float denom = 1.0f;
-  if (normalize) {
-    float s = 0.f;
-    if (vec4) {
-      const float4* x4 = reinterpret_cast<const float4*>(xr);
-      for (int c = lane; c < (D >> 2); c += 32) {
-        const float4 v = x4[c];
-        s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
-      }
-    } else {
-      for (int c = lane; c < D; c += 32) { const float v = xr[c]; s = fmaf(v, v, s); }
-    }
-    s = warp_sum(s);
-    denom = sqrtf(s) + 1e-12f;
-  }
+  if (normalize) denom = __fsqrt_rn(np_sumsq_global(xr, np, lv, lane)) + 1e-12f;   // numpy order: see NpPlan
   float acc = 0.f;
   if (vec4) {
     const float4* x4 = reinterpret_cast<const float4*>(xr);
@@ -199,7 +187,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
   // ---- query prep (every block, redundantly: nq * D elements)
   if (warp < NQ) {
     if (warp < nq) {
-      const float n2 = stream_prep_query<T>(p.q_raw + (long long)warp * p.D, p.D, ld, p.normalize, qs + warp * ld, lane);
+      const float n2 = stream_prep_query<T>(p.q_raw + (long long)warp * p.D, p.D, ld, p.normalize, qs + warp * ld, lane, p.np,
+                                               sm + NQ * ld + warp * p.np.nleaves);
       if (lane == 0) {
         s_qnorm[warp] = n2;
         if (MODE == STREAM_FILTER) s_pivot[warp] = __ldcg(&p.ctl->pivot[warp]);
@@ -434,8 +423,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
   if (threadIdx.x == 0) p.ctl->ticket = 0;
 }
 
-constexpr size_t stream_smem_bytes(int nq_t, int ld, int mode) {
-  const size_t a = size_t(nq_t) * ld * 4;
+constexpr size_t stream_smem_bytes(int nq_t, int ld, int mode, int np_leaves) {
+  const size_t a = size_t(nq_t) * ld * 4 + size_t(nq_t) * np_leaves * 4;   // queries + leaf sums of the norm
   const size_t b = (mode == STREAM_FILTER) ? size_t(STREAM_FCAP) * 8
                                            : size_t(nq_t) * STREAM_WARPS * 32 * (mode == STREAM_LIST4 ? 4 : 1) * 8;
   return a > b ? a : b;

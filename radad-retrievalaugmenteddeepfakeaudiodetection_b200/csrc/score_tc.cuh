@@ -67,14 +67,14 @@ struct TcParams {
   int nq, N, D;
   int nqt /* query-tile groups of 128 * CG queries */, S, tiles_per_chunk, ntiles, kout, num_units, nterms;
   uint32_t idesc;
-  int dbg;                  // profiling only (RDB_TC_DEBUG): 1 = skip the selection work (results invalid)
+  int dbg;                  // RDB_PROFILING builds only (option "tc_debug"): 1 = skip the selection work (results invalid)
   uint64_t hint_q, hint_y;  // TMA L2 eviction-priority hints for the query / database operand
   // Lock-step window (see below): progress counters [slot][sync_span][sync_groups], or null = off
   uint32_t* sync;
   int sync_groups, sync_window, sync_span, sync_spins;   // sync_span: chunks one slot can touch;   // sync_spins: polls (~1 us each) before a producer gives lock-step up
   uint32_t* sync_broken;    // set by the first producer that gives up: nobody waits any more in this launch
   int tile_step;            // 1 = every DB tile; > 1: strided sample pass (tile index t stands for tile t * tile_step)
-  int nstages;              // ring slots used (<= TcCfg::STAGES; profiling knob RDB_TC_STAGES)
+  int nstages;              // ring slots used (<= TcCfg::STAGES; option "tc_stages")
   int astat;                // query-stationary form (host: nterms == 1 && D <= 256)
   const int* run_if;        // fallback launch: all CTAs exit at once unless *run_if != 0 (null = always run)
   // k > 128 path (SelectDump): the launch covers rows [row_base, N) only (row_base a multiple of 256; tile t stands
@@ -433,7 +433,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
         const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * TC_BN + half * (TC_BN / 2));
         const int n0 = p.row_base + t * p.tile_step * TC_BN + half * (TC_BN / 2);
         const int nvalid = p.N - n0;         // >= 128 for full tiles
-        if (p.dbg & 1) {
+#ifdef RDB_PROFILING
+        if (p.dbg & 1) {      // bare main loop (selection skipped, results invalid): profiling builds only
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
@@ -441,6 +442,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
           if (acc == 0) acc_phase ^= 1;
           continue;
         }
+#endif
         uint32_t ra[32], rb[32];
         // L2: minima of |y|^2 over this half-tile's four 32-row groups (one 128-bit load; n0 is a multiple of 128)
         float ymin[4] = {0.f, 0.f, 0.f, 0.f};

@@ -10,6 +10,8 @@ torch CUDA tensors on the device-resident fast path (no host round trip).
 from __future__ import annotations
 
 import ctypes
+import functools
+import threading
 from typing import Optional, Tuple
 
 import numpy as np
@@ -32,6 +34,17 @@ ALGO_BY_NAME = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tc": ALGO_TC, "stream": A
 
 def _is_cuda_tensor(x) -> bool:
     return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+def _locked(fn):
+    """Selecting the stream (caller's torch stream vs the handle's own) and the C call that uses it must be one atomic
+    step: two Python threads sharing an index (Flask's `predict`, app.py:351) could otherwise flip the stream between the
+    other thread's selection and its launch.  ctypes releases the GIL inside the C call, so waiters do not spin."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        with self._lock:
+            return fn(self, *a, **kw)
+    return wrapper
 
 
 class _ReconstructCache:
@@ -73,8 +86,10 @@ class FlatIndex(_ReconstructCache):
                  keep_f32_master: bool = False, _handle=None):
         self._lib = _cabi.load()
         self._h = ctypes.c_void_p()
+        self._lock = threading.RLock()
         self._stream_set = "own"
         self.nprobe = 1        # accepted and ignored: the flat index is exhaustive (vector_database.py:176-177)
+        self._id_offset = 0
         if _handle is not None:
             self._h = _handle
         else:
@@ -136,6 +151,7 @@ class FlatIndex(_ReconstructCache):
     def reserve(self, n_total: int) -> None:
         self._check(self._lib.rdb_reserve(self._h, int(n_total)))
 
+    @_locked
     def add(self, x, normalize: bool = False) -> None:
         """index.add(x) (vector_database.py:138); ``normalize`` fuses _maybe_normalize (:100-105)."""
         if _is_cuda_tensor(x):
@@ -152,6 +168,7 @@ class FlatIndex(_ReconstructCache):
         self._check(self._lib.rdb_add(self._h, x.ctypes.data_as(ctypes.c_void_p), x.shape[0], MEM_HOST,
                                       int(bool(normalize))))
 
+    @_locked
     def search(self, q, k: int, normalize: bool = False, algo=ALGO_AUTO, return_labels: bool = False):
         """index.search(q, k) -> (distances float32[nq,k], ids int64[nq,k]) best-first
         (vector_database.py:181).  torch CUDA queries give torch CUDA results."""
@@ -185,6 +202,7 @@ class FlatIndex(_ReconstructCache):
         self._rc_note_search(I)
         return (D, I, L) if return_labels else (D, I)
 
+    @_locked
     def reconstruct(self, i: int) -> np.ndarray:
         """index.reconstruct(i) -> float32[d] (pipeline.py:503)."""
         hit = self._rc_lookup(int(i))
@@ -195,6 +213,7 @@ class FlatIndex(_ReconstructCache):
         self._check(self._lib.rdb_reconstruct(self._h, int(i), out.ctypes.data_as(ctypes.c_void_p)))
         return out
 
+    @_locked
     def reconstruct_batch(self, ids):
         """Rows ``ids`` in one kernel; ids < 0 / out of range give zero rows (pipeline.py:511-512)."""
         if _is_cuda_tensor(ids):
@@ -213,6 +232,7 @@ class FlatIndex(_ReconstructCache):
         return out
 
     # ------------------------------------------------------------------ additive API
+    @_locked
     def set_labels(self, labels) -> None:
         lab = np.ascontiguousarray(labels, dtype=np.float32).reshape(-1)
         self._use_own_stream()
@@ -220,7 +240,24 @@ class FlatIndex(_ReconstructCache):
 
     def set_id_offset(self, offset: int) -> None:
         self._check(self._lib.rdb_set_id_offset(self._h, int(offset)))
+        self._id_offset = int(offset)
 
+    def set_option(self, name: str, value: int) -> None:
+        """Per-handle tuning / test option (``rdb_set_option``): e.g. ``tc_cta_group``, ``tier1``, ``largek_scorer``."""
+        self._check(self._lib.rdb_set_option(self._h, str(name).encode(), int(value)))
+
+    def truncate(self, n_keep: int) -> None:
+        """Forget the rows beyond the first ``n_keep`` (rolls a partially applied multi-shard add back)."""
+        with self._lock:
+            self._check(self._lib.rdb_truncate(self._h, int(n_keep)))
+            self._rc_pending = self._rc_rows = None
+
+    def release_scratch(self) -> None:
+        """Free the grow-only search scratch; the index stays searchable (the scratch regrows on demand)."""
+        with self._lock:
+            self._check(self._lib.rdb_release_scratch(self._h))
+
+    @_locked
     def search_shard(self, q, k: int, normalize: bool = False):
         """Per-shard candidates in merge form (torch CUDA in/out): (key, gid, labels, qnorm)."""
         import torch
@@ -237,6 +274,7 @@ class FlatIndex(_ReconstructCache):
                                                ctypes.c_void_p(qn.data_ptr())))
         return key, gid, lab, qn
 
+    @_locked
     def merge_shards(self, key, gid, lab, qnorm):
         """Merge [nq, nlists, k] candidate lists (torch CUDA) -> (D, I, L) as an unsharded search."""
         import torch
@@ -273,6 +311,7 @@ class FlatIndex(_ReconstructCache):
     def ipc_free(self, ptr: int) -> None:
         self._check(self._lib.rdb_ipc_free(self._h, ctypes.c_void_p(ptr)))
 
+    @_locked
     def search_shard_into(self, q, k: int, normalize: bool, key_ptr: int, gid_ptr: int, lab_ptr: int, qnorm):
         """search_shard writing the candidates to raw device pointers (the IPC-exported buffer)."""
         import torch
@@ -283,6 +322,7 @@ class FlatIndex(_ReconstructCache):
                                                ctypes.c_void_p(gid_ptr), ctypes.c_void_p(lab_ptr),
                                                ctypes.c_void_p(qnorm.data_ptr())))
 
+    @_locked
     def merge_shards_peer(self, key_ptrs, gid_ptrs, lab_ptrs, nq: int, k: int, qnorm):
         """ONE kernel: gather list g from GPU g's memory over NVLink (P2P loads) while merging."""
         import torch
@@ -301,8 +341,10 @@ class FlatIndex(_ReconstructCache):
         """Let this index's kernels read device memory of ``peer_device`` (single-process multi-GPU merge)."""
         self._check(self._lib.rdb_enable_peer_access(self._h, int(peer_device)))
 
-    def filter_first_k(self, idx, dist, lab, row_codes, excl_sorted, K: int):
-        """Device-side rank-ordered exclusion + first-K compaction (pipeline.py:491-520); torch CUDA in/out."""
+    @_locked
+    def filter_first_k(self, idx, dist, lab, row_codes, excl_sorted, K: int, ntotal: Optional[int] = None):
+        """Device-side rank-ordered exclusion + first-K compaction (pipeline.py:491-520); torch CUDA in/out.  ``ntotal`` =
+        rows of the WHOLE database (row shards pass the global count; default: this index's own rows + id offset)."""
         import torch
         B, ks = idx.shape
         idx, dist, lab = idx.contiguous(), dist.contiguous(), lab.contiguous()
@@ -312,11 +354,15 @@ class FlatIndex(_ReconstructCache):
         ne = 0 if excl_sorted is None else int(excl_sorted.numel())
         p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() else None   # noqa: E731
         self._use_torch_stream(torch)
+        if ntotal is None:
+            ntotal = len(row_codes) if (ne and row_codes is not None) else self.ntotal + self._id_offset
         self._check(self._lib.rdb_filter_first_k(self._h, p(idx), p(dist), p(lab), B, ks, p(row_codes) if ne else None,
-                                                 p(excl_sorted) if ne else None, ne, int(K), ctypes.c_void_p(oi.data_ptr()),
+                                                 int(ntotal), p(excl_sorted) if ne else None, ne, int(K),
+                                                 ctypes.c_void_p(oi.data_ptr()),
                                                  ctypes.c_void_p(od.data_ptr()), ctypes.c_void_p(ol.data_ptr())))
         return oi, od, ol
 
+    @_locked
     def label_vote(self, labels_nq_k, kvote: int):
         if _is_cuda_tensor(labels_nq_k):
             import torch
@@ -363,11 +409,15 @@ class FlatIndex(_ReconstructCache):
         return int(c.value)
 
     def mem_info(self):
-        a, b, c = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
-        self._check(self._lib.rdb_mem_info(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
-        return {"index_bytes": int(a.value), "free": int(b.value), "total": int(c.value)}
+        """Device bytes of the stored rows / of the search scratch, and free / total of the device.  A closed index
+        reports 0 / 0 (and the current device)."""
+        a, s, b, c = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        self._check(self._lib.rdb_mem_info(self._h if self._h else None, ctypes.byref(a), ctypes.byref(s), ctypes.byref(b),
+                                           ctypes.byref(c)))
+        return {"index_bytes": int(a.value), "scratch_bytes": int(s.value), "free": int(b.value), "total": int(c.value)}
 
     # ------------------------------------------------------------------ persistence (faiss IndexFlat layout)
+    @_locked
     def save(self, path: str) -> None:
         self._use_own_stream()
         self._check(self._lib.rdb_serialize(self._h, str(path).encode()))
@@ -383,9 +433,11 @@ class FlatIndex(_ReconstructCache):
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:
-        h, self._h = self._h, ctypes.c_void_p()
-        if h:
-            self._lib.rdb_destroy(h)
+        """rdb_destroy: frees the rows, the scratch, the stream.  Idempotent."""
+        with self._lock:
+            h, self._h = self._h, ctypes.c_void_p()
+            if h:
+                self._lib.rdb_destroy(h)
 
     def __del__(self):
         try:

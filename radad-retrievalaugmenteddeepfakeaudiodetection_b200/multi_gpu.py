@@ -141,23 +141,34 @@ class MultiGpuFlatIndex(_ReconstructCache):
             want[g] = want.get(g, 0) + cnt
         for g, cnt in want.items():
             self._reserve_shard(g, self.shards[g].ntotal + cnt)
-        r0 = 0
-        for g, cnt in plan:
-            piece = x[r0:r0 + cnt]
-            shard = self.shards[g]
-            if _is_cuda_tensor(piece):
-                with torch.cuda.device(self.devices[g]):
-                    shard.add(piece.to(torch.device("cuda", self.devices[g]), non_blocking=True), normalize=normalize)
-            else:
-                shard.add(piece, normalize=normalize)
-            local0 = shard.ntotal - cnt
+        # all-or-nothing (faiss `add` is; VectorDatabase.add_vectors_batch logs a failed slice and carries on with the
+        # next one, vector_database.py:147-149): segments / ntotal are committed only after every piece is stored; a
+        # failure truncates the shards that already took their piece, so no orphan rows and no reused global ids
+        before = [s.ntotal for s in self.shards]
+        staged, r0 = [], 0
+        try:
+            for g, cnt in plan:
+                piece = x[r0:r0 + cnt]
+                shard = self.shards[g]
+                if _is_cuda_tensor(piece):
+                    with torch.cuda.device(self.devices[g]):
+                        shard.add(piece.to(torch.device("cuda", self.devices[g]), non_blocking=True), normalize=normalize)
+                else:
+                    shard.add(piece, normalize=normalize)
+                staged.append((g, shard.ntotal - cnt, self._ntotal + r0, cnt))
+                r0 += cnt
+        except Exception:
+            for g, shard in enumerate(self.shards):
+                if shard.ntotal != before[g]:
+                    shard.truncate(before[g])
+            raise
+        for g, local0, glob0, cnt in staged:
             seg = self._seg[g]
-            if seg and seg[-1][0] + seg[-1][2] == local0 and seg[-1][1] + seg[-1][2] == self._ntotal + r0:
+            if seg and seg[-1][0] + seg[-1][2] == local0 and seg[-1][1] + seg[-1][2] == glob0:
                 seg[-1] = (seg[-1][0], seg[-1][1], seg[-1][2] + cnt)
             else:
-                seg.append((local0, self._ntotal + r0, cnt))
+                seg.append((local0, glob0, cnt))
             self._seg_dev[g] = None
-            r0 += cnt
         self._ntotal += n
         self._glob = None
 
@@ -303,11 +314,14 @@ class MultiGpuFlatIndex(_ReconstructCache):
         return out.cpu().numpy()
 
     # ------------------------------------------------------------------ pass-throughs (elementwise on given tensors)
-    def filter_first_k(self, idx, dist, lab, row_codes, excl_sorted, K: int):
+    def filter_first_k(self, idx, dist, lab, row_codes, excl_sorted, K: int, ntotal: Optional[int] = None):
+        """Elementwise on the given tensors; ids are GLOBAL, so the bound is the global row count (a shard's own count
+        would drop every neighbour that lives on another shard)."""
         import torch
         with torch.cuda.device(idx.device):
             own = [s for g, s in enumerate(self.shards) if self.devices[g] == idx.device.index]
-            return (own[0] if own else self.shards[0]).filter_first_k(idx, dist, lab, row_codes, excl_sorted, K)
+            return (own[0] if own else self.shards[0]).filter_first_k(idx, dist, lab, row_codes, excl_sorted, K,
+                                                                      ntotal=self._ntotal if ntotal is None else ntotal)
 
     def label_vote(self, labels_nq_k, kvote: int):
         return self.shards[0].label_vote(labels_nq_k, kvote)
@@ -320,9 +334,18 @@ class MultiGpuFlatIndex(_ReconstructCache):
         r = [s.last_kernel_ms() for s in self.shards if s.ntotal]
         return max(v[0] for v in r), r[0][1], r[0][2]
 
+    def set_option(self, name: str, value: int) -> None:
+        for s in self.shards:
+            s.set_option(name, value)
+
+    def release_scratch(self) -> None:
+        for s in self.shards:
+            s.release_scratch()
+
     def mem_info(self):
         infos = [s.mem_info() for s in self.shards]
-        return {"index_bytes": sum(i["index_bytes"] for i in infos), "free": sum(i["free"] for i in infos),
+        return {"index_bytes": sum(i["index_bytes"] for i in infos), "scratch_bytes": sum(i["scratch_bytes"] for i in infos),
+                "free": sum(i["free"] for i in infos),
                 "total": sum(i["total"] for i in infos), "per_device": infos}
 
     # ------------------------------------------------------------------ persistence (faiss IndexFlat layout)

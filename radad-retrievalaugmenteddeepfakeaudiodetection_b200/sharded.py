@@ -95,7 +95,7 @@ class ShardedFlatIndex:
                 if r != self.rank:
                     self.local.ipc_close(p)
             self.local.ipc_free(self._peer[1])
-        cap = max(need, 4096)
+        cap = (max(need, 4096) + 3) & ~3       # the int64 id plane starts at base + 4 * cap: keep it 8-byte aligned (16 here)
         own, handle = self.local.ipc_alloc(2 * cap * 16)
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
         allh = torch.empty((self.world * 64,), dtype=torch.uint8, device=device)

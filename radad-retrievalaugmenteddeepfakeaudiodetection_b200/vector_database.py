@@ -221,11 +221,25 @@ class VectorDatabase:
         if k <= 0:
             z = np.zeros((len(query_vectors), 0), dtype=np.float32)
             return z, np.zeros((len(query_vectors), 0), dtype=np.int64), z.copy()
-        self._sync_labels()
+        synced = self._sync_labels()
         if not _is_cuda_tensor(query_vectors):
             query_vectors = np.ascontiguousarray(query_vectors.astype(np.float32, copy=False))
-        return self.index.search(query_vectors, k, normalize=bool(getattr(self, "_cosine", False)),
-                                 return_labels=True)
+        if synced:
+            return self.index.search(query_vectors, k, normalize=bool(getattr(self, "_cosine", False)),
+                                     return_labels=True)
+        # len(vector_labels) != index.ntotal (a metadata.pkl that does not belong to the index file, or a partially failed
+        # add): the device copy cannot be trusted, so index vector_labels by the returned ids on the host exactly like the
+        # reference caller (pipeline.py:504) -- an id without a label raises IndexError there and here, never label 0.
+        logging.error(f"labels out of sync with the index ({len(self.vector_labels)} labels, {self.index.ntotal} rows); "
+                      "gathering labels on the host")
+        dist, idx = self.index.search(query_vectors, k, normalize=bool(getattr(self, "_cosine", False)))
+        host_idx = idx.cpu().numpy() if _is_cuda_tensor(idx) else idx
+        lab = np.array([[float(self.vector_labels[int(i)]) if i >= 0 else 0.0 for i in row] for row in host_idx],
+                       dtype=np.float32).reshape(host_idx.shape)
+        if _is_cuda_tensor(idx):
+            import torch
+            return dist, idx, torch.from_numpy(lab).to(idx.device)
+        return dist, idx, lab
 
     def label_vote(self, neighbour_labels, kvote: int = None):
         """Sum of the first ``kvote`` neighbour labels per query (spoof = 1, bona-fide = 0: dataset.py:36-44)."""
@@ -289,12 +303,26 @@ class VectorDatabase:
         return None
 
     # ---- reference :259-273 ------------------------------------------------------------------------------
-    def cleanup_gpu_resources(self):
-        """Clean up GPU resources to prevent memory leaks (the index itself stays usable, as in the reference)."""
+    def cleanup_gpu_resources(self, release_index: bool = True):
+        """Clean up GPU resources to prevent memory leaks (reference :259-268).
+
+        In the reference this drops the GPU index handle and leaves the rest to destructors, and its only caller is
+        ``__del__`` (:270-273).  Here it actually returns the device memory: the search scratch (the counterpart of
+        ``faiss.StandardGpuResources``' temporary memory) and -- unless ``release_index=False`` -- the stored rows
+        (``rdb_destroy``); ``self.index`` then becomes ``None`` exactly as before the first add, so a later search raises
+        the reference's "Vector database is empty" error and ``load()`` brings a saved database back.  Idempotent."""
         if self.gpu_resources is not None:
             try:
                 del self.gpu_index
                 self.gpu_index = None
+                idx = self.index
+                if idx is not None:
+                    if release_index:
+                        self.index = None
+                        self._labels_synced = -1
+                        idx.close()
+                    else:
+                        idx.release_scratch()
                 logging.info("GPU resources cleaned up")
             except Exception as e:  # noqa: BLE001
                 logging.warning(f"Error during GPU cleanup: {e}")

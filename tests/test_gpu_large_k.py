@@ -30,15 +30,16 @@ def _lattice(N, D, Q, seed):
 @pytest.mark.parametrize("store,scorer", [("f32", "simt"), ("bf16", "tc"), ("bf16", "simt"), ("f16", "tc")])
 @pytest.mark.parametrize("metric_s", ["L2", "IP"])
 @pytest.mark.parametrize("k,rows", [(129, None), (200, 1024), (777, None), (2048, 2500)])
-def test_lattice_bit_exact_k_above_128(pkg, oracle, monkeypatch, metric_s, k, rows, store, scorer):
-    """rows = forced chunk length (RDB_LARGEK_ROWS): several per-chunk lists, ties straddling chunk borders.
+def test_lattice_bit_exact_k_above_128(pkg, oracle, metric_s, k, rows, store, scorer):
+    """rows = forced chunk length (option "largek_rows"): several per-chunk lists, ties straddling chunk borders.
     scorer = where the dense keys come from: the tensor cores (16-bit stores) or the exact CUDA-core kernel."""
-    monkeypatch.setenv("RDB_LARGEK_SCORER", scorer)
-    if rows:
-        monkeypatch.setenv("RDB_LARGEK_ROWS", str(rows))
     xb, xq = _lattice(6001, 64, 70, 11)
     metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
     idx = pkg.FlatIndex(64, metric, store)
+    idx.set_option("largek_scorer", {"simt": 1, "tc": 2}[scorer])
+    idx.set_option("largek_split", 0)                       # fp32 stores: the exact CUDA-core keys are what is tested here
+    if rows:
+        idx.set_option("largek_rows", rows)
     idx.add(xb[:4000])
     idx.add(xb[4000:])
     D, I = idx.search(xq, k)
@@ -69,14 +70,14 @@ def test_all_rows_identical(pkg):
     (9000,   768, 1,   150,  "L2", False, "bf16", None),      # batch-1 (beyond the streaming scorer's k)
     (4100,   40,  5,   2048, "L2", False, "f16",  None),
 ], ids=["l2_f32_k1000", "cos_bf16_k500_chunks", "ip_f32_oddD_k256", "l2_bf16_q1_k150", "l2_f16_k2048"])
-def test_gaussian_vs_oracle_k_above_128(pkg, oracle, monkeypatch, case):
+def test_gaussian_vs_oracle_k_above_128(pkg, oracle, case):
     N, Dm, Q, k, metric_s, cos, store, rows = case
-    if rows:
-        monkeypatch.setenv("RDB_LARGEK_ROWS", str(rows))
     metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
     xb, xq = _gauss(N, Dm, 1234), _gauss(Q, Dm, 5678)
     xq[0] = xb[5]
     idx = pkg.FlatIndex(Dm, metric, store)
+    if rows:
+        idx.set_option("largek_rows", rows)
     idx.add(xb, normalize=cos)
     D, I = idx.search(xq, k, normalize=cos)
     ref = oracle.FlatIndexOracle(Dm, metric, store=store)
@@ -99,12 +100,10 @@ def test_gaussian_vs_oracle_k_above_128(pkg, oracle, monkeypatch, case):
 
 @pytest.mark.parametrize("sample", [True, False])
 @pytest.mark.parametrize("kind", ["gauss", "lattice", "on_stride"])
-def test_long_rows_sampled_pivot_select(pkg, oracle, monkeypatch, kind, sample):
+def test_long_rows_sampled_pivot_select(pkg, oracle, kind, sample):
     """Chunks of >= 32768 rows take the select's fast path (pivot from a strided sample + one collect pass); it must be
     exact on Gaussian keys, on lattice keys (ties ordered by id), and when the sample misleads (the best rows sit
     exactly on the sample stride -> too few rows reach the pivot -> exact path).  Same answers with the fast path off."""
-    if not sample:
-        monkeypatch.setenv("RDB_LARGEK_NO_SAMPLE", "1")
     N, Dm, Q, k = 163_840, 32, 12, 700
     rng = np.random.default_rng(8)
     if kind == "gauss":
@@ -115,6 +114,7 @@ def test_long_rows_sampled_pivot_select(pkg, oracle, monkeypatch, kind, sample):
         if kind == "on_stride":
             xb[::10] = xq[0]                                      # stride of the sample = N // 16384 = 10
     idx = pkg.FlatIndex(Dm, pkg.METRIC_L2, "bf16" if kind != "gauss" else "f32")
+    idx.set_option("largek_sample", 1 if sample else 0)
     idx.add(xb)
     D, I = idx.search(xq, k)
     ref = oracle.FlatIndexOracle(Dm, pkg.METRIC_L2)

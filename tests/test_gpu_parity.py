@@ -275,7 +275,7 @@ def test_lattice_bit_exact_large_k(pkg, oracle, metric_s, k):
 @pytest.mark.parametrize("store", ["bf16", "f32"])
 @pytest.mark.parametrize("metric_s", ["L2", "IP"])
 @pytest.mark.parametrize("k", [10, 24, 100])
-def test_cta_pair_kernel_bit_exact(pkg, oracle, monkeypatch, metric_s, k, store):
+def test_cta_pair_kernel_bit_exact(pkg, oracle, metric_s, k, store):
     """The cta_group::2 form of the tensor-core scorer (a CTA pair runs M = 256 MMAs, RDB_TC_CG=2): lattice data, ragged
     query count (an odd number of 128-query tiles, last tile partly empty) and ragged N -- ids and distances must equal
     the oracle bit-for-bit, and the single-CTA form must agree."""
@@ -293,9 +293,9 @@ def test_cta_pair_kernel_bit_exact(pkg, oracle, monkeypatch, metric_s, k, store)
     ref = oracle.FlatIndexOracle(Dm, metric)
     ref.add(xb)
     Dr, Ir = ref.search(xq, k, direct=False)
-    monkeypatch.setenv("RDB_TC_CG", "2")
+    idx.set_option("tc_cta_group", 2)
     D2, I2 = idx.search(xq, k, algo="tc")
-    monkeypatch.setenv("RDB_TC_CG", "1")
+    idx.set_option("tc_cta_group", 1)
     D1, I1 = idx.search(xq, k, algo="tc")
     np.testing.assert_array_equal(I2, Ir)
     np.testing.assert_array_equal(D2, Dr)

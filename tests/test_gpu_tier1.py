@@ -28,7 +28,7 @@ def _check_vs_oracle(pkg, oracle, idx, xb, xq, D, I, k, metric, cos):
 
 
 @pytest.mark.parametrize("metric_s,cos,k", [("IP", True, 10), ("L2", False, 15), ("IP", False, 32), ("L2", False, 64)])
-def test_tier1_certifies_gaussian(pkg, oracle, monkeypatch, metric_s, cos, k):
+def test_tier1_certifies_gaussian(pkg, oracle, metric_s, cos, k):
     """Well-separated data: tier 1 certifies (nearly) everything; neighbours == oracle; identical to the search with
     tier 1 switched off (both end in the same exact fp32 re-rank, so distances agree bit-for-bit)."""
     N, Dm, Q = 300_000, 64, 300
@@ -45,7 +45,7 @@ def test_tier1_certifies_gaussian(pkg, oracle, monkeypatch, metric_s, cos, k):
     assert idx.last_tier1_candidates == (32 if k <= 16 else 128)
     assert idx.last_kernel_ms()[1] == "tc"
     _check_vs_oracle(pkg, oracle, idx, xb, xq, D, I, k, metric, cos)
-    monkeypatch.setenv("RDB_NO_TIER1", "1")
+    idx.set_option("tier1", 0)
     D3, I3 = idx.search(xq, k, normalize=cos)
     assert idx.last_tier1 == (0, 0)
     np.testing.assert_array_equal(I, I3)

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Interleaved A/B of scorer knobs on ONE box in ONE process (boxes differ by a few % under the power cap, so variants
-must alternate inside the same run).  The library reads its RDB_* environment knobs at every search call.
+must alternate inside the same run).  Variants are per-handle options (rdb_set_option); "tc_debug" needs a library built
+with RDB_PROFILING=1.
 
-    python tools/ab_knobs.py N D Q k store metric 'RDB_TC_CG=1' 'RDB_TC_CG=2' ['A=1,B=2' ...]
+    python tools/ab_knobs.py N D Q k store metric 'tc_cta_group=1' 'tc_cta_group=2' ['a=1,b=2' ...]
 
 Prints one JSON line per variant: median / min scorer-kernel ms (CUDA events inside the library) and TFLOP/s.
 Profiling aid only -- not a product path."""
@@ -18,6 +19,11 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("radad-retrievalaugmenteddeepfakeaudiodetection_b200")
+
+
+DEFAULTS = {"tc_cta_group": 0, "tc_lockstep": 8, "tc_lockstep_spins": 4096, "tc_stages": 64, "tc_query_stationary": 1,
+            "tc_pivot": 1, "tc_debug": 0, "tier1": 1, "tier1_kc": 0, "largek_scorer": 0, "largek_rows": 0,
+            "largek_sample": 1, "largek_split": 1}
 
 
 def main():
@@ -43,11 +49,11 @@ def main():
     for r in range(rounds + 1):
         for v in variants:
             for name in knobs:
-                os.environ.pop(name, None)
+                idx.set_option(name, DEFAULTS[name])
             for kv in v.split(","):
                 if kv:
                     a, b = kv.split("=")
-                    os.environ[a] = b
+                    idx.set_option(a, int(b))
             for _ in range(2):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
