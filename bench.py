@@ -16,7 +16,13 @@ Prints ONE JSON line on rank 0.  Keys follow the driver's contract:
   roofline     dominant kernel (tcgen05 score+select): algorithmic FLOPs 2*Q*N_shard*D per launch / its average
                CUDA-event duration, against the measured sustained bf16 peak of MEASURED_PEAKS.json
   cpu_baseline the oracle's torch-CPU restatement of the reference's faiss sgemm path on the host cores, on a
-               bounded sample (rank 0, N=1 only)
+               bounded sample (rank 0, N=1 only); its neighbour ids are compared with the CUDA path's on the same rows
+  secondary    the other BASELINE.json configs measured in the same run (N=1): C2 (1M x 768 fp32, 10k queries, L2 and
+               cosine, exact-fp32 neighbours), C4 (batch-1 latency over 10 000 sequential host queries, bf16 and fp32),
+               ingest GB/s with / without the fused normalisation -- each beside its roofline
+  correctness  recall@10 of >= 4096 queries against a brute force over the stored rows (N>1: per-rank brute force over the
+               local shard -> all-gather -> merge) and, at N>1, ids_equal_n1_subset: the N-GPU answer against the answer of
+               ONE GPU holding the whole database
 """
 import argparse
 import importlib
@@ -194,7 +200,7 @@ def cpu_baseline(torch, orc, idx, q_dev):
     ids = torch.arange(n_s, device=q_dev.device, dtype=torch.int64)
     xb = idx.reconstruct_batch(ids).cpu().numpy()                # stored (bf16-rounded, normalised) rows as fp32
     xq = q_dev[:16384].cpu().numpy()
-    qn = orc.maybe_normalize(xq, True)
+    qn = orc.round_bf16(orc.maybe_normalize(xq, True))           # bf16 config: the oracle sees the rounded values
     orc.torch_cpu_flat_search(xb, qn[:64], K, orc.METRIC_IP)     # warm-up
     t0 = time.perf_counter()
     orc.torch_cpu_flat_search(xb, qn[:256], K, orc.METRIC_IP)    # calibration
@@ -209,25 +215,133 @@ def cpu_baseline(torch, orc, idx, q_dev):
                       f"QPS scaled linearly in rows to the full database"}, (xb, qn[:nq_s], Ic)
 
 
-def recall_check(torch, idx, q_dev, I_ours, nsub=256):
-    """recall@k of the first `nsub` queries against a torch fp32 brute force over the STORED rows (checker only)."""
+def brute_force_topk(torch, idx, q_dev, nsub, row0, dist=None, world=1):
+    """Checker: exact top-K of the first `nsub` queries by an fp32 matmul over the STORED rows of this rank's shard
+    (read back through reconstruct_batch), merged over the ranks with one all-gather.  Returns (values, global ids)."""
     n = idx.ntotal
+    dev = q_dev.device
     qs = torch.nn.functional.normalize(q_dev[:nsub], dim=1, eps=1e-12).to(torch.bfloat16).to(torch.float32)
-    best_v = torch.full((nsub, K), float("-inf"), device=q_dev.device)
-    best_i = torch.full((nsub, K), -1, dtype=torch.int64, device=q_dev.device)
-    step = 500_000
-    for s in range(0, n, step):
-        e = min(n, s + step)
-        rows = idx.reconstruct_batch(torch.arange(s, e, device=q_dev.device, dtype=torch.int64))
+    best_v = torch.full((nsub, K), float("-inf"), device=dev)
+    best_i = torch.full((nsub, K), -1, dtype=torch.int64, device=dev)
+    step = 250_000
+    for s0 in range(0, n, step):
+        e = min(n, s0 + step)
+        rows = idx.reconstruct_batch(torch.arange(row0 + s0, row0 + e, device=dev, dtype=torch.int64))
         sc = qs @ rows.T
-        v, i = torch.topk(sc, K, dim=1)
-        cv, ci = torch.cat([best_v, v], 1), torch.cat([best_i, i + s], 1)
+        v, i = torch.topk(sc, min(K, e - s0), dim=1)
+        cv, ci = torch.cat([best_v, v], 1), torch.cat([best_i, i + row0 + s0], 1)
         best_v, sel = torch.topk(cv, K, dim=1)
         best_i = torch.gather(ci, 1, sel)
         del rows, sc
-    ours = I_ours[:nsub]
-    hit = (ours.unsqueeze(2) == best_i.unsqueeze(1)).any(2).float().mean().item()
-    return hit
+    if world > 1:
+        gv = torch.empty((world,) + tuple(best_v.shape), device=dev)
+        gi = torch.empty((world,) + tuple(best_i.shape), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gv, best_v.contiguous())
+        dist.all_gather_into_tensor(gi, best_i.contiguous())
+        cv, ci = gv.permute(1, 0, 2).reshape(nsub, -1), gi.permute(1, 0, 2).reshape(nsub, -1)
+        best_v, sel = torch.topk(cv, K, dim=1)
+        best_i = torch.gather(ci, 1, sel)
+    return best_v, best_i
+
+
+def recall_at_k(torch, ours_i, ref_i):
+    return (ours_i.unsqueeze(2) == ref_i.unsqueeze(1)).any(2).float().mean().item()
+
+
+def _percentiles(ms):
+    ms = sorted(ms)
+    return ms[len(ms) // 2], ms[min(len(ms) - 1, int(len(ms) * 0.99))]
+
+
+def secondary_block(torch, np, pkg, orc, dev, q_dev, pk):
+    """BASELINE.json configs[1] (C2), configs[3] (C4) and north_star (a) (ingest) on this GPU, in this run."""
+    out = {}
+    n2, q2 = 1_000_000, 10_000
+    vdbs = {}
+
+    class _Cfg:
+        def __init__(self, itype, dtype):
+            self.vector_db_path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"rdb_bench_sec_{os.getpid()}")
+            self.vector_db_index_type, self.top_k, self.db_dtype = itype, K, dtype
+
+    # ---- ingest (north_star a): 1M x 768 fp32 device rows -> bf16 store, with and without the fused normalisation
+    x = torch.cat([gen_db_chunk(torch, c, dev) for c in range(n2 // GEN_CHUNK)], 0)
+    for norm in (False, True):
+        scratch = pkg.FlatIndex(DIM, pkg.METRIC_IP, "bf16", device=dev.index)
+        scratch.reserve(4 * n2)
+        scratch.add(x, normalize=norm)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            scratch.add(x, normalize=norm)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        gbs = n2 * (DIM * 4 + DIM * 2 + 4) / (ms * 1e-3) / 1e9
+        out["ingest_bf16_normalize" if norm else "ingest_bf16"] = {
+            "rows": n2, "ms": ms, "GBs": gbs, "frac_of_hbm": gbs / pk["hbm"],
+            "bytes_per_row": DIM * 4 + DIM * 2 + 4, "kernel": "ingest_rows_kernel (+ 2 norm-summary kernels)"}
+        scratch.close()
+    # ---- C2: 1M x 768 fp32 store, 10k-query batch, k=10, exact-fp32 neighbours (tiered certified tensor-core search)
+    roof_c2 = pk["bf16_sustained"] * 1e12 / (2.0 * n2 * DIM)           # one-term tensor roofline, queries/s (SURVEY 8d)
+    for name, metric, norm in (("c2_l2", pkg.METRIC_L2, False), ("c2_cosine", pkg.METRIC_IP, True)):
+        idx = pkg.FlatIndex(DIM, metric, "f32", device=dev.index)
+        idx.reserve(n2)
+        idx.add(x, normalize=norm)
+        q = q_dev[:q2]
+        for _ in range(3):
+            Dv, Iv = idx.search(q, K, normalize=norm)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kms = []
+        e0.record()
+        for _ in range(5):
+            Dv, Iv = idx.search(q, K, normalize=norm)
+            kms.append(idx.last_kernel_ms()[0])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        t1q, t1u = idx.last_tier1
+        # checker: the oracle's CPU search over the stored rows for 128 of the queries
+        xb = idx.reconstruct_batch(torch.arange(n2, device=dev, dtype=torch.int64)).cpu().numpy()
+        qn = orc.maybe_normalize(q[:128].cpu().numpy(), norm)
+        _, Ic = orc.torch_cpu_flat_search(xb, qn, K, metric)
+        eq = float((np.asarray(Ic) == Iv[:128].cpu().numpy()).all(1).mean())
+        out[name] = {"workload": f"C2: {n2}x{DIM} fp32 store, {q2}-query batch, k={K}, {'cosine' if norm else 'L2'}, exact fp32",
+                     "qps": q2 / (ms * 1e-3), "ms_per_batch": ms, "scorer_kernel_ms": sum(kms) / len(kms),
+                     "roofline_qps_one_term_tensor": roof_c2, "frac_of_roofline": q2 / (ms * 1e-3) / roof_c2,
+                     "tier1_queries": t1q, "tier1_uncertified": t1u, "exact_fallback_queries": idx.last_uncertified,
+                     "ids_equal_oracle_128q": eq}
+        vdbs[name] = idx
+        del xb
+    # ---- C4: batch-1 latency, 10 000 sequential HOST queries through VectorDatabase.search (k = top_k + 10 = 15)
+    bf = pkg.FlatIndex(DIM, pkg.METRIC_IP, "bf16", device=dev.index)
+    bf.reserve(n2)
+    bf.add(x, normalize=True)
+    del x
+    qh = np.array(q_dev[:10_000].cpu().numpy())                         # pageable host memory
+    for name, idx, cos, bpe in (("c4_bf16", bf, True, 2), ("c4_fp32", vdbs["c2_l2"], False, 4)):
+        vdb = pkg.VectorDatabase(_Cfg("IP" if cos else "L2", "bf16" if bpe == 2 else "f32"))
+        vdb.index, vdb._cosine = idx, cos
+        for i in range(200):
+            vdb.search(qh[i], k=15)
+        lat = []
+        for i in range(len(qh)):
+            t0 = time.perf_counter()
+            vdb.search(qh[i], k=15)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        p50, p99 = _percentiles(lat)
+        kms = idx.last_kernel_ms()[0]
+        floor = n2 * DIM * bpe / (pk["hbm"] * 1e9) * 1e3
+        out[name] = {"workload": f"C4: {n2}x{DIM} {'bf16' if bpe == 2 else 'fp32'} store, 10000 sequential host queries, k=15",
+                     "p50_ms": p50, "p99_ms": p99, "mean_ms": sum(lat) / len(lat), "kernel_ms_last": kms,
+                     "hbm_floor_ms": floor, "p50_frac_of_floor": floor / p50, "kernel_frac_of_floor": floor / kms,
+                     "qps_single_stream": 1e3 / p50}
+        vdb.index = None
+    for idx in list(vdbs.values()) + [bf]:
+        idx.close()
+    return out
 
 
 def main():
@@ -237,6 +351,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C2 / C4 / ingest block (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -268,8 +383,8 @@ def main():
     sidx.set_labels_local(torch.randint(0, 2, (end - start,), generator=lab_gen, device=dev).float().cpu().numpy())
     idx = sidx.local
     q_dev = gen_queries(torch, dev)
-    q_host = torch.empty((NQ, DIM), dtype=torch.float32, pin_memory=True)
-    q_host.copy_(q_dev)
+    # what a reference caller hands over: ordinary (pageable) host memory, never a pinned buffer
+    q_host = q_dev.cpu()
     torch.cuda.synchronize()
 
     def barrier():
@@ -296,7 +411,7 @@ def main():
             return vdb.search_batch(q_np, k=K)
     else:
         def step_e2e():
-            # every rank uploads 1/G of the (pinned host) batch; one all-gather over NVLink assembles it on every GPU
+            # every rank uploads 1/G of the (pageable) host batch; one all-gather over NVLink assembles it on every GPU
             D, I, L = sidx.search_from_host(q_host, K, normalize=True)
             return D.cpu(), I.cpu()
 
@@ -333,6 +448,33 @@ def main():
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
 
+    # ---- correctness of THIS run's answer (every rank takes part: the brute force is sharded like the database)
+    nchk = min(NQ, int(os.environ.get("RDB_BENCH_CHECK_Q", 4096)))
+    corr = {"queries_checked": nchk}
+    try:
+        bv, bi = brute_force_topk(torch, idx, q_dev, nchk, start, dist if world > 1 else None, world)
+        corr[f"recall_at_{K}"] = recall_at_k(torch, out[1][:nchk], bi)
+        corr["ids_equal_bruteforce"] = float((out[1][:nchk] == bi).all(1).float().mean().item())
+        corr["checker"] = ("fp32 matmul + top-k over the stored rows" +
+                           (f", per-rank over the local shard, all-gather, merge ({world} ranks)" if world > 1 else ""))
+        if world > 1:
+            # the same queries on ONE GPU holding the whole database (rank 0 builds it; the other ranks wait)
+            eq = torch.zeros((2,), device=dev)
+            if rank == 0:
+                full = pkg.FlatIndex(DIM, pkg.METRIC_IP, "bf16", device=local_rank)
+                full.reserve(N_DB)
+                for c in range(-(-N_DB // GEN_CHUNK)):
+                    full.add(gen_db_chunk(torch, c, dev), normalize=True)
+                D1, I1 = full.search(q_dev[:nchk], K, normalize=True)
+                eq[0] = (I1 == out[1][:nchk]).all(1).float().mean()
+                eq[1] = (D1 == out[0][:nchk]).all(1).float().mean()
+                full.close()
+            dist.broadcast(eq, 0)
+            corr["ids_equal_n1_subset"] = float(eq[0].item())
+            corr["distances_equal_n1_subset"] = float(eq[1].item())
+    except Exception as e:  # noqa: BLE001
+        corr["error"] = f"{type(e).__name__}: {e}"
+
     t = torch.tensor([ms_dev, ms_e2e, sum(kern_ms) / len(kern_ms)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -354,8 +496,8 @@ def main():
                        "l2_policy": "inputs larger than L2 (database shard >> 126 MB), no flush needed"},
             "e2e": {"value": NQ / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": NQ * DIM * 4, "d2h_bytes_per_step": NQ * K * 12 * world,
-                    "note": ("host numpy in/out through VectorDatabase.search_batch" if world == 1 else
-                             "each rank uploads 1/N of the pinned host batch (total = h2d_bytes_per_step), NVLink "
+                    "note": ("pageable host numpy in/out through VectorDatabase.search_batch" if world == 1 else
+                             "each rank uploads 1/N of the pageable host batch (total = h2d_bytes_per_step), NVLink "
                              "all-gather, sharded search, every rank reads the merged result back")},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -370,15 +512,27 @@ def main():
                          "frac_of_burst": ach / pk["bf16_burst"],
                          "hbm_frac": (rows_local * DIM * 2 / (ms_kern * 1e-3) / 1e9) / pk["hbm"]},
         }
+        line["correctness"] = corr
         if world == 1:
-            try:
-                line["recall_at_10_vs_fp32_bruteforce_256q"] = recall_check(torch, idx, q_dev, out[1])
-            except Exception as e:  # noqa: BLE001
-                line["recall_error"] = str(e)
+            orc = importlib.import_module("oracle.flat_oracle")
             if not args.no_cpu_baseline:
-                orc = importlib.import_module("oracle.flat_oracle")
-                cb, _ = cpu_baseline(torch, orc, idx, q_dev)
+                cb, (xb_s, qn_s, Ic) = cpu_baseline(torch, orc, idx, q_dev)
+                # the oracle's answer is a checker too: the CUDA path over the SAME rows (the first 1M stored rows in an
+                # index of their own) must return the oracle's neighbours for the sampled queries
+                sub = pkg.FlatIndex(DIM, pkg.METRIC_IP, "bf16", device=local_rank)
+                sub.add(torch.from_numpy(xb_s).to(dev))
+                _, Is = sub.search(torch.from_numpy(np.ascontiguousarray(qn_s)).to(dev), K)
+                Is = Is.cpu().numpy()
+                Ic = np.asarray(Ic)
+                cb["ids_equal_cuda_vs_oracle"] = float((Is == Ic).all(1).mean())
+                cb["recall_cuda_vs_oracle"] = float(np.mean([len(set(a) & set(b)) / K for a, b in zip(Is, Ic)]))
+                sub.close()
                 line["cpu_baseline"] = cb
+            if not args.no_secondary:
+                try:
+                    line["secondary"] = secondary_block(torch, np, pkg, orc, dev, q_dev, pk)
+                except Exception as e:  # noqa: BLE001
+                    line["secondary_error"] = f"{type(e).__name__}: {e}"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

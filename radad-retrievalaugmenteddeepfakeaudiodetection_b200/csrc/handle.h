@@ -85,7 +85,7 @@ struct rdb_handle {
   size_t pin_bytes = 0;
   float* d_ynorm_max = nullptr;   // max |y|^2 over the shard (device scalar; feeds the re-rank certificate)
   rdb::DevBuf np_tab;             // piece table of numpy's pairwise summation for rows of d floats (ingest.cuh: NpPlan)
-  int np_nleaves = 0, np_nops = 0;
+  int np_nleaves = 0, np_nops = 0, np_balanced = 0;
   int64_t last_uncertified = 0;
   bool has_master() const { return store == RDB_STORE_F32 || (flags & RDB_FLAG_KEEP_F32_MASTER); }
   bool has_hi() const { return true; }

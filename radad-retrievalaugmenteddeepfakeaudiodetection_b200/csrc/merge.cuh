@@ -310,6 +310,114 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_exact_kernel(const long
   }
 }
 
+// Exact re-rank for LARGE candidate sets (the k > 104 searches of fp32 stores: tensor-core split-precision keys, dense
+// select of kc = k + slack candidates, then this kernel).  One block per query: the warps re-score the kc candidates
+// exactly in fp32 against the master rows (same arithmetic as rerank_exact_kernel and the exact CUDA-core scorer), the
+// block sorts the exact (key, id) pairs (bitonic, shared memory, key desc / id asc), evaluates the same certificate
+//     exact_key[kout - 1] > worst approximate candidate key + B
+// and writes the first kout in FINAL form (distance or merge key, global id, label).  Uncertified queries are appended
+// to uncert_list for the exact CUDA-core search.   Dynamic smem: next_pow2(kc) * 8 bytes.
+constexpr int RERANK_LARGE_THREADS = 256;
+template <bool L2, typename IdxT>
+__global__ void __launch_bounds__(RERANK_LARGE_THREADS) rerank_exact_large_kernel(
+    const IdxT* __restrict__ cand_idx, const float* __restrict__ cand_key, int Q, int kc, int kout,
+    const float* __restrict__ qf, const float* __restrict__ master, const float* __restrict__ ynorm, int D, float eps,
+    const float* __restrict__ qnorm, const float* __restrict__ ynorm_max, long long ntotal, long long id_offset,
+    const float* __restrict__ labels, float* __restrict__ out_dist, long long* __restrict__ out_idx,
+    float* __restrict__ out_lbl, float* __restrict__ out_key, int* __restrict__ uncert_list,
+    int* __restrict__ uncert_count) {
+  extern __shared__ __align__(16) unsigned long long rl_buf[];
+  __shared__ float s_worst[RERANK_LARGE_THREADS / 32];
+  __shared__ int s_nvalid[RERANK_LARGE_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int q = blockIdx.x;
+  if (q >= Q) return;
+  const float* qr = qf + (long long)q * D;
+  const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(qr) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(master) & 15) == 0);
+  float worst = CUDART_INF_F;
+  int nvalid = 0;
+  for (int j = w; j < kc; j += RERANK_LARGE_THREADS / 32) {
+    const long long id = (long long)cand_idx[(long long)q * kc + j];
+    if (id < 0) { if (lane == 0) rl_buf[j] = 0ull; continue; }
+    worst = fminf(worst, cand_key[(long long)q * kc + j]);
+    ++nvalid;
+    const float* yr = master + id * (long long)D;
+    float s = 0.f;
+    if (vec4) {
+      const float4* q4 = reinterpret_cast<const float4*>(qr);
+      const float4* y4 = reinterpret_cast<const float4*>(yr);
+      const int n4 = D >> 2;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int c = lane;
+      for (; c + 96 < n4; c += 128) {
+        const float4 y0 = __ldg(y4 + c), y1 = __ldg(y4 + c + 32), y2 = __ldg(y4 + c + 64), y3 = __ldg(y4 + c + 96);
+        const float4 x0 = q4[c], x1 = q4[c + 32], x2 = q4[c + 64], x3 = q4[c + 96];
+        a0 = fmaf(x0.x, y0.x, a0); a0 = fmaf(x0.y, y0.y, a0); a0 = fmaf(x0.z, y0.z, a0); a0 = fmaf(x0.w, y0.w, a0);
+        a1 = fmaf(x1.x, y1.x, a1); a1 = fmaf(x1.y, y1.y, a1); a1 = fmaf(x1.z, y1.z, a1); a1 = fmaf(x1.w, y1.w, a1);
+        a2 = fmaf(x2.x, y2.x, a2); a2 = fmaf(x2.y, y2.y, a2); a2 = fmaf(x2.z, y2.z, a2); a2 = fmaf(x2.w, y2.w, a2);
+        a3 = fmaf(x3.x, y3.x, a3); a3 = fmaf(x3.y, y3.y, a3); a3 = fmaf(x3.z, y3.z, a3); a3 = fmaf(x3.w, y3.w, a3);
+      }
+      for (; c < n4; c += 32) {
+        const float4 y0 = __ldg(y4 + c);
+        const float4 x0 = q4[c];
+        a0 = fmaf(x0.x, y0.x, a0); a0 = fmaf(x0.y, y0.y, a0); a0 = fmaf(x0.z, y0.z, a0); a0 = fmaf(x0.w, y0.w, a0);
+      }
+      s = (a0 + a1) + (a2 + a3);
+    } else {
+      for (int c = lane; c < D; c += 32) s = fmaf(qr[c], __ldg(yr + c), s);
+    }
+    s = warp_sum(s);
+    const float key = L2 ? fmaf(2.0f, s, -ynorm[id]) : s;
+    if (lane == 0) rl_buf[j] = pack_cand(key, uint32_t(id));
+  }
+  if (lane == 0) { s_worst[w] = worst; s_nvalid[w] = nvalid; }
+  int n2 = 1;
+  while (n2 < kc) n2 <<= 1;
+  for (int i = kc + threadIdx.x; i < n2; i += RERANK_LARGE_THREADS) rl_buf[i] = 0ull;      // below every real element
+  __syncthreads();
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (n2 >> 1); i += RERANK_LARGE_THREADS) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = rl_buf[lo], b = rl_buf[hi];
+        if ((a < b) == desc) { rl_buf[lo] = b; rl_buf[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = threadIdx.x; r < kout; r += RERANK_LARGE_THREADS) {
+    const unsigned long long v = rl_buf[r];
+    const long long o = (long long)q * kout + r;
+    if (v == 0ull) {
+      if (out_dist) out_dist[o] = L2 ? CUDART_INF_F : -CUDART_INF_F;
+      out_idx[o] = -1;
+      if (out_lbl) out_lbl[o] = 0.f;
+      if (out_key) out_key[o] = -CUDART_INF_F;
+    } else {
+      const float kv = unordered_f32(uint32_t(v >> 32));
+      const long long id = (long long)(0xFFFFFFFFu - uint32_t(v));
+      if (out_dist) out_dist[o] = L2 ? fmaxf(0.f, qnorm[q] - kv) : kv;
+      out_idx[o] = id + id_offset;
+      if (out_lbl) out_lbl[o] = labels ? __ldg(labels + id) : 0.f;
+      if (out_key) out_key[o] = kv;
+    }
+  }
+  if (threadIdx.x == 0) {
+    float aw = CUDART_INF_F;
+    int nv = 0;
+    for (int i = 0; i < RERANK_LARGE_THREADS / 32; ++i) { aw = fminf(aw, s_worst[i]); nv += s_nvalid[i]; }
+    const unsigned long long vk = (kout >= 1 && kout <= kc) ? rl_buf[kout - 1] : 0ull;
+    const bool has = vk != 0ull;
+    const float kth_key = has ? unordered_f32(uint32_t(vk >> 32)) : -CUDART_INF_F;
+    const float bound = eps * sqrtf(qnorm[q]) * sqrtf(*ynorm_max) * (L2 ? 2.0f : 1.0f);
+    const bool ok = (nv >= ntotal) || (nv == kc && has && kth_key > aw + bound);
+    if (!ok) uncert_list[atomicAdd(uncert_count, 1)] = q;
+  }
+}
+
 // ---- sampled pivot for the large-k tensor-core path (see launch_tc_pivoted in radad_flat.cu) ---------------------------
 // gthr[q] <- ordered(key of rank `rank` of the sample's merged list), 0 (= no bound) when the sample holds fewer rows
 static __global__ void gthr_from_pivot_kernel(const float* __restrict__ sample_key, int Q, int kc, int rank,

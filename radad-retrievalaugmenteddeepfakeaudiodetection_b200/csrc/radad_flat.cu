@@ -71,18 +71,21 @@ int grow_to(rdb_handle* h, int64_t need, bool exact = false) {
 
 // numpy's pairwise_sum recursion for a row of n floats (numpy/_core/src/umath/loops_utils.h.src: PW_BLOCKSIZE = 128,
 // left part = n / 2 rounded down to a multiple of 8): leaves in left-to-right order + the post-order fold program.
-int np_plan_rec(int off, int n, std::vector<int>& offs, std::vector<int>& lens, std::vector<int>& ops) {
+int np_plan_rec(int off, int n, std::vector<int>& offs, std::vector<int>& lens, std::vector<int>& ops, bool* balanced) {
   if (n <= 128) { offs.push_back(off); lens.push_back(n); return int(offs.size()) - 1; }
   int n2 = n / 2;
   n2 -= n2 % 8;
-  const int a = np_plan_rec(off, n2, offs, lens, ops);
-  const int b = np_plan_rec(off + n2, n - n2, offs, lens, ops);
+  const int a = np_plan_rec(off, n2, offs, lens, ops, balanced);
+  const int b = np_plan_rec(off + n2, n - n2, offs, lens, ops, balanced);
+  if (b - a != int(offs.size()) - b) *balanced = false;      // left and right subtree hold different numbers of leaves
   ops.push_back(a); ops.push_back(b);
   return a;
 }
 int np_plan_build(rdb_handle* h) {
   std::vector<int> offs, lens, ops;
-  np_plan_rec(0, h->d, offs, lens, ops);
+  bool balanced = true;
+  np_plan_rec(0, h->d, offs, lens, ops, &balanced);
+  h->np_balanced = balanced ? 1 : 0;
   std::vector<int> tab(offs);
   tab.insert(tab.end(), lens.begin(), lens.end());
   tab.insert(tab.end(), ops.begin(), ops.end());
@@ -91,7 +94,7 @@ int np_plan_build(rdb_handle* h) {
   h->np_nleaves = int(offs.size()); h->np_nops = int(ops.size() / 2);
   return RDB_OK;
 }
-NpPlan np_plan(rdb_handle* h) { return NpPlan{h->np_tab.as<int>(), h->np_nleaves, h->np_nops}; }
+NpPlan np_plan(rdb_handle* h) { return NpPlan{h->np_tab.as<int>(), h->np_nleaves, h->np_nops, h->np_balanced}; }
 
 // launch the fused ingest kernel (also used to prepare queries)
 int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int norm_of_hi, float* master, void* hi,
@@ -103,26 +106,59 @@ int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int n
   int64_t blocks = std::min<int64_t>((n + warps_per_block - 1) / warps_per_block, int64_t(h->num_sms) * 16);
   dim3 grid((unsigned)blocks), block(256);
   cudaStream_t s = h->stream;
+  // rows of 128 * NC floats with a store layout the specialised kernel knows: hi only / master + hi + lo / master + hi
+  {
+    const int mode = (!master && hi && !lo && norm_of_hi) ? 0 : ((master && hi && lo && !norm_of_hi) ? 1
+                     : ((master && hi && !lo && norm_of_hi) ? 2 : -1));
+    if (vec4 && mode >= 0 && norm2 && D == Dp && D % 128 == 0 && D <= 1024) {
+      const int ncf = D / 128;
+      dim3 grid((unsigned)blocks), block(256);
+#define FAST_LAUNCH(T16, NC, NORM, MODE)                                                                                  \
+      ingest_fast_kernel<T16, NC, NORM, MODE><<<grid, block, NORM ? warps_per_block * FastShape<NC>::WARP_FLOATS * 4 : 0, \
+                                                h->stream>>>(x, n, master, (T16*)hi, (T16*)lo, norm2)
+#define FAST_MODE(T16, NC, NORM)                                                                                          \
+      do { if (mode == 0) FAST_LAUNCH(T16, NC, NORM, 0); else if (mode == 1) FAST_LAUNCH(T16, NC, NORM, 1);               \
+           else FAST_LAUNCH(T16, NC, NORM, 2); } while (0)
+#define FAST_NORM(T16, NC) do { if (normalize) FAST_MODE(T16, NC, true); else FAST_MODE(T16, NC, false); } while (0)
+#define FAST_NC(T16)                                                                                                      \
+      do { switch (ncf) { case 1: FAST_NORM(T16, 1); break; case 2: FAST_NORM(T16, 2); break; case 3: FAST_NORM(T16, 3); break; \
+                          case 4: FAST_NORM(T16, 4); break; case 5: FAST_NORM(T16, 5); break; case 6: FAST_NORM(T16, 6); break; \
+                          case 7: FAST_NORM(T16, 7); break; default: FAST_NORM(T16, 8); break; } } while (0)
+      if (h->f16()) FAST_NC(__half); else FAST_NC(__nv_bfloat16);
+#undef FAST_NC
+#undef FAST_NORM
+#undef FAST_MODE
+#undef FAST_LAUNCH
+      h->launches++;
+      CUDA_TRY(h, cudaGetLastError());
+      return RDB_OK;
+    }
+  }
   // rows of up to 1024 floats are held in registers (one read, NC independent 128-bit loads per lane)
-  const int nc = !vec4 ? 0 : (Dp <= 256 ? 2 : (Dp <= 512 ? 4 : (Dp <= 1024 ? 8 : 0)));
+  int nc = !vec4 ? 0 : (Dp <= 256 ? 2 : (Dp <= 512 ? 4 : (Dp <= 1024 ? 8 : 0)));
+  if (normalize && h->np_nleaves > NP_MAX_REG_LEAVES) nc = 0;
   // normalising launches stage the row's squares / leaf sums of numpy's summation order in shared memory (ingest.cuh)
   const size_t smem = normalize ? size_t(warps_per_block) * ingest_warp_floats(h->np_nleaves, D, nc > 0) * 4 : 0;
   if (smem > 200 * 1024) return fail(h, RDB_ERR_UNSUPPORTED, "normalisation of rows this long is not supported");
   const NpPlan np = np_plan(h);
-#define INGEST_LAUNCH(T16, V4, NC)                                                                                        \
+#define INGEST_LAUNCH(T16, V4, NC, NORM)                                                                                  \
   do {                                                                                                                    \
     if (smem > 48 * 1024)                                                                                                 \
-      CUDA_TRY(h, cudaFuncSetAttribute(ingest_rows_kernel<T16, V4, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
-    ingest_rows_kernel<T16, V4, NC><<<grid, block, smem, s>>>(x, n, D, Dp, normalize, norm_of_hi, master, (T16*)hi,       \
-                                                              (T16*)lo, norm2, np);                                       \
+      CUDA_TRY(h, cudaFuncSetAttribute(ingest_rows_kernel<T16, V4, NC, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       int(smem)));                                                                       \
+    ingest_rows_kernel<T16, V4, NC, NORM><<<grid, block, smem, s>>>(x, n, D, Dp, norm_of_hi, master, (T16*)hi, (T16*)lo,  \
+                                                                    norm2, np);                                           \
   } while (0)
+#define INGEST_N(T16, V4, NC)                                                                             \
+  do { if (normalize) INGEST_LAUNCH(T16, V4, NC, true); else INGEST_LAUNCH(T16, V4, NC, false); } while (0)
 #define INGEST_T(T16)                                                                                     \
   do {                                                                                                    \
-    if (nc == 2) INGEST_LAUNCH(T16, true, 2); else if (nc == 4) INGEST_LAUNCH(T16, true, 4);              \
-    else if (nc == 8) INGEST_LAUNCH(T16, true, 8); else if (vec4) INGEST_LAUNCH(T16, true, 0);            \
-    else INGEST_LAUNCH(T16, false, 0);                                                                    \
+    if (nc == 2) INGEST_N(T16, true, 2); else if (nc == 4) INGEST_N(T16, true, 4);                        \
+    else if (nc == 8) INGEST_N(T16, true, 8); else if (vec4) INGEST_N(T16, true, 0);                      \
+    else INGEST_N(T16, false, 0);                                                                         \
   } while (0)
   if (h->f16()) INGEST_T(__half); else INGEST_T(__nv_bfloat16);
+#undef INGEST_N
 #undef INGEST_T
 #undef INGEST_LAUNCH
   h->launches++;
@@ -412,13 +448,15 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
 // ---- large k (128 < k <= 2048): exact fp32 keys of (query block x row chunk) written to HBM by the CUDA-core scorer's
 // DUMP form, exact radix select per query and chunk (select_large.cuh) -> one sorted list per chunk in
 // h->cand_key / h->cand_idx, laid out [nq][S][k] for merge_lists_kernel.  *L_out = S.
-int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
+int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out, int nterms = 1) {
   const int64_t N = h->n;
   // 16-bit stores: the keys come from the tensor cores (SelectDump epilogue of kernel 2); fp32 stores need exact fp32
   // keys -> CUDA-core scorer.  Option "largek_scorer" = 1 (CUDA cores) | 2 (tensor cores) overrides (tests).
+  // nterms == 3 (largek_split_search): approximate split-precision tensor-core keys of an fp32 store.
   bool use_tc = h->store != RDB_STORE_F32 && N >= kMinRowsTc;
   if (h->opt.largek_scorer == 1) use_tc = false;
   else if (h->opt.largek_scorer == 2 && h->store != RDB_STORE_F32 && N >= TC_BN) use_tc = true;
+  if (nterms == 3) use_tc = true;
   const int64_t align = use_tc ? TC_BN : SIMT_BN;
   int64_t rows = kLargeKRowsDefault;
   if (h->opt.largek_rows > 0) rows = h->opt.largek_rows;       // tests: force several chunks
@@ -444,13 +482,14 @@ int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out) {
       const int64_t row0 = int64_t(c) * rows, row_end = std::min<int64_t>(N, row0 + rows);
       const int len = int(row_end - row0);
       if (use_tc) {
-        const int cg = tc_cta_group(h, nqs, 1, h->d);
+        const int cg = tc_cta_group(h, nqs, nterms, h->d);
         const int nqg = (nqs + TC_BM * cg - 1) / (TC_BM * cg);
         const int tiles = (len + TC_BN - 1) / TC_BN;
         int tpc;
         const int units = choose_splits(nqg, tiles, h->num_sms / cg, 256, 4, &tpc);
         const char* qhi = static_cast<const char*>(qv.qhi) + size_t(q0) * h->dp * 2;
-        if ((rc = launch_tc(h, qhi, nullptr, nqs, k, cg, nqg, units, tpc, tiles, 1, nullptr, nullptr, 1, false, nullptr,
+        const char* qlo = nterms == 3 ? static_cast<const char*>(qv.qlo) + size_t(q0) * h->dp * 2 : nullptr;
+        if ((rc = launch_tc(h, qhi, qlo, nqs, k, cg, nqg, units, tpc, tiles, nterms, nullptr, nullptr, 1, false, nullptr,
                             scores, rows, int(row0), int(row_end)))) return rc;
       } else {
         const int tiles = (len + SIMT_BN - 1) / SIMT_BN;
@@ -658,6 +697,87 @@ int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mod
   return RDB_OK;
 }
 
+// ---- fp32 stores, k beyond the certified fused selectors (104 < k <= 2048): the same certificate idea on the dense-key
+// path.  Split-precision tensor-core keys (three MMA terms, |error| <= B) are dumped to HBM, the radix select keeps
+// kc = k + slack candidates per query, rerank_exact_large_kernel re-scores them exactly in fp32, sorts, and certifies
+// query q iff exact_key[k-1] > worst approximate candidate key + B (no row outside the candidate set can then belong to
+// the exact top-k).  Uncertified queries (ties at the boundary thicker than the slack) are searched by the exact
+// CUDA-core dense-key path.  Replaces the 37 TFLOP/s FFMA scorer for these searches.
+constexpr int kLargeKSlackMin = 32;
+int largek_slack(int k) { return std::max(kLargeKSlackMin, k / 8); }
+
+int largek_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mode, float* d_a, int64_t* d_i, float* d_l,
+                        const float* labels) {
+  const int nb = qv.nq, D = h->d;
+  const bool l2 = h->metric == RDB_METRIC_L2;
+  cudaStream_t s = h->stream;
+  const int kc = int(std::min<int64_t>(k + largek_slack(k), std::max<int64_t>(h->n, 1)));
+  int rc, L = 0;
+  if ((rc = run_largek(h, qv, kc, &L, 3))) return rc;
+  // approximate top-kc per query: the per-chunk lists folded into one (local ids, raw keys)
+  const float* ckey = h->cand_key.as<float>();
+  const void* cidx = h->cand_idx.p;
+  bool idx64 = false;
+  if (L > 1) {
+    CUDA_TRY(h, h->rr_key.ensure(size_t(nb) * kc * 4));
+    CUDA_TRY(h, h->rr_idx.ensure(size_t(nb) * kc * 8));
+    if ((rc = run_merge_local(h, nb, L, kc, kc, qv.qnorm, false, nullptr, h->rr_idx.as<int64_t>(), nullptr, 0, nullptr,
+                              h->rr_key.as<float>()))) return rc;
+    ckey = h->rr_key.as<float>(); cidx = h->rr_idx.p; idx64 = true;
+  }
+  CUDA_TRY(h, h->uncert.ensure(size_t(nb + 1) * 4));
+  int* ucount = h->uncert.as<int>();
+  int* ulist = ucount + 1;
+  CUDA_TRY(h, cudaMemsetAsync(ucount, 0, 4, s));
+  const int nks = (D + TC_BK - 1) / TC_BK;
+  const float accum = 2.0f * (float(nks * (TC_BK / 16) * 3) + 16.f) * 1.1920928955078125e-07f /*2^-23*/;
+  const float eps = 3.02f * 3.814697265625e-06f /*2^-18*/ + accum;
+  int n2 = 1;
+  while (n2 < kc) n2 <<= 1;
+  const size_t smem = size_t(n2) * 8;
+#define RERANK_LARGE(L2V, IDXT)                                                                                         \
+  rerank_exact_large_kernel<L2V, IDXT><<<nb, RERANK_LARGE_THREADS, smem, s>>>(                                          \
+      reinterpret_cast<const IDXT*>(cidx), ckey, nb, kc, k, qv.qf, h->master, h->ynorm, D, eps, qv.qnorm,               \
+      h->d_ynorm_max, h->n, h->id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l,   \
+      shard_mode ? d_a : nullptr, ulist, ucount)
+  if (l2) { if (idx64) RERANK_LARGE(true, long long); else RERANK_LARGE(true, int); }
+  else { if (idx64) RERANK_LARGE(false, long long); else RERANK_LARGE(false, int); }
+#undef RERANK_LARGE
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  int m = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&m, ucount, 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  h->last_uncertified += m;
+  if (m > 0) {
+    // exact CUDA-core dense keys + radix select for the queries the certificate refused
+    CUDA_TRY(h, h->fb_qf.ensure(size_t(m) * D * 4));
+    CUDA_TRY(h, h->fb_qnorm.ensure(size_t(m) * 4));
+    CUDA_TRY(h, h->fb_a.ensure(size_t(m) * k * 4));
+    CUDA_TRY(h, h->fb_i.ensure(size_t(m) * k * 8));
+    CUDA_TRY(h, h->fb_l.ensure(size_t(m) * k * 4));
+    gather_f32_rows_kernel<<<(m + 7) / 8, 256, 0, s>>>(qv.qf, ulist, m, D, h->fb_qf.as<float>());
+    h->launches++;
+    if ((rc = launch_ingest(h, h->fb_qf.as<float>(), m, 0, 0, nullptr, nullptr, nullptr, h->fb_qnorm.as<float>())))
+      return rc;
+    QueryView fv{h->fb_qf.as<float>(), nullptr, nullptr, h->fb_qnorm.as<float>(), m};
+    int Lf = 0;
+    const int saved = h->opt.largek_scorer;
+    h->opt.largek_scorer = 1;
+    rc = run_largek(h, fv, k, &Lf, 1);
+    h->opt.largek_scorer = saved;
+    if (rc) return rc;
+    if ((rc = run_merge_local(h, m, Lf, k, k, fv.qnorm, shard_mode, h->fb_a.as<float>(), h->fb_i.as<int64_t>(),
+                              h->fb_l.as<float>(), h->id_offset, labels, nullptr))) return rc;
+    scatter_results_kernel<<<(m * k + 255) / 256, 256, 0, s>>>(ulist, m, k, h->fb_a.as<float>(),
+                                                               h->fb_i.as<long long>(), h->fb_l.as<float>(), d_a,
+                                                               reinterpret_cast<long long*>(d_i), d_l);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  return RDB_OK;
+}
+
 // One search over the local shard.  shard_mode: out_a receives merge keys instead of distances.
 int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int normalize, int algo, bool shard_mode,
                 float* out_a, int64_t* out_idx, float* out_lbl, float* out_qnorm) {
@@ -667,7 +787,7 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   if (nq < 0 || k < 1 || (!q && nq > 0) || !out_a || !out_idx)
     return fail(h, RDB_ERR_INVALID, "search: bad arguments (nq >= 0, k >= 1, non-null buffers)");
   if (k > kMaxKLarge) return fail(h, RDB_ERR_UNSUPPORTED, "search: k > 2048 is not supported (the limit of faiss-gpu itself)");
-  const bool largek = k > kMaxK;     // dense keys + radix select (exact fp32 keys on CUDA cores)
+  bool largek = k > kMaxK;           // dense keys + radix select
   if (largek && algo == RDB_ALGO_STREAM)
     return fail(h, RDB_ERR_UNSUPPORTED, "search: the streaming scorer holds k <= 128 (use RDB_ALGO_AUTO for larger k)");
   if (nq == 0) return RDB_OK;
@@ -680,13 +800,19 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   const bool tc_ok = sixteen ? (k <= kMaxKTc && h->n >= TC_BN) : (k <= kMaxKSplit && h->n >= TC_BN);
   // small batches are a pure HBM stream of the stored rows: dedicated streaming scorer (exact fp32 for fp32 stores)
   const bool stream_ok = nq <= 4 && k <= 128 && h->n >= 1 && (sixteen || D % 4 == 0);
-  if (largek) algo = RDB_ALGO_SIMT;
+  // fp32 stores beyond the certified fused selectors (k > 104): split-precision tensor-core dense keys + exact re-rank
+  // + certificate (largek_split_search) unless the caller forces the exact CUDA-core scorer
+  const bool lk_split = !sixteen && k > kMaxKSplit && h->n >= kMinRowsTc && h->opt.largek_split && h->d % 4 == 0 &&
+                        (algo == RDB_ALGO_AUTO || algo == RDB_ALGO_TC) && k + largek_slack(k) <= SELK_CAP / 2 &&
+                        !(nq <= 4 && k <= kMaxK);      // tiny batches with k <= 128 stay on the streaming scorer
+  if (lk_split) { largek = true; algo = RDB_ALGO_TC; }
+  else if (largek) algo = RDB_ALGO_SIMT;
   if (algo == RDB_ALGO_AUTO) {
     algo = (stream_ok && h->n >= 4096) ? RDB_ALGO_STREAM : ((tc_ok && h->n >= kMinRowsTc) ? RDB_ALGO_TC : RDB_ALGO_SIMT);
   }
   if (algo == RDB_ALGO_STREAM && !stream_ok)
     return fail(h, RDB_ERR_UNSUPPORTED, "search: streaming scorer needs nq <= 4, k <= 128 (and D % 4 == 0 for fp32 stores)");
-  if (algo == RDB_ALGO_TC && !tc_ok)
+  if (algo == RDB_ALGO_TC && !tc_ok && !lk_split)
     return fail(h, RDB_ERR_UNSUPPORTED,
                 "search: tensor-core scorer needs ntotal >= 256 and k <= 128 (16-bit store) / k <= 104 (fp32 store)");
   const bool split = (algo == RDB_ALGO_TC) && !sixteen;
@@ -755,8 +881,9 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
                                   flag))) return rc;
       }
     } else {
-      // ---- fp32 store on the tensor cores: certified approximate pass(es) + exact fp32 re-rank (exact_split_search)
-      if ((rc = exact_split_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels))) return rc;
+      // ---- fp32 store on the tensor cores: certified approximate pass(es) + exact fp32 re-rank
+      if ((rc = lk_split ? largek_split_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels)
+                         : exact_split_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels))) return rc;
     }
     if (out_qnorm)
       CUDA_TRY(h, cudaMemcpyAsync(out_qnorm + b0, h->qnorm.p, size_t(nb) * 4,

@@ -27,17 +27,20 @@ def _lattice(N, D, Q, seed):
     return xb, xq
 
 
-@pytest.mark.parametrize("store,scorer", [("f32", "simt"), ("bf16", "tc"), ("bf16", "simt"), ("f16", "tc")])
+@pytest.mark.parametrize("store,scorer", [("f32", "simt"), ("f32", "split"), ("bf16", "tc"), ("bf16", "simt"), ("f16", "tc")])
 @pytest.mark.parametrize("metric_s", ["L2", "IP"])
 @pytest.mark.parametrize("k,rows", [(129, None), (200, 1024), (777, None), (2048, 2500)])
 def test_lattice_bit_exact_k_above_128(pkg, oracle, metric_s, k, rows, store, scorer):
     """rows = forced chunk length (option "largek_rows"): several per-chunk lists, ties straddling chunk borders.
-    scorer = where the dense keys come from: the tensor cores (16-bit stores) or the exact CUDA-core kernel."""
+    scorer = where the dense keys come from: the tensor cores (16-bit stores; fp32 stores: split precision + certified
+    exact re-rank) or the exact CUDA-core kernel."""
     xb, xq = _lattice(6001, 64, 70, 11)
     metric = pkg.METRIC_IP if metric_s == "IP" else pkg.METRIC_L2
     idx = pkg.FlatIndex(64, metric, store)
-    idx.set_option("largek_scorer", {"simt": 1, "tc": 2}[scorer])
-    idx.set_option("largek_split", 0)                       # fp32 stores: the exact CUDA-core keys are what is tested here
+    # fp32 stores: "simt" = exact CUDA-core dense keys, "split" = split-precision tensor-core keys + exact re-rank +
+    # certificate (the 300 identical rows outnumber the candidate slack, so those queries also walk the exact fallback)
+    idx.set_option("largek_scorer", {"simt": 1, "tc": 2, "split": 0}[scorer])
+    idx.set_option("largek_split", 1 if scorer == "split" else 0)
     if rows:
         idx.set_option("largek_rows", rows)
     idx.add(xb[:4000])
@@ -49,7 +52,9 @@ def test_lattice_bit_exact_k_above_128(pkg, oracle, metric_s, k, rows, store, sc
     np.testing.assert_array_equal(I, Ir)
     np.testing.assert_array_equal(D, Dr)
     assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (70, k)
-    assert idx.last_kernel_ms()[1] == scorer
+    assert idx.last_kernel_ms()[1] in {"split": ("tc", "simt")}.get(scorer, (scorer,))
+    if scorer == "split":
+        assert idx.last_uncertified >= 1            # the tie block cannot be certified: exact fallback exercised
 
 
 def test_all_rows_identical(pkg):

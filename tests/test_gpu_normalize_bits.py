@@ -20,6 +20,12 @@ def test_stored_rows_bit_equal_numpy(pkg, d):
     x = (rng.standard_normal((301, d)) * rng.uniform(1e-3, 50.0, size=(301, 1))).astype(np.float32)
     x[5] = 0.0                                                            # zero row stays zero (0 / 1e-12)
     x[6] = 1e-20                                                          # squares underflow: norm = 0 in numpy too
+    x[7] *= 1e-25                                                         # denormal squares / tiny quotients
+    x[8] *= 1e17                                                          # squares near overflow
+    x[9, ::3] = 0.0                                                       # sparse row (ReLU-like exact zeros)
+    x[10, ::2] = -0.0                                                     # negative zeros keep their sign
+    x[11, 0] = 3e38 if d > 1 else x[11, 0]                                # |x|^2 overflows: norm = inf, row -> 0
+    x[12] = np.where(np.arange(d) % 5 == 0, x[12] * 1e-30, x[12])         # tiny components next to normal ones
     idx = pkg.FlatIndex(d, pkg.METRIC_IP, "f32")
     idx.add(x[:100], normalize=True)
     import torch
