@@ -62,6 +62,8 @@ struct rdb_handle {
   float* ynorm = nullptr;
   float* ynmin32 = nullptr;       // [cap / 32] min |y|^2 over each aligned group of 32 rows (L2 coarse filter of the tcgen05 epilogue)
   float* labels = nullptr;
+  void* yext = nullptr;           // [cap][8] bf16: -|y|^2 in three exact bf16 parts (norm slice of the tcgen05 scorer; L2, bf16 operands)
+  float cur_hscale = 1.0f;        // scale of the 16-bit query copies of the search in flight (2 = norm-slice scorer)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
@@ -80,6 +82,8 @@ struct rdb_handle {
   int last_tier1_kc = 0;
   int64_t last_tier1_queries = 0, last_tier1_uncertified = 0;
   rdb::DevBuf lk_scores;          // large-k path: dense keys of one (query block x row chunk)
+  rdb::DevBuf qext;               // [nq][8] bf16 {1, 1, 1, 0, ...}: query side of the norm slice
+  int64_t qext_rows = 0;
   rdb::DevBuf dev_ctl;            // device-side control words of the stream-ordered certified search (counts, flags)
   void* pin = nullptr;            // pinned host staging of the small-batch path
   size_t pin_bytes = 0;
@@ -91,6 +95,8 @@ struct rdb_handle {
   bool has_hi() const { return true; }
   bool has_lo() const { return store == RDB_STORE_F32; }
   bool f16() const { return store == RDB_STORE_F16; }
+  // L2 keys straight from the tensor cores (norm slice): bf16 operands only (an f16 part cannot hold |y|^2 > 65504)
+  bool use_ext() const { return metric == RDB_METRIC_L2 && store != RDB_STORE_F16; }
 };
 
 namespace rdb {

@@ -39,6 +39,8 @@ int launch_simt_k(rdb_handle* h, const float* qf, const void* qhi, int nq, int n
 
 int launch_simt(rdb_handle* h, const float* qf, const void* qhi, int nq, int k, int nqt, int S, int rows_per_chunk,
                 float* ck, int* ci) {
+  if (h->store != RDB_STORE_F32 && h->cur_hscale != 1.0f)
+    return fail(h, RDB_ERR_INVALID, "internal: the CUDA-core scorer was handed queries staged for the tensor-core norm slice");
   const bool l2 = h->metric == RDB_METRIC_L2;
 #define SIMT_CASE(KT)                                                                          \
   return l2 ? launch_simt_k<KT, true>(h, qf, qhi, nq, nqt, S, rows_per_chunk, ck, ci, k)       \

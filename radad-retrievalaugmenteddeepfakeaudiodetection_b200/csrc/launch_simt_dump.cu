@@ -35,6 +35,8 @@ int launch_simt_dump_l2(rdb_handle* h, const QueryView& qv, int q0, int nq, int 
 
 int launch_simt_dump(rdb_handle* h, const QueryView& qv, int q0, int nq, int nqt, int S, int rows_per_chunk, int row0,
                      int row_end, float* dump, long long pitch) {
+  if (h->store != RDB_STORE_F32 && h->cur_hscale != 1.0f)
+    return fail(h, RDB_ERR_INVALID, "internal: the CUDA-core scorer was handed queries staged for the tensor-core norm slice");
   return h->metric == RDB_METRIC_L2
              ? launch_simt_dump_l2<true>(h, qv, q0, nq, nqt, S, rows_per_chunk, row0, row_end, dump, pitch)
              : launch_simt_dump_l2<false>(h, qv, q0, nq, nqt, S, rows_per_chunk, row0, row_end, dump, pitch);

@@ -37,9 +37,10 @@ int launch_tc_cg_t(rdb_handle* h, TcParams& p, int k) {
   if ((rc = encode_2d(h, &p.tmap_y[0], h->hi, h->n, h->d, h->dp, TC_BN / CG))) return rc;
   if (p.nterms == 3) { if ((rc = encode_2d(h, &p.tmap_y[1], h->lo, h->n, h->d, h->dp, TC_BN / CG))) return rc; }
   else p.tmap_y[1] = p.tmap_y[0];
+  if (p.ext && (rc = encode_2d(h, &p.tmap_yx, h->yext, h->n, 8, 8, TC_BN / CG))) return rc;
   p.idesc = make_idesc_f16(TC_BM * CG, TC_BN, h->f16() ? 0 : 1);
   const int groups = std::min(p.num_units, h->num_sms / CG);
-  const bool l2 = h->metric == RDB_METRIC_L2;
+  const bool l2 = h->metric == RDB_METRIC_L2 && !p.ext;     // norm slice: the accumulator already is the L2 key
   if (p.dump)       return l2 ? launch_tc_kernel<SelectDump, true, CG>(h, p, groups) : launch_tc_kernel<SelectDump, false, CG>(h, p, groups);
   if (k <= 16)      return l2 ? launch_tc_kernel<SelectSmall<16>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<16>, false, CG>(h, p, groups);
   else if (k <= 32) return l2 ? launch_tc_kernel<SelectSmall<32>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<32>, false, CG>(h, p, groups);

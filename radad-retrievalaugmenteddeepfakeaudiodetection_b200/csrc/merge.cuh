@@ -449,6 +449,30 @@ static __global__ void ynorm_min32_kernel(const float* __restrict__ ynorm, long 
   if ((threadIdx.x & 31) == 0) out[g0 + w] = m;
 }
 
+// Norm slice of the tcgen05 scorer (score_tc.cuh, TcParams::ext): yext[row] = {p1, p2, p3, 0, 0, 0, 0, 0} with
+// p1 + p2 + p3 == -|y|^2 EXACTLY (three round-to-nearest bf16 parts hold the 24 significant bits of an fp32), and the
+// constant query side {1, 1, 1, 0, ...}.
+static __global__ void yext_fill_kernel(const float* __restrict__ ynorm, long long m, uint4* __restrict__ yext) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float n = -ynorm[i];
+  const __nv_bfloat16 p1 = __float2bfloat16_rn(n);
+  const float r1 = n - __bfloat162float(p1);
+  const __nv_bfloat16 p2 = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(p2);
+  const __nv_bfloat16 p3 = __float2bfloat16_rn(r2);
+  uint4 o;
+  o.x = uint32_t(__bfloat16_as_ushort(p1)) | (uint32_t(__bfloat16_as_ushort(p2)) << 16);
+  o.y = uint32_t(__bfloat16_as_ushort(p3));
+  o.z = 0u; o.w = 0u;
+  yext[i] = o;
+}
+static __global__ void qext_fill_kernel(long long n, uint4* __restrict__ qext) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  qext[i] = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);       // bf16 1.0 = 0x3F80
+}
+
 // max over rows of |y|^2 (positive floats order like their bit patterns) -- feeds the re-rank certificate
 static __global__ void ynorm_max_kernel(const float* __restrict__ ynorm, long long n, float* __restrict__ out) {
   float m = 0.f;

@@ -40,13 +40,15 @@ int grow_to(rdb_handle* h, int64_t need, bool exact = false) {
   if (cap >= (int64_t(1) << 31)) return fail(h, RDB_ERR_UNSUPPORTED, "more than 2^31-1 rows per shard");
   const size_t D = h->d, Dp = h->dp;
   float* master = nullptr; void* hi = nullptr; void* lo = nullptr; float* ynorm = nullptr; float* ynmin32 = nullptr;
-  auto cleanup = [&] { cudaFree(master); cudaFree(hi); cudaFree(lo); cudaFree(ynorm); cudaFree(ynmin32); cudaGetLastError(); };
+  void* yext = nullptr;
+  auto cleanup = [&] { cudaFree(master); cudaFree(hi); cudaFree(lo); cudaFree(ynorm); cudaFree(ynmin32); cudaFree(yext); cudaGetLastError(); };
   cudaError_t e = cudaSuccess;
   if (h->has_master()) e = cudaMalloc(&master, size_t(cap) * D * 4);
   if (e == cudaSuccess) e = cudaMalloc(&hi, size_t(cap) * Dp * 2);
   if (e == cudaSuccess && h->has_lo()) e = cudaMalloc(&lo, size_t(cap) * Dp * 2);
   if (e == cudaSuccess) e = cudaMalloc(&ynorm, size_t(cap) * 4);
   if (e == cudaSuccess) e = cudaMalloc(&ynmin32, size_t(cap / 32) * 4);
+  if (e == cudaSuccess && h->use_ext()) e = cudaMalloc(&yext, size_t(cap) * 16);
   if (e != cudaSuccess) {
     cleanup();
     return fail(h, RDB_ERR_NOMEM, std::string("device allocation for ") + std::to_string(cap) + " rows failed: " +
@@ -62,10 +64,11 @@ int grow_to(rdb_handle* h, int64_t need, bool exact = false) {
   cudaMemsetAsync(ynorm + h->n, 0, size_t(cap - h->n) * 4, s);
   cudaMemsetAsync(ynmin32, 0, size_t(cap / 32) * 4, s);
   if (h->n > 0) cudaMemcpyAsync(ynmin32, h->ynmin32, size_t((h->n + 31) / 32) * 4, cudaMemcpyDeviceToDevice, s);
+  if (h->n > 0 && yext) cudaMemcpyAsync(yext, h->yext, size_t(h->n) * 16, cudaMemcpyDeviceToDevice, s);
   cudaError_t es = cudaStreamSynchronize(s);
   if (es != cudaSuccess) { cleanup(); return fail(h, RDB_ERR_CUDA, std::string("grow copy: ") + cudaGetErrorString(es)); }
-  cudaFree(h->master); cudaFree(h->hi); cudaFree(h->lo); cudaFree(h->ynorm); cudaFree(h->ynmin32);
-  h->master = master; h->hi = hi; h->lo = lo; h->ynorm = ynorm; h->ynmin32 = ynmin32; h->cap = cap;
+  cudaFree(h->master); cudaFree(h->hi); cudaFree(h->lo); cudaFree(h->ynorm); cudaFree(h->ynmin32); cudaFree(h->yext);
+  h->master = master; h->hi = hi; h->lo = lo; h->ynorm = ynorm; h->ynmin32 = ynmin32; h->yext = yext; h->cap = cap;
   return RDB_OK;
 }
 
@@ -98,7 +101,7 @@ NpPlan np_plan(rdb_handle* h) { return NpPlan{h->np_tab.as<int>(), h->np_nleaves
 
 // launch the fused ingest kernel (also used to prepare queries)
 int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int norm_of_hi, float* master, void* hi,
-                  void* lo, float* norm2) {
+                  void* lo, float* norm2, float hscale = 1.0f) {
   if (n <= 0) return RDB_OK;
   const int D = h->d, Dp = h->dp;
   const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
@@ -115,7 +118,7 @@ int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int n
       dim3 grid((unsigned)blocks), block(256);
 #define FAST_LAUNCH(T16, NC, NORM, MODE)                                                                                  \
       ingest_fast_kernel<T16, NC, NORM, MODE><<<grid, block, NORM ? warps_per_block * FastShape<NC>::WARP_FLOATS * 4 : 0, \
-                                                h->stream>>>(x, n, master, (T16*)hi, (T16*)lo, norm2)
+                                                h->stream>>>(x, n, master, (T16*)hi, (T16*)lo, norm2, hscale)
 #define FAST_MODE(T16, NC, NORM)                                                                                          \
       do { if (mode == 0) FAST_LAUNCH(T16, NC, NORM, 0); else if (mode == 1) FAST_LAUNCH(T16, NC, NORM, 1);               \
            else FAST_LAUNCH(T16, NC, NORM, 2); } while (0)
@@ -147,7 +150,7 @@ int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int n
       CUDA_TRY(h, cudaFuncSetAttribute(ingest_rows_kernel<T16, V4, NC, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        int(smem)));                                                                       \
     ingest_rows_kernel<T16, V4, NC, NORM><<<grid, block, smem, s>>>(x, n, D, Dp, norm_of_hi, master, (T16*)hi, (T16*)lo,  \
-                                                                    norm2, np);                                           \
+                                                                    norm2, np, hscale);                                   \
   } while (0)
 #define INGEST_N(T16, V4, NC)                                                                             \
   do { if (normalize) INGEST_LAUNCH(T16, V4, NC, true); else INGEST_LAUNCH(T16, V4, NC, false); } while (0)
@@ -217,7 +220,19 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
   if (!keep_gthr) CUDA_TRY(h, cudaMemsetAsync(h->gthr.p, 0, size_t(nq) * 4, h->stream));
   p.tile_step = tile_step; p.run_if = run_if;
   p.nstages = std::max(2, h->opt.tc_stages);
-  p.astat = (nterms == 1 && h->d <= TcCfg<1>::ASTAT_MAX_KS * TC_BK && h->opt.tc_query_stationary) ? 1 : 0;
+  // norm slice (L2 keys straight from the accumulator): the queries of this search were staged as 2 q (search_impl)
+  p.ext = (h->cur_hscale == 2.0f && h->yext) ? 1 : 0;
+  if (p.ext) {
+    if (h->qext_rows < nq) {
+      const int64_t rows = round_up(std::max<int64_t>(nq, 4096), 4096);
+      CUDA_TRY(h, h->qext.ensure(size_t(rows) * 16));
+      qext_fill_kernel<<<unsigned((rows + 255) / 256), 256, 0, h->stream>>>(rows, h->qext.as<uint4>());
+      h->launches++;
+      h->qext_rows = rows;
+    }
+    if ((rc = encode_2d(h, &p.tmap_qx, h->qext.p, nq, 8, 8, TC_BM))) return rc;
+  }
+  p.astat = (nterms == 1 && (h->d + TC_BK - 1) / TC_BK + p.ext <= TcCfg<1>::ASTAT_MAX_KS && h->opt.tc_query_stationary) ? 1 : 0;
   p.gthr = (S > 1 || TC_LISTS > 1) ? h->gthr.as<uint32_t>() : nullptr;
   p.nq = nq; p.N = int(h->n); p.D = h->d;
   if (dump) { p.dump = dump; p.dump_pitch = dump_pitch; p.row_base = row_base; p.N = row_end; }   // k > 128: rows [row_base, row_end)
@@ -448,15 +463,19 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
 // ---- large k (128 < k <= 2048): exact fp32 keys of (query block x row chunk) written to HBM by the CUDA-core scorer's
 // DUMP form, exact radix select per query and chunk (select_large.cuh) -> one sorted list per chunk in
 // h->cand_key / h->cand_idx, laid out [nq][S][k] for merge_lists_kernel.  *L_out = S.
+bool largek_use_tc(const rdb_handle* h, int nterms) {
+  bool use_tc = h->store != RDB_STORE_F32 && h->n >= kMinRowsTc;
+  if (h->opt.largek_scorer == 1) use_tc = false;
+  else if (h->opt.largek_scorer == 2 && h->store != RDB_STORE_F32 && h->n >= TC_BN) use_tc = true;
+  return nterms == 3 ? true : use_tc;
+}
+
 int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out, int nterms = 1) {
   const int64_t N = h->n;
   // 16-bit stores: the keys come from the tensor cores (SelectDump epilogue of kernel 2); fp32 stores need exact fp32
   // keys -> CUDA-core scorer.  Option "largek_scorer" = 1 (CUDA cores) | 2 (tensor cores) overrides (tests).
   // nterms == 3 (largek_split_search): approximate split-precision tensor-core keys of an fp32 store.
-  bool use_tc = h->store != RDB_STORE_F32 && N >= kMinRowsTc;
-  if (h->opt.largek_scorer == 1) use_tc = false;
-  else if (h->opt.largek_scorer == 2 && h->store != RDB_STORE_F32 && N >= TC_BN) use_tc = true;
-  if (nterms == 3) use_tc = true;
+  const bool use_tc = largek_use_tc(h, nterms);
   const int64_t align = use_tc ? TC_BN : SIMT_BN;
   int64_t rows = kLargeKRowsDefault;
   if (h->opt.largek_rows > 0) rows = h->opt.largek_rows;       // tests: force several chunks
@@ -684,8 +703,8 @@ int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mod
   gather_f32_rows_kernel<<<(m + 7) / 8, 256, 0, s>>>(qv.qf, ulist, m, D, h->t2_qf.as<float>());
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
-  if ((rc = launch_ingest(h, h->t2_qf.as<float>(), m, 0, 0, nullptr, h->t2_qhi.p, h->t2_qlo.p, h->t2_qnorm.as<float>())))
-    return rc;
+  if ((rc = launch_ingest(h, h->t2_qf.as<float>(), m, 0, 0, nullptr, h->t2_qhi.p, h->t2_qlo.p, h->t2_qnorm.as<float>(),
+                          h->cur_hscale))) return rc;
   QueryView sub{h->t2_qf.as<float>(), h->t2_qhi.p, h->t2_qlo.p, h->t2_qnorm.as<float>(), m};
   if ((rc = split3_search(h, sub, k, shard_mode, h->t2_a.as<float>(), h->t2_i.as<int64_t>(), h->t2_l.as<float>(), labels,
                           false))) return rc;
@@ -819,6 +838,9 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   const float* labels = (h->labels && h->nlabels == h->n) ? h->labels : nullptr;
   cudaStream_t s = h->stream;
   h->last_uncertified = 0; h->last_tier1_queries = 0; h->last_tier1_uncertified = 0;
+  // L2 on bf16 operands: when the tensor cores consume the 16-bit query copies they are staged as 2 q (norm slice)
+  const bool tc_consumer = algo == RDB_ALGO_TC || (largek && sixteen && largek_use_tc(h, 1));
+  h->cur_hscale = (tc_consumer && h->use_ext() && h->yext) ? 2.0f : 1.0f;
   if (algo == RDB_ALGO_STREAM)
     return search_stream(h, q, int(nq), k, mem, normalize, shard_mode, out_a, out_idx, out_lbl, out_qnorm);
 
@@ -837,7 +859,8 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
     QueryView qv{nullptr, nullptr, nullptr, h->qnorm.as<float>(), nb};
     if (sixteen) {
       CUDA_TRY(h, h->qhi.ensure(size_t(nb) * Dp * 2));
-      if ((rc = launch_ingest(h, qsrc, nb, normalize, 1, nullptr, h->qhi.p, nullptr, h->qnorm.as<float>()))) return rc;
+      if ((rc = launch_ingest(h, qsrc, nb, normalize, 1, nullptr, h->qhi.p, nullptr, h->qnorm.as<float>(), h->cur_hscale)))
+        return rc;
       qv.qhi = h->qhi.p;
     } else {
       CUDA_TRY(h, h->qf.ensure(size_t(nb) * D * 4));
@@ -846,7 +869,7 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
         CUDA_TRY(h, h->qlo.ensure(size_t(nb) * Dp * 2));
       }
       if ((rc = launch_ingest(h, qsrc, nb, normalize, 0, h->qf.as<float>(), split ? h->qhi.p : nullptr,
-                              split ? h->qlo.p : nullptr, h->qnorm.as<float>()))) return rc;
+                              split ? h->qlo.p : nullptr, h->qnorm.as<float>(), h->cur_hscale))) return rc;
       qv.qf = h->qf.as<float>(); qv.qhi = h->qhi.p; qv.qlo = h->qlo.p;
     }
     // ---- output views (device scratch when the caller's buffers are on the host)
@@ -908,7 +931,7 @@ const DevBufMember kScratch[] = {
     &rdb_handle::fb_i, &rdb_handle::fb_l, &rdb_handle::gthr, &rdb_handle::tcsync, &rdb_handle::stream_ctl,
     &rdb_handle::fkey, &rdb_handle::fidx, &rdb_handle::lk_scores, &rdb_handle::uncert1, &rdb_handle::t2_qf,
     &rdb_handle::t2_qhi, &rdb_handle::t2_qlo, &rdb_handle::t2_qnorm, &rdb_handle::t2_a, &rdb_handle::t2_i,
-    &rdb_handle::t2_l, &rdb_handle::dev_ctl};
+    &rdb_handle::t2_l, &rdb_handle::dev_ctl, &rdb_handle::qext};
 
 }  // namespace
 
@@ -961,7 +984,7 @@ int rdb_destroy(rdb_handle* h) {
   {
     DeviceGuard dg(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->master); cudaFree(h->hi); cudaFree(h->lo); cudaFree(h->ynorm); cudaFree(h->ynmin32); cudaFree(h->labels);
+    cudaFree(h->master); cudaFree(h->hi); cudaFree(h->lo); cudaFree(h->ynorm); cudaFree(h->ynmin32); cudaFree(h->yext); cudaFree(h->labels);
     cudaFree(h->d_ynorm_max);
     for (auto m : kScratch) (h->*m).release();
     h->np_tab.release();
@@ -1039,7 +1062,11 @@ int rdb_add(rdb_handle* h, const float* x, int64_t n, int mem, int normalize) {
       // minima of the (aligned) 32-row groups these rows touch; unfilled rows of the last group still hold |y|^2 = 0,
       // which only loosens the bound until they are added
       const int64_t g0 = row0 / 32, g1 = (row0 + m - 1) / 32;
-      ynorm_min32_kernel<<<unsigned((g1 - g0 + 1 + 7) / 8), 256, 0, h->stream>>>(h->ynorm, g0, g1 - g0 + 1, h->ynmin32);
+      if (h->yext)     // bf16 operands: the L2 key comes out of the accumulator (norm slice), no epilogue filter needed
+        yext_fill_kernel<<<unsigned((m + 255) / 256), 256, 0, h->stream>>>(h->ynorm + row0, m,
+                                                                            static_cast<uint4*>(h->yext) + row0);
+      else
+        ynorm_min32_kernel<<<unsigned((g1 - g0 + 1 + 7) / 8), 256, 0, h->stream>>>(h->ynorm, g0, g1 - g0 + 1, h->ynmin32);
     }
     h->launches += 2;
     if (mem == RDB_MEM_HOST) CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // staging buffer reuse
@@ -1287,7 +1314,7 @@ int rdb_mem_info(rdb_handle* h, size_t* index_bytes, size_t* scratch_bytes, size
     CUDA_TRY(h, cudaMemGetInfo(&fr, &tot));
     if (h->has_master()) ib += size_t(h->cap) * h->d * 4;
     ib += size_t(h->cap) * h->dp * 2 * (h->has_lo() ? 2 : 1);
-    ib += size_t(h->cap) * 4 + size_t(h->cap / 32) * 4 + size_t(h->nlabels) * 4;
+    ib += size_t(h->cap) * 4 + size_t(h->cap / 32) * 4 + size_t(h->nlabels) * 4 + (h->yext ? size_t(h->cap) * 16 : 0);
     for (auto m : kScratch) sb += (h->*m).bytes;
     sb += h->pin_bytes;
   } else {
@@ -1308,6 +1335,7 @@ int rdb_release_scratch(rdb_handle* h) {
   for (auto m : kScratch) (h->*m).release();
   if (h->pin) cudaFreeHost(h->pin);
   h->pin = nullptr; h->pin_bytes = 0;
+  h->qext_rows = 0;
   h->ev_valid = false;
   cudaGetLastError();
   return RDB_OK;

@@ -59,6 +59,14 @@ template <int CG> constexpr size_t tc_smem_bytes() { return TcCfg<CG>::SMEM; }
 struct TcParams {
   CUtensorMap tmap_q[2];  // [0] = hi, [1] = lo   bf16/f16 [nq, D], box {64, 128}, SWIZZLE_128B
   CUtensorMap tmap_y[2];  // [0] = hi, [1] = lo   bf16/f16 [N,  D], box {64, 256 / CG}, SWIZZLE_128B
+  // Norm slice (L2 metric on bf16 operands, `ext` != 0): one extra K-slice per tile whose first three columns hold
+  // -|y|^2 split into three bf16 parts on the database side and 1, 1, 1 on the query side, while the queries are staged
+  // as 2 q.  The accumulator then IS the L2 key 2 q.y - |y|^2 (fp32 accumulation, the split is exact), and the epilogue
+  // is the inner-product one: no per-column fix-up, no norm loads, no coarse filter.  Both maps are [rows, 8] arrays
+  // read with the regular {64, rows} box: columns 8..63 are out of bounds and zero-filled by TMA (16 bytes of traffic
+  // per row); only the first K = 16 MMA of the slice is issued.
+  CUtensorMap tmap_qx, tmap_yx;
+  int ext;
   const float* ynorm;     // [N] |y|^2 (L2 only)
   const float* ynmin32;   // [N / 32] min |y|^2 per aligned 32-row group (L2 only): coarse filter
   float* cand_key;        // [nq][S * TC_LISTS][kout]
@@ -279,6 +287,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_q[0]);
     tma_prefetch_desc(&p.tmap_y[0]);
+    if (p.ext) { tma_prefetch_desc(&p.tmap_qx); tma_prefetch_desc(&p.tmap_yx); }
     for (int s = 0; s < Cfg::MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], TC_EPI_WARPS * CG); }
     mbar_init(afull_bar, 1); mbar_init(aempty_bar, 1);
@@ -317,13 +326,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
           // the unit's query tile: loaded once, after every MMA of the previous unit has retired
           mbar_wait(aempty_bar, aphase ^ 1);
           if (CG == 2) {
-            if (rank == 0) mbar_expect_tx(afull_bar, 2 * nks * TC_A_BYTES);
+            if (rank == 0) mbar_expect_tx(afull_bar, 2 * (nks + p.ext) * TC_A_BYTES);
             for (int ks = 0; ks < nks; ++ks)
               tma_load_2d_pair(smem + ks * TC_A_BYTES, &p.tmap_q[0], afull_bar, ks * TC_BK, qtile * TC_BM, p.hint_q);
+            if (p.ext) tma_load_2d_pair(smem + nks * TC_A_BYTES, &p.tmap_qx, afull_bar, 0, qtile * TC_BM, p.hint_q);
           } else {
-            mbar_expect_tx(afull_bar, nks * TC_A_BYTES);
+            mbar_expect_tx(afull_bar, (nks + p.ext) * TC_A_BYTES);
             for (int ks = 0; ks < nks; ++ks)
               tma_load_2d(smem + ks * TC_A_BYTES, &p.tmap_q[0], afull_bar, ks * TC_BK, qtile * TC_BM, p.hint_q);
+            if (p.ext) tma_load_2d(smem + nks * TC_A_BYTES, &p.tmap_qx, afull_bar, 0, qtile * TC_BM, p.hint_q);
           }
           aphase ^= 1;
         }
@@ -347,24 +358,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
               if (g + 1 >= p.sync_window) seen = ld_relaxed_u32(ctr + g + 1 - p.sync_window);   // for the next check
             }
           }
-          for (int term = 0; term < p.nterms; ++term) {
-            // nterms == 1: (hi, hi).  nterms == 3: (lo, hi), (hi, lo), (hi, hi) -- small terms first.
+          for (int term = 0; term <= p.nterms; ++term) {
+            // nterms == 1: (hi, hi).  nterms == 3: (lo, hi), (hi, lo), (hi, hi) -- small terms first.  term == nterms:
+            // the norm slice (ext), one slice from the [rows, 8] side arrays.
+            const bool xs = term == p.nterms;
+            if (xs && !p.ext) break;
             const int qsel = (p.nterms == 3 && term == 0) ? 1 : 0;
             const int ysel = (p.nterms == 3 && term == 1) ? 1 : 0;
-            for (int ks = 0; ks < nks; ++ks) {
+            const CUtensorMap* mq = xs ? &p.tmap_qx : &p.tmap_q[qsel];
+            const CUtensorMap* my = xs ? &p.tmap_yx : &p.tmap_y[ysel];
+            const int nsl = xs ? 1 : nks;
+            for (int ks = 0; ks < nsl; ++ks) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = ring + stage * ring_stride;
               const int slot_bytes = astat ? Cfg::B_BYTES : Cfg::STAGE_BYTES;
               if (CG == 2) {
                 // both CTAs' bytes complete on the leader's barrier; the leader posts the expectation for both
                 if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * slot_bytes);
-                if (!astat) tma_load_2d_pair(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
-                tma_load_2d_pair(sa + b_off, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK,
+                if (!astat) tma_load_2d_pair(sa, mq, &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
+                tma_load_2d_pair(sa + b_off, my, &full_bar[stage], ks * TC_BK,
                                  p.row_base + t * p.tile_step * TC_BN + rank * Cfg::B_ROWS, p.hint_y);
               } else {
                 mbar_expect_tx(&full_bar[stage], slot_bytes);
-                if (!astat) tma_load_2d(sa, &p.tmap_q[qsel], &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
-                tma_load_2d(sa + b_off, &p.tmap_y[ysel], &full_bar[stage], ks * TC_BK, p.row_base + t * p.tile_step * TC_BN,
+                if (!astat) tma_load_2d(sa, mq, &full_bar[stage], ks * TC_BK, qtile * TC_BM, p.hint_q);
+                tma_load_2d(sa + b_off, my, &full_bar[stage], ks * TC_BK, p.row_base + t * p.tile_step * TC_BN,
                             p.hint_y);
               }
               if (++stage == nst) { stage = 0; phase ^= 1; }
@@ -387,15 +404,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + uint32_t(acc * TC_BN);
-          const int nslices = nks * p.nterms;
+          const int nslices = nks * p.nterms + p.ext;
           for (int ks = 0; ks < nslices; ++ks) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(ring + stage * ring_stride);
             const uint64_t da = make_sw128_kmajor_desc(astat ? smem_u32(smem + ks * TC_A_BYTES) : sa);
             const uint64_t db = make_sw128_kmajor_desc(sa + b_off);
+            const int nkk = (p.ext && ks == nslices - 1) ? 1 : TC_BK / 16;   // norm slice: columns 0..2 only
 #pragma unroll
             for (int kk = 0; kk < TC_BK / 16; ++kk) {
+              if (kk >= nkk) break;
               // +32 bytes per K=16 step inside the 128-byte swizzle atom (descriptor address unit = 16 B)
               if (CG == 2) umma_f16_ss_pair(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), p.idesc, (ks | kk) != 0);
               else umma_f16_ss(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), p.idesc, (ks | kk) != 0);

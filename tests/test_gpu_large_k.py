@@ -97,7 +97,8 @@ def test_gaussian_vs_oracle_k_above_128(pkg, oracle, case):
         floor = 1e-6
     st = oracle.compare_topk(D, I, Dr, Ir, lambda ids: ref.exact_scores(qn, ids), metric, tol=tol, abs_floor=floor)
     assert st["recall"] >= 0.999, st
-    assert idx.last_kernel_ms()[1] == ("simt" if store == "f32" else "tc")
+    # fp32 stores: split-precision tensor-core keys + certified exact re-rank (exact CUDA-core keys when D % 4 != 0)
+    assert idx.last_kernel_ms()[1] == ("simt" if (store == "f32" and Dm % 4) else "tc")
     # sorted best-first, no duplicate ids
     assert np.all(np.diff(D, axis=1) >= 0) if metric == pkg.METRIC_L2 else np.all(np.diff(D, axis=1) <= 0)
     assert all(len(set(r.tolist())) == k for r in I)
