@@ -171,7 +171,7 @@ int rdb_truncate(rdb_handle* h, int64_t n_keep);
 
 /* Per-handle tuning / test options; every default is the production path and the library never reads the process
  * environment.  Names: "tc_cta_group" (0 auto | 1 | 2), "tc_lockstep" (window in groups of 8 tiles, 0 = off),
- * "tc_lockstep_spins", "tc_stages", "tc_query_stationary" (0 | 1), "tc_pivot" (0 | 1), "tier1" (0 | 1), "tier1_kc"
+ * "tc_lockstep_spins", "tc_stages", "tc_chunks" (0 = cost model), "tc_query_stationary" (0 | 1), "tc_pivot" (0 | 1), "tier1" (0 | 1), "tier1_kc"
  * (0 auto | 32 | 64 | 128), "largek_scorer" (0 auto | 1 CUDA cores | 2 tensor cores), "largek_rows" (rows per dense key
  * chunk, 0 = default), "largek_sample" (0 | 1), "largek_split" (0 | 1: split-precision tensor-core keys for fp32 stores).
  * Unknown names fail with RDB_ERR_INVALID.  No reference counterpart. */
@@ -179,6 +179,11 @@ int rdb_set_option(rdb_handle* h, const char* name, int64_t value);
 
 /* Number of kernels this handle has launched since creation (bench.py's `gpu_launches`). */
 int64_t rdb_launch_count(rdb_handle* h);
+
+/* How often a call on this handle blocked the host on its stream (cudaStreamSynchronize).  RDB_MEM_HOST calls block by
+ * contract (results land in the caller's buffers); RDB_MEM_DEVICE searches with k <= 104 must not -- every data-dependent
+ * step of the certified fp32 search is sized on the device (diagnostic; no reference counterpart). */
+int64_t rdb_host_sync_count(rdb_handle* h);
 
 /* Elapsed milliseconds (CUDA events on the handle's stream) of the scoring kernel of the last search, and
  * its name ("tc" / "simt"); 0 on success. */

@@ -65,6 +65,7 @@ SIGNATURES = {
     "rdb_truncate": (c_int, [_h, c_int64]),
     "rdb_set_option": (c_int, [_h, c_char_p, c_int64]),
     "rdb_launch_count": (c_int64, [_h]),
+    "rdb_host_sync_count": (c_int64, [_h]),
     "rdb_last_kernel_ms": (c_int, [_h, POINTER(c_float), POINTER(c_int), POINTER(c_int)]),
     "rdb_last_uncertified": (c_int64, [_h]),
     "rdb_last_tier1": (c_int, [_h, POINTER(c_int64), POINTER(c_int64), POINTER(c_int)]),

@@ -218,6 +218,19 @@ struct SelectDump {
 };
 
 // ----------------------------------------------------------------------------------------------
+// Device-side work plan.  The certified search of fp32 stores re-searches only the queries a cheaper pass could not
+// certify; how many there are is known on the DEVICE only.  Instead of reading the count back (a host round trip per
+// batch), the follow-up launches are always enqueued with grids sized for the worst case and read their real extent --
+// number of queries, the chunking of the database that fills the machine for that many queries -- from a DevPlan a
+// one-thread planning kernel derived from the count.  nq == 0 makes every consumer return at once.
+// ----------------------------------------------------------------------------------------------
+struct DevPlan {
+  int nq;                         // queries of this stage
+  int nqg, S, tpc, num_units, L;  // tensor-core scorer: query-tile groups, chunks, tiles per chunk, units, lists per query
+  int s_nqt, s_S, s_rows, s_units, s_L;   // CUDA-core scorer: query tiles, chunks, rows per chunk, units, lists per query
+};
+
+// ----------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA, tcgen05 (Blackwell 5th-gen tensor cores, TMEM).
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

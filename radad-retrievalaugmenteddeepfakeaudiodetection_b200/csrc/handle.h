@@ -42,6 +42,7 @@ struct rdb_options {
   int tc_stages = 64;            // ring slots used (clamped to what the kernel has)
   int tc_query_stationary = 1;   // D <= 256 one-term searches keep the query tile resident
   int tc_pivot = 1;              // sampled admission bound for 32 < k <= 128
+  int tc_chunks = 0;             // 0 = cost model, else force the number of database chunks per query tile (A/B)
   int tc_debug = 0;              // RDB_PROFILING builds only: 1 = skip the selection work (results invalid)
   int tier1 = 1;                 // fp32 stores: one-term certified pass first
   int tier1_kc = 0;              // 0 = auto, else force 32 | 64 | 128 candidates
@@ -72,6 +73,7 @@ struct rdb_handle {
   int tc_cg = 1, tc_nqg = 0, tc_S = 0, tc_tpc = 0, tc_ntiles = 0;
   int num_sms = 148;
   int64_t launches = 0;
+  int64_t host_syncs = 0;         // times a call blocked the host on the stream (rdb_host_sync_count)
   std::string err;
   std::mutex mu;
   // scratch
@@ -81,13 +83,19 @@ struct rdb_handle {
   int t1_level = 0, t1_hold = 0;  // adaptive tier-1 level (exact_split_search) and batches until it decays
   int last_tier1_kc = 0;
   int64_t last_tier1_queries = 0, last_tier1_uncertified = 0;
+  // counters of the certified search in flight (read back asynchronously: counts_post / counts_resolve)
+  int* pin_counts = nullptr;      // pinned host: [0] tier-1 uncertified, [1] exact-fallback queries
+  cudaEvent_t ev_counts = nullptr;
+  bool counts_pending = false, pending_tier1 = false;
+  int pending_nb = 0, pending_kc1 = 0;
   rdb::DevBuf lk_scores;          // large-k path: dense keys of one (query block x row chunk)
+  rdb::DevBuf qres, res_stage;    // |q - q_hi|^2 per query / per-row residuals of the rows being added (fp32 stores)
   rdb::DevBuf qext;               // [nq][8] bf16 {1, 1, 1, 0, ...}: query side of the norm slice
   int64_t qext_rows = 0;
   rdb::DevBuf dev_ctl;            // device-side control words of the stream-ordered certified search (counts, flags)
   void* pin = nullptr;            // pinned host staging of the small-batch path
   size_t pin_bytes = 0;
-  float* d_ynorm_max = nullptr;   // max |y|^2 over the shard (device scalar; feeds the re-rank certificate)
+  float* d_ynorm_max = nullptr;   // [0] max |y|^2 over the shard, [1] max |y - y_hi|^2 (device scalars of the re-rank certificate)
   rdb::DevBuf np_tab;             // piece table of numpy's pairwise summation for rows of d floats (ingest.cuh: NpPlan)
   int np_nleaves = 0, np_nops = 0, np_balanced = 0;
   int64_t last_uncertified = 0;
@@ -127,6 +135,7 @@ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 // ---- launchers exported by the per-family translation units (launch_tc.cu, launch_simt.cu, launch_stream.cu)
 struct TcParams;
 struct StreamParams;
+struct DevPlan;
 struct QueryView {
   const float* qf;    // fp32 [nq, D] (fp32 stores)
   const void* qhi;    // 16-bit [nq, Dp]
@@ -140,7 +149,7 @@ int launch_tc_cg(rdb_handle* h, TcParams& p, int k, int cg);
 int encode_2d(rdb_handle* h, CUtensorMap* m, const void* base, int64_t rows, int D, int Dp, int box_rows);
 // exact CUDA-core scorer (selecting form and the k > 128 DUMP form)
 int launch_simt(rdb_handle* h, const float* qf, const void* qhi, int nq, int k, int nqt, int S, int rows_per_chunk,
-                float* ck, int* ci);
+                float* ck, int* ci, const DevPlan* plan = nullptr);
 int launch_simt_dump(rdb_handle* h, const QueryView& qv, int q0, int nq, int nqt, int S, int rows_per_chunk, int row0,
                      int row_end, float* dump, long long pitch);
 // small-batch streaming scorer

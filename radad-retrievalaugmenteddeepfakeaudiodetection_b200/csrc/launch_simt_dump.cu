@@ -12,7 +12,7 @@ int launch_simt_dump_t(rdb_handle* h, const T* Q, const T* Y, int nq, int ld, in
   auto kern = score_select_simt_kernel<16, L2, T, ALIGNED, true>;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt_smem_bytes()));
   kern<<<dim3(unsigned(nqt) * unsigned(S)), dim3(256), simt_smem_bytes(), h->stream>>>(
-      Q, Y, h->ynorm, nq, row_end, h->d, ld, nqt, S, rows_per_chunk, nullptr, nullptr, 0, dump, pitch, row0);
+      Q, Y, h->ynorm, nq, row_end, h->d, ld, nqt, S, rows_per_chunk, nullptr, nullptr, 0, dump, pitch, row0, nullptr);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return RDB_OK;

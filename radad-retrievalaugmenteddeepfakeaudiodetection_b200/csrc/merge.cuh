@@ -12,6 +12,7 @@
 namespace rdb {
 
 constexpr int MERGE_LPL = 8;  // lists per lane -> up to 256 lists per query
+constexpr int TC_PLAN_LISTS = 2;   // candidate lists per (query, chunk) of the tensor-core scorer (== TC_LISTS, score_tc.cuh)
 
 struct MergeHead {
   uint32_t ok;     // ordered key, 0 = exhausted
@@ -140,9 +141,13 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
                                                           float* __restrict__ out_lbl,
                                                           float* __restrict__ out_key,
                                                           const int* __restrict__ run_if = nullptr,
-                                                          int stage_bytes_per_warp = 0) {
+                                                          int stage_bytes_per_warp = 0,
+                                                          const int* __restrict__ q_dev = nullptr,
+                                                          const int* __restrict__ l_dev = nullptr) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q_dev) Q = min(Q, __ldcg(q_dev));        // device-sized launch (DevPlan): the grid covers the worst case
+  if (l_dev) L = __ldcg(l_dev);
   if (q >= Q) return;
   if (run_if && __ldcg(run_if) == 0) return;
   if (stage_bytes_per_warp > 0) {
@@ -225,13 +230,18 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_exact_kernel(const long
                                                                       long long ntotal, float* __restrict__ out_key,
                                                                       long long* __restrict__ out_idx,
                                                                       int* __restrict__ uncert_list,
-                                                                      int* __restrict__ uncert_count) {
+                                                                      int* __restrict__ uncert_count,
+                                                                      const float* __restrict__ qres = nullptr,
+                                                                      const float* __restrict__ yres_max = nullptr,
+                                                                      float accum_eps = 0.f,
+                                                                      const int* __restrict__ q_dev = nullptr,
+                                                                      const int* __restrict__ qmap = nullptr) {
   __shared__ uint32_t s_ok[RERANK_MAX_KC];     // ordered exact keys (0 = empty slot)
   __shared__ long long s_id[RERANK_MAX_KC];
   __shared__ float s_kth;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int q = blockIdx.x;
-  if (q >= Q) return;
+  if (q_dev) Q = min(Q, __ldcg(q_dev));        // device-sized launch: the grid covers the worst case
+  for (int q = blockIdx.x; q < Q; q += gridDim.x) {
   const float* qr = qf + (long long)q * D;
   const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(qr) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(master) & 15) == 0);
@@ -304,9 +314,24 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_exact_kernel(const long
       if (cand_idx[(long long)q * kc + j] >= 0) approx_worst = fminf(approx_worst, cand_key[(long long)q * kc + j]);
     const float kth_key = s_kth;
     const bool has = nvalid >= kout;
-    const float bound = eps * sqrtf(qnorm[q]) * sqrtf(*ynorm_max) * (L2 ? 2.0f : 1.0f);
+    // One-term pass with measured residuals (qres != null): q.y - q_hi.y_hi = (q - q_hi).y + q_hi.(y - y_hi), so
+    // |error| <= |q - q_hi| max|y| + |q_hi| max|y - y_hi| (Cauchy-Schwarz with the ACTUAL rounding residuals, ~2.3x below
+    // the worst case 2 * 2^-9 |q||y| that `eps` encodes) + the accumulation term; 1.001 covers the fp32 rounding of the
+    // norms themselves.
+    const float qn = sqrtf(qnorm[q]), ymax = sqrtf(*ynorm_max);
+    float bound = eps * qn * ymax;
+    if (qres) {
+      const float qr = sqrtf(qres[q]);
+      bound = fminf(bound, 1.001f * (qr * ymax + (qn + qr) * sqrtf(*yres_max)) + accum_eps * qn * ymax);
+    }
+    bound *= (L2 ? 2.0f : 1.0f);
+    // L2 keys taken from the accumulator (norm slice) also carry the accumulation rounding of the -|y|^2 parts
+    if (L2) bound += 4.0f * 1.1920928955078125e-07f * (*ynorm_max);
     const bool ok = (nvalid >= ntotal) || (nvalid == kc && has && kth_key > approx_worst + bound);
-    if (!ok) uncert_list[atomicAdd(uncert_count, 1)] = q;
+    // uncertified queries are listed by their ORIGINAL query index when the batch is itself a compacted sub-batch
+    if (!ok) uncert_list[atomicAdd(uncert_count, 1)] = qmap ? qmap[q] : q;
+  }
+  __syncthreads();     // the shared arrays are reused by the next query of this block
   }
 }
 
@@ -412,7 +437,8 @@ __global__ void __launch_bounds__(RERANK_LARGE_THREADS) rerank_exact_large_kerne
     const unsigned long long vk = (kout >= 1 && kout <= kc) ? rl_buf[kout - 1] : 0ull;
     const bool has = vk != 0ull;
     const float kth_key = has ? unordered_f32(uint32_t(vk >> 32)) : -CUDART_INF_F;
-    const float bound = eps * sqrtf(qnorm[q]) * sqrtf(*ynorm_max) * (L2 ? 2.0f : 1.0f);
+    float bound = eps * sqrtf(qnorm[q]) * sqrtf(*ynorm_max) * (L2 ? 2.0f : 1.0f);
+    if (L2) bound += 4.0f * 1.1920928955078125e-07f * (*ynorm_max);      // norm slice: see rerank_exact_kernel
     const bool ok = (nv >= ntotal) || (nv == kc && has && kth_key > aw + bound);
     if (!ok) uncert_list[atomicAdd(uncert_count, 1)] = q;
   }
@@ -483,28 +509,82 @@ static __global__ void ynorm_max_kernel(const float* __restrict__ ynorm, long lo
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
 }
 
-// rows list[i] of src [*, D] -> dst [m, D]   (compact the uncertified queries)
+// rows list[i] of src [*, D] -> dst [m, D]   (compact the uncertified queries); m_dev (optional) = count on the device
 static __global__ void gather_f32_rows_kernel(const float* __restrict__ src, const int* __restrict__ list, int m, int D,
-                                       float* __restrict__ dst) {
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= m) return;
-  const float* s = src + (long long)list[w] * D;
-  float* d = dst + (long long)w * D;
-  for (int c = (threadIdx.x & 31); c < D; c += 32) d[c] = s[c];
+                                       float* __restrict__ dst, const int* __restrict__ m_dev = nullptr) {
+  if (m_dev) m = min(m, __ldcg(m_dev));
+  const int nw = gridDim.x * (blockDim.x >> 5);
+  for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < m; w += nw) {
+    const float* s = src + (long long)list[w] * D;
+    float* d = dst + (long long)w * D;
+    for (int c = (threadIdx.x & 31); c < D; c += 32) d[c] = s[c];
+  }
 }
 
 // scatter rows of the fallback results back to their query slots
 static __global__ void scatter_results_kernel(const int* __restrict__ list, int m, int k, const float* __restrict__ s_a,
                                        const long long* __restrict__ s_i, const float* __restrict__ s_l,
                                        float* __restrict__ d_a, long long* __restrict__ d_i,
-                                       float* __restrict__ d_l) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= m * k) return;
-  const int r = t / k, j = t % k;
-  const long long o = (long long)list[r] * k + j;
-  d_a[o] = s_a[t];
-  d_i[o] = s_i[t];
-  if (d_l && s_l) d_l[o] = s_l[t];
+                                       float* __restrict__ d_l, const int* __restrict__ m_dev = nullptr) {
+  if (m_dev) m = min(m, __ldcg(m_dev));
+  const long long total = (long long)m * k;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int r = int(t / k), j = int(t % k);
+    const long long o = (long long)list[r] * k + j;
+    d_a[o] = s_a[t];
+    d_i[o] = s_i[t];
+    if (d_l && s_l) d_l[o] = s_l[t];
+  }
+}
+
+// ---- planning kernels of the device-sized launches (DevPlan, common.cuh) -- one thread each ----------------------------
+// same cost model as the host's choose_splits (radad_flat.cu): waves * (tiles per chunk + per-unit overhead)
+__device__ __forceinline__ int plan_choose_splits(long long nqt, long long ntiles, int slots, int max_lists, int min_tiles,
+                                                  float overhead, int* tpc_out) {
+  long long maxS = min((long long)max_lists, ntiles);
+  maxS = min(maxS, max(1ll, ntiles / max(min_tiles, 1)));
+  float best = 3.0e38f;
+  int bestS = 1;
+  long long best_tpc = ntiles;
+  for (long long S = 1; S <= maxS; ++S) {
+    const long long tpc = (ntiles + S - 1) / S;
+    const long long S2 = (ntiles + tpc - 1) / tpc;
+    if (S2 != S) continue;
+    const long long units = nqt * S2;
+    const long long waves = (units + slots - 1) / slots;
+    const float cost = float(waves) * (float(tpc) + overhead);
+    if (cost < best * 0.999f) { best = cost; bestS = int(S2); best_tpc = tpc; }
+  }
+  *tpc_out = int(best_tpc);
+  return bestS;
+}
+// Tensor-core stage over `*count` queries (clamped to cap): query-tile groups of 128 * cg queries, chunking chosen to
+// fill `slots` CTA groups; lists per query bounded by the candidate buffer (cand_entries slots of kc entries).
+static __global__ void plan_tc_kernel(const int* __restrict__ count, int cap, int cg, long long ntiles, int slots,
+                                      int max_lists, int min_tiles, float overhead, long long cand_lists_cap,
+                                      DevPlan* __restrict__ plan) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int nq = min(max(*count, 0), cap);
+  plan->nq = nq;
+  if (nq == 0) { plan->nqg = 0; plan->S = 1; plan->tpc = int(ntiles); plan->num_units = 0; plan->L = TC_PLAN_LISTS; return; }
+  const int nqg = (nq + 128 * cg - 1) / (128 * cg);
+  const long long lists_fit = max(1ll, cand_lists_cap / ((long long)nqg * 128 * cg) / TC_PLAN_LISTS);
+  int tpc;
+  const int S = plan_choose_splits(nqg, ntiles, slots, int(min((long long)max_lists, lists_fit)), min_tiles, overhead, &tpc);
+  plan->nqg = nqg; plan->S = S; plan->tpc = tpc; plan->num_units = nqg * S; plan->L = S * TC_PLAN_LISTS;
+}
+// CUDA-core stage (exact fallback) over `*count` queries: 128-query tiles x chunks of 128-row tiles, 2 lists per chunk
+static __global__ void plan_simt_kernel(const int* __restrict__ count, int cap, long long ntiles, int slots, int max_lists,
+                                        long long cand_lists_cap, DevPlan* __restrict__ plan) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int nq = min(max(*count, 0), cap);
+  plan->nq = nq;
+  if (nq == 0) { plan->s_nqt = 0; plan->s_S = 1; plan->s_rows = 128; plan->s_units = 0; plan->s_L = 2; return; }
+  const int nqt = (nq + 127) / 128;
+  const long long lists_fit = max(1ll, cand_lists_cap / ((long long)nqt * 128) / 2);
+  int tpc;
+  const int S = plan_choose_splits(nqt, ntiles, slots, int(min((long long)max_lists, lists_fit)), 2, 2.0f, &tpc);
+  plan->s_nqt = nqt; plan->s_S = S; plan->s_rows = tpc * 128; plan->s_units = nqt * S; plan->s_L = S * 2;
 }
 
 // Fused gather + merge over NVLink peer memory (multi-GPU row shards).  Each rank left its [Q][k] candidates

@@ -32,6 +32,9 @@ namespace rdb { thread_local std::string g_err; }
 
 namespace {
 
+// every place a call blocks the host on the handle's stream goes through here (rdb_host_sync_count)
+cudaError_t host_sync(rdb_handle* h) { h->host_syncs++; return cudaStreamSynchronize(h->stream); }
+
 // ---------------------------------------------------------------------------------------------- storage
 int grow_to(rdb_handle* h, int64_t need, bool exact = false) {
   if (need <= h->cap) return RDB_OK;
@@ -101,7 +104,7 @@ NpPlan np_plan(rdb_handle* h) { return NpPlan{h->np_tab.as<int>(), h->np_nleaves
 
 // launch the fused ingest kernel (also used to prepare queries)
 int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int norm_of_hi, float* master, void* hi,
-                  void* lo, float* norm2, float hscale = 1.0f) {
+                  void* lo, float* norm2, float hscale = 1.0f, float* res2 = nullptr, const int* n_dev = nullptr) {
   if (n <= 0) return RDB_OK;
   const int D = h->d, Dp = h->dp;
   const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
@@ -118,7 +121,7 @@ int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int n
       dim3 grid((unsigned)blocks), block(256);
 #define FAST_LAUNCH(T16, NC, NORM, MODE)                                                                                  \
       ingest_fast_kernel<T16, NC, NORM, MODE><<<grid, block, NORM ? warps_per_block * FastShape<NC>::WARP_FLOATS * 4 : 0, \
-                                                h->stream>>>(x, n, master, (T16*)hi, (T16*)lo, norm2, hscale)
+                                                h->stream>>>(x, n, master, (T16*)hi, (T16*)lo, norm2, hscale, res2, n_dev)
 #define FAST_MODE(T16, NC, NORM)                                                                                          \
       do { if (mode == 0) FAST_LAUNCH(T16, NC, NORM, 0); else if (mode == 1) FAST_LAUNCH(T16, NC, NORM, 1);               \
            else FAST_LAUNCH(T16, NC, NORM, 2); } while (0)
@@ -150,7 +153,7 @@ int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int n
       CUDA_TRY(h, cudaFuncSetAttribute(ingest_rows_kernel<T16, V4, NC, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        int(smem)));                                                                       \
     ingest_rows_kernel<T16, V4, NC, NORM><<<grid, block, smem, s>>>(x, n, D, Dp, norm_of_hi, master, (T16*)hi, (T16*)lo,  \
-                                                                    norm2, np, hscale);                                   \
+                                                                    norm2, np, hscale, res2, n_dev);                      \
   } while (0)
 #define INGEST_N(T16, V4, NC)                                                                             \
   do { if (normalize) INGEST_LAUNCH(T16, V4, NC, true); else INGEST_LAUNCH(T16, V4, NC, false); } while (0)
@@ -208,7 +211,7 @@ int tc_cta_group(const rdb_handle* h, int nq, int nterms, int d) {
 int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, int cg, int nqg, int S, int tiles_per_chunk,
               int ntiles, int nterms, float* ck, int* ci, int tile_step = 1, bool keep_gthr = false,
               const int* run_if = nullptr, float* dump = nullptr, long long dump_pitch = 0, int row_base = 0,
-              int row_end = 0) {
+              int row_end = 0, const DevPlan* plan = nullptr) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -218,7 +221,7 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
   p.ynorm = h->ynorm; p.ynmin32 = h->ynmin32; p.cand_key = ck; p.cand_idx = ci;
   CUDA_TRY(h, h->gthr.ensure(size_t(nq) * 4));
   if (!keep_gthr) CUDA_TRY(h, cudaMemsetAsync(h->gthr.p, 0, size_t(nq) * 4, h->stream));
-  p.tile_step = tile_step; p.run_if = run_if;
+  p.tile_step = tile_step; p.run_if = run_if; p.plan = plan;
   p.nstages = std::max(2, h->opt.tc_stages);
   // norm slice (L2 keys straight from the accumulator): the queries of this search were staged as 2 q (search_impl)
   p.ext = (h->cur_hscale == 2.0f && h->yext) ? 1 : 0;
@@ -280,6 +283,7 @@ constexpr int64_t kLargeKRowsDefault = 1 << 20;       // rows per chunk: 256 x 1
 constexpr int kMaxKTc = 128;       // k <= 32: register-resident list; 32 < k <= 128: local-memory reservoir
 constexpr int kMaxKSplit = 104;    // split-precision path keeps kc = 16 / 32 / 64 / 128 candidates: slack >= 6 / 8 / 16 / 24
 constexpr int64_t kMinRowsTc = 1024;
+constexpr int kTier1Hold = 8;         // batches a raised tier-1 level is kept before it decays by one
 constexpr int kTcSample = 64;          // large-k pivot: every 64th DB tile
 constexpr int kTcPivotRank = 16;       // ... and the sample's 16th best key
 constexpr int kTcPivotMinTiles = 1024; // >= 16 sampled tiles (N >= 262144)
@@ -385,7 +389,7 @@ int search_stream(rdb_handle* h, const float* q, int nq, int k, int mem, int nor
   h->ev_valid = true; h->last_algo = RDB_ALGO_STREAM; h->last_S = S;
   if (host) {
     CUDA_TRY(h, cudaMemcpyAsync(h->pin, h->o_dist.p, pack_bytes, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, host_sync(h));
     const char* base = static_cast<const char*>(h->pin);
     memcpy(out_a, base, nk * 4);
     if (out_lbl) memcpy(out_lbl, base + off_l, nk * 4);
@@ -412,6 +416,10 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
     const int min_tiles = std::max(1, std::min(base_min, base_min * 12 / slices_per_tile));
     S = choose_splits(nqg, ntiles, h->num_sms / cg, 256 / TC_LISTS, min_tiles, &tpc,
                       (kc > 32 ? 64.0 : 2.0) * min_tiles / base_min);
+    if (h->opt.tc_chunks > 0) {                                   // A/B option
+      tpc = (ntiles + h->opt.tc_chunks - 1) / h->opt.tc_chunks;
+      S = (ntiles + tpc - 1) / tpc;
+    }
     CUDA_TRY(h, h->cand_key.ensure(size_t(qv.nq) * S * TC_LISTS * kc * 4));
     CUDA_TRY(h, h->cand_idx.ensure(size_t(qv.nq) * S * TC_LISTS * kc * 4));
     if (timed) cudaEventRecord(h->ev0, s);
@@ -534,7 +542,18 @@ int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out, int nterms
 // fold the local candidate lists: final form (dist or key, global id, label)
 int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float* qnorm, bool shard_mode, float* d_a,
                     int64_t* d_i, float* d_l, long long id_offset, const float* labels, float* raw_key,
-                    const int* run_if = nullptr) {
+                    const int* run_if = nullptr, const int* q_dev = nullptr, const int* l_dev = nullptr) {
+  if (q_dev) {
+    // device-sized launch (DevPlan): nq is the grid capacity, the real query / list counts are read on the device
+    dim3 grid((nq + 3) / 4), block(128);
+    merge_lists_kernel<int, MERGE_LPL><<<grid, block, 0, h->stream>>>(
+        h->cand_key.as<float>(), h->cand_idx.as<int>(), nullptr, nq, L, kc, kout, h->metric == RDB_METRIC_L2 ? 1 : 0, qnorm,
+        id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l, shard_mode ? d_a : raw_key,
+        nullptr, 0, q_dev, l_dev);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return RDB_OK;
+  }
   if (L == 1 && kc == kout && !run_if) {
     // one sorted list per query (k > 128 with a single row chunk): elementwise conversion instead of k merge rounds
     const long long total = (long long)nq * kout;
@@ -574,89 +593,172 @@ int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float*
 // Queries tier 1 cannot certify are compacted and go through tier 2; what tier 2 cannot certify (adversarial ties) is
 // searched by the exact CUDA-core kernel.  Every tier ends in exact fp32 keys, so the result does not depend on which
 // tier certified a query.
+// Candidate-list capacity (lists of kc entries) of a device-sized stage over at most `cap` queries: 16 lists per query,
+// and never fewer than what one query-tile group needs to be split into 128 chunks.
+int64_t planned_lists_cap(int cap) { return std::max<int64_t>(round_up(cap, 256) * 16, int64_t(256) * 256); }
+
+// `plan` == null: host-sized pass over v.nq queries.  `plan` != null: device-sized pass -- v.nq is the CAPACITY (grids,
+// buffers, tensor maps), the real number of queries and the chunking live in *plan (written by plan_tc_kernel from a
+// device-side count); every launch is enqueued unconditionally and returns at once when the plan holds no query.
 int certified_pass(rdb_handle* h, const QueryView& v, int k, int kc, int nterms, bool shard_mode, float* o_a,
-                   int64_t* o_i, float* o_l, const float* labels, int* ucount, int* ulist, bool timed) {
+                   int64_t* o_i, float* o_l, const float* labels, int* ucount, int* ulist, bool timed,
+                   const DevPlan* plan = nullptr) {
   const int nb = v.nq, D = h->d;
   const bool l2 = h->metric == RDB_METRIC_L2;
   cudaStream_t s = h->stream;
   int rc, L = 0;
-  if ((rc = run_scorer(h, RDB_ALGO_TC, nterms, v, kc, &L, timed))) return rc;
+  const int* q_dev = plan ? &plan->nq : nullptr;
+  if (!plan) {
+    if ((rc = run_scorer(h, RDB_ALGO_TC, nterms, v, kc, &L, timed))) return rc;
+  } else {
+    const int ntiles = int((h->n + TC_BN - 1) / TC_BN);
+    const int cg = nb > TC_BM ? 2 : 1;                       // must match plan_tc_kernel's cg (split3_search)
+    const int64_t lists = planned_lists_cap(nb);
+    CUDA_TRY(h, h->cand_key.ensure(size_t(lists) * kc * 4));
+    CUDA_TRY(h, h->cand_idx.ensure(size_t(lists) * kc * 4));
+    const int nqg_cap = (nb + TC_BM * cg - 1) / (TC_BM * cg);
+    if ((rc = launch_tc(h, v.qhi, v.qlo, nb, kc, cg, nqg_cap, 256 / TC_LISTS, ntiles, ntiles, nterms, h->cand_key.as<float>(),
+                        h->cand_idx.as<int>(), 1, false, nullptr, nullptr, 0, 0, 0, plan))) return rc;
+    L = 256;
+  }
   CUDA_TRY(h, h->rr_key.ensure(size_t(nb) * kc * 4));
   CUDA_TRY(h, h->rr_idx.ensure(size_t(nb) * kc * 8));
   CUDA_TRY(h, h->rr_key2.ensure(size_t(nb) * kc * 4));
   CUDA_TRY(h, h->rr_idx2.ensure(size_t(nb) * kc * 8));
   // approximate top-kc per query (local ids, raw keys)
   if ((rc = run_merge_local(h, nb, L, kc, kc, v.qnorm, false, nullptr, h->rr_idx.as<int64_t>(), nullptr, 0, nullptr,
-                            h->rr_key.as<float>()))) return rc;
+                            h->rr_key.as<float>(), nullptr, q_dev, plan ? &plan->L : nullptr))) return rc;
   CUDA_TRY(h, cudaMemsetAsync(ucount, 0, 4, s));
   const int nks = (D + TC_BK - 1) / TC_BK;
   const float n_mma = float(nks * (TC_BK / 16) * nterms);
   const float accum = 2.0f * (n_mma + 16.f) * 1.1920928955078125e-07f /*2^-23*/;
+  // one-term pass of the main batch: measured rounding residuals tighten the certificate (see rerank_exact_kernel)
+  const float* qres = (nterms == 1 && v.qf == h->qf.as<float>()) ? h->qres.as<float>() : nullptr;
   const float eps = (nterms == 3 ? 3.02f * 3.814697265625e-06f /*2^-18*/
                                  : 0.00390625f /*2 * 2^-9*/ + 3.814697265625e-06f /*2^-18*/) + accum;
   const int warps = 4;
   dim3 grid((nb + warps - 1) / warps), block(32 * warps);
-  dim3 rgrid(nb), rblock(RERANK_THREADS);                       // re-rank: one block per query
+  dim3 rgrid(plan ? std::min(nb, h->num_sms * 8) : nb), rblock(RERANK_THREADS);     // re-rank: one block per query
   if (l2) rerank_exact_kernel<true><<<rgrid, rblock, 0, s>>>(
       h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, v.qf, h->master, h->ynorm, D, eps, v.qnorm,
-      h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount);
+      h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount, qres, h->d_ynorm_max + 1,
+      accum, q_dev);
   else rerank_exact_kernel<false><<<rgrid, rblock, 0, s>>>(
       h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, v.qf, h->master, h->ynorm, D, eps, v.qnorm,
-      h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount);
+      h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount, qres, h->d_ynorm_max + 1,
+      accum, q_dev);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   // exact list (L = 1, already sorted) -> final form
   merge_lists_kernel<long long><<<grid, block, 0, s>>>(
       h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), nullptr, nb, 1, kc, k, l2 ? 1 : 0, v.qnorm, h->id_offset,
-      labels, shard_mode ? nullptr : o_a, reinterpret_cast<long long*>(o_i), o_l, shard_mode ? o_a : nullptr);
+      labels, shard_mode ? nullptr : o_a, reinterpret_cast<long long*>(o_i), o_l, shard_mode ? o_a : nullptr, nullptr, 0,
+      q_dev, nullptr);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return RDB_OK;
 }
 
-// tier 2 (+ exact CUDA-core search of what it cannot certify) over the queries of `v`; results [v.nq][k] into o_*
+// Counts of the certified search, read back WITHOUT blocking the stream: the device counters are copied to pinned host
+// memory behind the batch and folded into the statistics / the adaptive tier-1 level when the copy has landed (checked
+// at the next search, or waited for by the getters and by host-path searches, which synchronise anyway).
+void counts_resolve(rdb_handle* h, bool wait) {
+  if (!h->counts_pending) return;
+  if (wait) cudaEventSynchronize(h->ev_counts);
+  else if (cudaEventQuery(h->ev_counts) != cudaSuccess) { cudaGetLastError(); return; }
+  h->counts_pending = false;
+  const int m1 = h->pin_counts[0], m2 = h->pin_counts[1];
+  if (h->pending_tier1) {
+    h->last_tier1_queries += h->pending_nb;
+    h->last_tier1_uncertified += m1;
+    h->last_tier1_kc = h->pending_kc1;
+    if (h->pending_kc1 < 128 ? (4 * int64_t(m1) > h->pending_nb) : (2 * int64_t(m1) > h->pending_nb)) {
+      h->t1_level = h->pending_kc1 < 128 ? 1 : 2;
+      h->t1_hold = kTier1Hold;
+    }
+  }
+  h->last_uncertified += m2;
+}
+int counts_post(rdb_handle* h, const int* ucount1, const int* ucount2, bool tier1, int nb, int kc1) {
+  counts_resolve(h, true);             // one set of counters in flight at a time
+  if (!h->pin_counts) {
+    CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void**>(&h->pin_counts), 16, cudaHostAllocDefault));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_counts, cudaEventDisableTiming));
+  }
+  h->pin_counts[0] = 0; h->pin_counts[1] = 0;
+  if (ucount1) CUDA_TRY(h, cudaMemcpyAsync(&h->pin_counts[0], ucount1, 4, cudaMemcpyDeviceToHost, h->stream));
+  if (ucount2) CUDA_TRY(h, cudaMemcpyAsync(&h->pin_counts[1], ucount2, 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev_counts, h->stream));
+  h->counts_pending = true; h->pending_tier1 = tier1; h->pending_nb = nb; h->pending_kc1 = kc1;
+  return RDB_OK;
+}
+
+// Tier 2 (three-term pass + exact re-rank + certificate) followed by the exact CUDA-core search of what it cannot
+// certify; results [.][k] into o_*.  `count_dev` == null: the batch is v (v.nq queries, host-sized).  Otherwise v is a
+// compacted sub-batch of CAPACITY v.nq whose real size is *count_dev (device), and tier 2 is device-sized as well.
+// The exact fallback is ALWAYS device-sized: how many queries tier 2 refuses is only known on the device, and nothing
+// here waits for it -- the whole search is stream-ordered (no host round trip, graph-capturable).
+// *ucount2_out = device counter of the queries that took the exact fallback.
 int split3_search(rdb_handle* h, const QueryView& v, int k, bool shard_mode, float* o_a, int64_t* o_i, float* o_l,
-                  const float* labels, bool timed) {
-  const int nb = v.nq, D = h->d;
+                  const float* labels, bool timed, const int* count_dev, const int** ucount2_out) {
+  const int cap = v.nq, D = h->d;
   cudaStream_t s = h->stream;
   int rc;
   const int kc = (k <= 10) ? 16 : (k <= 24 ? 32 : (k <= 48 ? 64 : 128));
-  CUDA_TRY(h, h->uncert.ensure(size_t(nb + 1) * 4));
+  CUDA_TRY(h, h->uncert.ensure(size_t(cap + 1) * 4));
+  CUDA_TRY(h, h->dev_ctl.ensure(2 * sizeof(DevPlan)));
   int* ucount = h->uncert.as<int>();
   int* ulist = ucount + 1;
-  if ((rc = certified_pass(h, v, k, kc, 3, shard_mode, o_a, o_i, o_l, labels, ucount, ulist, timed))) return rc;
-  int m = 0;
-  CUDA_TRY(h, cudaMemcpyAsync(&m, ucount, 4, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(h, cudaStreamSynchronize(s));
-  h->last_uncertified += m;
-  if (m > 0) {
-    CUDA_TRY(h, h->fb_qf.ensure(size_t(m) * D * 4));
-    CUDA_TRY(h, h->fb_qnorm.ensure(size_t(m) * 4));
-    CUDA_TRY(h, h->fb_a.ensure(size_t(m) * k * 4));
-    CUDA_TRY(h, h->fb_i.ensure(size_t(m) * k * 8));
-    CUDA_TRY(h, h->fb_l.ensure(size_t(m) * k * 4));
-    gather_f32_rows_kernel<<<(m + 7) / 8, 256, 0, s>>>(v.qf, ulist, m, D, h->fb_qf.as<float>());
-    h->launches++;
-    if ((rc = launch_ingest(h, h->fb_qf.as<float>(), m, 0, 0, nullptr, nullptr, nullptr, h->fb_qnorm.as<float>())))
-      return rc;
-    QueryView fv{h->fb_qf.as<float>(), nullptr, nullptr, h->fb_qnorm.as<float>(), m};
-    int Lf = 0;
-    if ((rc = run_scorer(h, RDB_ALGO_SIMT, 1, fv, k, &Lf, false))) return rc;
-    if ((rc = run_merge_local(h, m, Lf, k, k, fv.qnorm, shard_mode, h->fb_a.as<float>(), h->fb_i.as<int64_t>(),
-                              h->fb_l.as<float>(), h->id_offset, labels, nullptr))) return rc;
-    scatter_results_kernel<<<(m * k + 255) / 256, 256, 0, s>>>(ulist, m, k, h->fb_a.as<float>(),
-                                                               h->fb_i.as<long long>(), h->fb_l.as<float>(), o_a,
-                                                               reinterpret_cast<long long*>(o_i), o_l);
+  DevPlan* plan2 = h->dev_ctl.as<DevPlan>();           // tier 2 (device-sized form only)
+  DevPlan* plan3 = plan2 + 1;                          // exact fallback
+  if (count_dev) {
+    const int ntiles = int((h->n + TC_BN - 1) / TC_BN);
+    const int cg = cap > TC_BM ? 2 : 1;
+    const int slices_per_tile = ((D + TC_BK - 1) / TC_BK) * 3;
+    const int base_min = kc > 32 ? 64 : 4;
+    const int min_tiles = std::max(1, std::min(base_min, base_min * 12 / slices_per_tile));
+    plan_tc_kernel<<<1, 32, 0, s>>>(count_dev, cap, cg, ntiles, h->num_sms / cg, 256 / TC_LISTS, min_tiles,
+                                    float((kc > 32 ? 64.0 : 2.0) * min_tiles / base_min), planned_lists_cap(cap), plan2);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
   }
+  if ((rc = certified_pass(h, v, k, kc, 3, shard_mode, o_a, o_i, o_l, labels, ucount, ulist, timed,
+                           count_dev ? plan2 : nullptr))) return rc;
+  // ---- exact CUDA-core search of the uncertified queries, device-sized
+  const int ntiles_s = int((h->n + SIMT_BN - 1) / SIMT_BN);
+  const int64_t lists3 = std::max<int64_t>(round_up(cap, 128) * 8, int64_t(128) * 256);
+  plan_simt_kernel<<<1, 32, 0, s>>>(ucount, cap, ntiles_s, 2 * h->num_sms, 256 / SIMT_LISTS, lists3, plan3);
+  h->launches++;
+  CUDA_TRY(h, h->fb_qf.ensure(size_t(cap) * D * 4));
+  CUDA_TRY(h, h->fb_qnorm.ensure(size_t(cap) * 4));
+  CUDA_TRY(h, h->fb_a.ensure(size_t(cap) * k * 4));
+  CUDA_TRY(h, h->fb_i.ensure(size_t(cap) * k * 8));
+  CUDA_TRY(h, h->fb_l.ensure(size_t(cap) * k * 4));
+  CUDA_TRY(h, h->cand_key.ensure(size_t(lists3) * k * 4));
+  CUDA_TRY(h, h->cand_idx.ensure(size_t(lists3) * k * 4));
+  const int gblocks = std::min((cap + 7) / 8, h->num_sms * 4);
+  gather_f32_rows_kernel<<<gblocks, 256, 0, s>>>(v.qf, ulist, cap, D, h->fb_qf.as<float>(), &plan3->nq);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  if ((rc = launch_ingest(h, h->fb_qf.as<float>(), cap, 0, 0, nullptr, nullptr, nullptr, h->fb_qnorm.as<float>(), 1.0f,
+                          nullptr, &plan3->nq))) return rc;
+  if ((rc = launch_simt(h, h->fb_qf.as<float>(), nullptr, cap, k, (cap + 127) / 128, 1, SIMT_BN, h->cand_key.as<float>(),
+                        h->cand_idx.as<int>(), plan3))) return rc;
+  if ((rc = run_merge_local(h, cap, 256, k, k, h->fb_qnorm.as<float>(), shard_mode, h->fb_a.as<float>(),
+                            h->fb_i.as<int64_t>(), h->fb_l.as<float>(), h->id_offset, labels, nullptr, nullptr, &plan3->nq,
+                            &plan3->s_L))) return rc;
+  scatter_results_kernel<<<std::min((cap * k + 255) / 256, h->num_sms * 8), 256, 0, s>>>(
+      ulist, cap, k, h->fb_a.as<float>(), h->fb_i.as<long long>(), h->fb_l.as<float>(), o_a,
+      reinterpret_cast<long long*>(o_i), o_l, &plan3->nq);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  if (ucount2_out) *ucount2_out = ucount;
   return RDB_OK;
 }
 
 constexpr int kTier1MaxK = 64;        // kc = 128 candidates: >= 2x slack (k = 64 vs 128: the gap is ~2.6 sd above the bound on Gaussian data)
 constexpr int kTier1SmallK = 16;      // k <= 16 (the reference asks for top_k + 10 = 15): 32 candidates (register-list epilogue, no
                                       // sample pass); a failed query only costs its share of a three-term pass
-constexpr int kTier1Hold = 8;         // batches a raised level is kept before it decays by one
 
 int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mode, float* d_a, int64_t* d_i, float* d_l,
                        const float* labels) {
@@ -664,14 +766,20 @@ int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mod
   cudaStream_t s = h->stream;
   int rc;
   const int64_t ntiles = (h->n + TC_BN - 1) / TC_BN;
+  counts_resolve(h, false);            // fold the previous batch's counters in if they have arrived
   // Tier-1 level, adapted to how the data certifies: 0 = 32 candidates when k <= 16 (on iid Gaussian data at D = 768
-  // the exact 10th key clears the 32nd approximate key by ~2.7 standard deviations of that gap: ~0.3 % of the queries
-  // fail; k = 15: ~5 %), 1 = 128 candidates (more than a quarter failed with 32: beyond that the three-term pass over
-  // the failures costs more than the larger epilogue), 2 = no tier 1 (more than half failed with 128).  A raised level
-  // decays by one after kTier1Hold batches, so a change of the data is picked up again.
+  // the exact 10th key clears the 32nd approximate key by a wide margin under the measured-residual bound), 1 = 128
+  // candidates (more than a quarter failed with 32: beyond that the three-term pass over the failures costs more than
+  // the larger epilogue), 2 = no tier 1 (more than half failed with 128).  A raised level decays by one after
+  // kTier1Hold batches, so a change of the data is picked up again.  The counters arrive asynchronously, so a level
+  // change takes effect one batch late.
   if (h->t1_hold > 0 && --h->t1_hold == 0 && h->t1_level > 0) { h->t1_level--; h->t1_hold = h->t1_level > 0 ? kTier1Hold : 0; }
   const bool tier1 = k <= kTier1MaxK && ntiles >= kTcPivotMinTiles && h->t1_level < 2 && h->opt.tier1;
-  if (!tier1) return split3_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels, true);
+  const int* ucount2 = nullptr;
+  if (!tier1) {
+    if ((rc = split3_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels, true, nullptr, &ucount2))) return rc;
+    return counts_post(h, nullptr, ucount2, false, nb, 0);
+  }
   int kc1 = (h->t1_level == 0 && k <= kTier1SmallK) ? 32 : 128;
   if (const int f = h->opt.tier1_kc)                      // A/B option: force the candidate count (never below what k needs)
     if (f == 32 || f == 64 || f == 128) kc1 = (k <= kTier1SmallK) ? f : 128;
@@ -681,39 +789,29 @@ int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mod
   int* ulist = ucount + 1;
   if ((rc = certified_pass(h, qv, k, kc1, 1, shard_mode, d_a, d_i, d_l, labels, ucount, ulist, true)))
     return rc;
-  int m = 0;
-  CUDA_TRY(h, cudaMemcpyAsync(&m, ucount, 4, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(h, cudaStreamSynchronize(s));
-  h->last_tier1_queries += nb;
-  h->last_tier1_uncertified += m;
-  h->last_tier1_kc = kc1;
-  if (kc1 < 128 ? (4 * int64_t(m) > nb) : (2 * int64_t(m) > nb)) {
-    h->t1_level = kc1 < 128 ? 1 : 2;
-    h->t1_hold = kTier1Hold;
-  }
-  if (m == 0) return RDB_OK;
-  // compact the uncertified queries and run tier 2 on them
-  CUDA_TRY(h, h->t2_qf.ensure(size_t(m) * D * 4));
-  CUDA_TRY(h, h->t2_qhi.ensure(size_t(m) * Dp * 2));
-  CUDA_TRY(h, h->t2_qlo.ensure(size_t(m) * Dp * 2));
-  CUDA_TRY(h, h->t2_qnorm.ensure(size_t(m) * 4));
-  CUDA_TRY(h, h->t2_a.ensure(size_t(m) * k * 4));
-  CUDA_TRY(h, h->t2_i.ensure(size_t(m) * k * 8));
-  CUDA_TRY(h, h->t2_l.ensure(size_t(m) * k * 4));
-  gather_f32_rows_kernel<<<(m + 7) / 8, 256, 0, s>>>(qv.qf, ulist, m, D, h->t2_qf.as<float>());
+  // ---- tier 2 on the queries tier 1 could not certify: compacted on the device, every launch device-sized from ucount
+  CUDA_TRY(h, h->t2_qf.ensure(size_t(nb) * D * 4));
+  CUDA_TRY(h, h->t2_qhi.ensure(size_t(nb) * Dp * 2));
+  CUDA_TRY(h, h->t2_qlo.ensure(size_t(nb) * Dp * 2));
+  CUDA_TRY(h, h->t2_qnorm.ensure(size_t(nb) * 4));
+  CUDA_TRY(h, h->t2_a.ensure(size_t(nb) * k * 4));
+  CUDA_TRY(h, h->t2_i.ensure(size_t(nb) * k * 8));
+  CUDA_TRY(h, h->t2_l.ensure(size_t(nb) * k * 4));
+  gather_f32_rows_kernel<<<std::min((nb + 7) / 8, h->num_sms * 4), 256, 0, s>>>(qv.qf, ulist, nb, D, h->t2_qf.as<float>(),
+                                                                                ucount);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
-  if ((rc = launch_ingest(h, h->t2_qf.as<float>(), m, 0, 0, nullptr, h->t2_qhi.p, h->t2_qlo.p, h->t2_qnorm.as<float>(),
-                          h->cur_hscale))) return rc;
-  QueryView sub{h->t2_qf.as<float>(), h->t2_qhi.p, h->t2_qlo.p, h->t2_qnorm.as<float>(), m};
+  if ((rc = launch_ingest(h, h->t2_qf.as<float>(), nb, 0, 0, nullptr, h->t2_qhi.p, h->t2_qlo.p, h->t2_qnorm.as<float>(),
+                          h->cur_hscale, nullptr, ucount))) return rc;
+  QueryView sub{h->t2_qf.as<float>(), h->t2_qhi.p, h->t2_qlo.p, h->t2_qnorm.as<float>(), nb};
   if ((rc = split3_search(h, sub, k, shard_mode, h->t2_a.as<float>(), h->t2_i.as<int64_t>(), h->t2_l.as<float>(), labels,
-                          false))) return rc;
-  scatter_results_kernel<<<(m * k + 255) / 256, 256, 0, s>>>(ulist, m, k, h->t2_a.as<float>(), h->t2_i.as<long long>(),
-                                                             h->t2_l.as<float>(), d_a, reinterpret_cast<long long*>(d_i),
-                                                             d_l);
+                          false, ucount, &ucount2))) return rc;
+  scatter_results_kernel<<<std::min((nb * k + 255) / 256, h->num_sms * 8), 256, 0, s>>>(
+      ulist, nb, k, h->t2_a.as<float>(), h->t2_i.as<long long>(), h->t2_l.as<float>(), d_a,
+      reinterpret_cast<long long*>(d_i), d_l, ucount);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
-  return RDB_OK;
+  return counts_post(h, ucount, ucount2, true, nb, kc1);
 }
 
 // ---- fp32 stores, k beyond the certified fused selectors (104 < k <= 2048): the same certificate idea on the dense-key
@@ -766,7 +864,7 @@ int largek_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mo
   CUDA_TRY(h, cudaGetLastError());
   int m = 0;
   CUDA_TRY(h, cudaMemcpyAsync(&m, ucount, 4, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(h, cudaStreamSynchronize(s));
+  CUDA_TRY(h, host_sync(h));
   h->last_uncertified += m;
   if (m > 0) {
     // exact CUDA-core dense keys + radix select for the queries the certificate refused
@@ -837,7 +935,8 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   const bool split = (algo == RDB_ALGO_TC) && !sixteen;
   const float* labels = (h->labels && h->nlabels == h->n) ? h->labels : nullptr;
   cudaStream_t s = h->stream;
-  h->last_uncertified = 0; h->last_tier1_queries = 0; h->last_tier1_uncertified = 0;
+  counts_resolve(h, false);
+  if (!h->counts_pending) { h->last_uncertified = 0; h->last_tier1_queries = 0; h->last_tier1_uncertified = 0; }
   // L2 on bf16 operands: when the tensor cores consume the 16-bit query copies they are staged as 2 q (norm slice)
   const bool tc_consumer = algo == RDB_ALGO_TC || (largek && sixteen && largek_use_tc(h, 1));
   h->cur_hscale = (tc_consumer && h->use_ext() && h->yext) ? 2.0f : 1.0f;
@@ -867,9 +966,11 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
       if (split) {
         CUDA_TRY(h, h->qhi.ensure(size_t(nb) * Dp * 2));
         CUDA_TRY(h, h->qlo.ensure(size_t(nb) * Dp * 2));
+        CUDA_TRY(h, h->qres.ensure(size_t(nb) * 4));
       }
       if ((rc = launch_ingest(h, qsrc, nb, normalize, 0, h->qf.as<float>(), split ? h->qhi.p : nullptr,
-                              split ? h->qlo.p : nullptr, h->qnorm.as<float>(), h->cur_hscale))) return rc;
+                              split ? h->qlo.p : nullptr, h->qnorm.as<float>(), h->cur_hscale,
+                              split ? h->qres.as<float>() : nullptr))) return rc;
       qv.qf = h->qf.as<float>(); qv.qhi = h->qhi.p; qv.qlo = h->qlo.p;
     }
     // ---- output views (device scratch when the caller's buffers are on the host)
@@ -915,7 +1016,8 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
       CUDA_TRY(h, cudaMemcpyAsync(out_a + b0 * k, d_a, size_t(nb) * k * 4, cudaMemcpyDeviceToHost, s));
       CUDA_TRY(h, cudaMemcpyAsync(out_idx + b0 * k, d_i, size_t(nb) * k * 8, cudaMemcpyDeviceToHost, s));
       if (out_lbl) CUDA_TRY(h, cudaMemcpyAsync(out_lbl + b0 * k, d_l, size_t(nb) * k * 4, cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(h, cudaStreamSynchronize(s));   // scratch is reused by the next batch
+      CUDA_TRY(h, host_sync(h));   // scratch is reused by the next batch
+      counts_resolve(h, true);
     }
   }
   return RDB_OK;
@@ -931,7 +1033,8 @@ const DevBufMember kScratch[] = {
     &rdb_handle::fb_i, &rdb_handle::fb_l, &rdb_handle::gthr, &rdb_handle::tcsync, &rdb_handle::stream_ctl,
     &rdb_handle::fkey, &rdb_handle::fidx, &rdb_handle::lk_scores, &rdb_handle::uncert1, &rdb_handle::t2_qf,
     &rdb_handle::t2_qhi, &rdb_handle::t2_qlo, &rdb_handle::t2_qnorm, &rdb_handle::t2_a, &rdb_handle::t2_i,
-    &rdb_handle::t2_l, &rdb_handle::dev_ctl, &rdb_handle::qext};
+    &rdb_handle::t2_l, &rdb_handle::dev_ctl, &rdb_handle::qext, &rdb_handle::qres,
+    &rdb_handle::res_stage};
 
 }  // namespace
 
@@ -969,7 +1072,7 @@ int rdb_create(int d, int metric, int store_dtype, int device, unsigned flags, r
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
   if (e != cudaSuccess) { delete h; cudaGetLastError(); return fail(nullptr, RDB_ERR_CUDA, std::string("rdb_create: ") + cudaGetErrorString(e)); }
   h->stream = h->own_stream;
-  if (cudaMalloc(&h->d_ynorm_max, 4) != cudaSuccess || cudaMemset(h->d_ynorm_max, 0, 4) != cudaSuccess) {
+  if (cudaMalloc(&h->d_ynorm_max, 8) != cudaSuccess || cudaMemset(h->d_ynorm_max, 0, 8) != cudaSuccess) {
     cudaGetLastError();
     rdb_destroy(h);
     return fail(nullptr, RDB_ERR_NOMEM, "rdb_create: device allocation failed");
@@ -989,6 +1092,8 @@ int rdb_destroy(rdb_handle* h) {
     for (auto m : kScratch) (h->*m).release();
     h->np_tab.release();
     if (h->pin) cudaFreeHost(h->pin);
+    if (h->pin_counts) cudaFreeHost(h->pin_counts);
+    if (h->ev_counts) cudaEventDestroy(h->ev_counts);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1019,7 +1124,7 @@ int rdb_use_own_stream(rdb_handle* h) {
 int rdb_sync(rdb_handle* h) {
   if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
   DeviceGuard dg(h->device);
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, host_sync(h));
   return RDB_OK;
 }
 
@@ -1055,9 +1160,15 @@ int rdb_add(rdb_handle* h, const float* x, int64_t n, int mem, int normalize) {
     float* master = h->has_master() ? h->master + row0 * D : nullptr;
     void* hi = reinterpret_cast<char*>(h->hi) + size_t(row0) * Dp * es;
     void* lo = h->has_lo() ? reinterpret_cast<char*>(h->lo) + size_t(row0) * Dp * es : nullptr;
-    if ((rc = launch_ingest(h, src, m, normalize, norm_of_hi, master, hi, lo, h->ynorm + row0))) return rc;
+    float* res2 = nullptr;
+    if (lo) { CUDA_TRY(h, h->res_stage.ensure(size_t(m) * 4)); res2 = h->res_stage.as<float>(); }
+    if ((rc = launch_ingest(h, src, m, normalize, norm_of_hi, master, hi, lo, h->ynorm + row0, 1.0f, res2))) return rc;
     ynorm_max_kernel<<<unsigned(std::min<int64_t>((m + 255) / 256, 1024)), 256, 0, h->stream>>>(h->ynorm + row0, m,
                                                                                             h->d_ynorm_max);
+    if (res2) {
+      ynorm_max_kernel<<<unsigned(std::min<int64_t>((m + 255) / 256, 1024)), 256, 0, h->stream>>>(res2, m, h->d_ynorm_max + 1);
+      h->launches++;
+    }
     {
       // minima of the (aligned) 32-row groups these rows touch; unfilled rows of the last group still hold |y|^2 = 0,
       // which only loosens the bound until they are added
@@ -1069,7 +1180,7 @@ int rdb_add(rdb_handle* h, const float* x, int64_t n, int mem, int normalize) {
         ynorm_min32_kernel<<<unsigned((g1 - g0 + 1 + 7) / 8), 256, 0, h->stream>>>(h->ynorm, g0, g1 - g0 + 1, h->ynmin32);
     }
     h->launches += 2;
-    if (mem == RDB_MEM_HOST) CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // staging buffer reuse
+    if (mem == RDB_MEM_HOST) CUDA_TRY(h, host_sync(h));  // staging buffer reuse
   }
   h->n += n;
   return RDB_OK;
@@ -1202,7 +1313,7 @@ int rdb_reconstruct_batch(rdb_handle* h, const int64_t* ids, int64_t n, int mem,
   CUDA_TRY(h, cudaGetLastError());
   if (mem == RDB_MEM_HOST) {
     CUDA_TRY(h, cudaMemcpyAsync(out, d_out, size_t(n) * D * 4, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, host_sync(h));
   }
   return RDB_OK;
 }
@@ -1224,7 +1335,7 @@ int rdb_set_labels(rdb_handle* h, const float* labels, int64_t n) {
   if (n == 0) return RDB_OK;
   CUDA_TRY(h, cudaMalloc(&h->labels, size_t(n) * 4));
   CUDA_TRY(h, cudaMemcpyAsync(h->labels, labels, size_t(n) * 4, cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, host_sync(h));
   h->nlabels = n;
   return RDB_OK;
 }
@@ -1266,7 +1377,7 @@ int rdb_label_vote(rdb_handle* h, const float* lbl, int64_t nq, int k, int kvote
   CUDA_TRY(h, cudaGetLastError());
   if (mem == RDB_MEM_HOST) {
     CUDA_TRY(h, cudaMemcpyAsync(vote, d_v, size_t(nq) * 4, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, host_sync(h));
   }
   return RDB_OK;
 }
@@ -1276,6 +1387,7 @@ int rdb_dim(rdb_handle* h) { return h ? h->d : 0; }
 int rdb_metric(rdb_handle* h) { return h ? h->metric : -1; }
 int rdb_store_dtype(rdb_handle* h) { return h ? h->store : -1; }
 int64_t rdb_launch_count(rdb_handle* h) { return h ? h->launches : 0; }
+int64_t rdb_host_sync_count(rdb_handle* h) { return h ? h->host_syncs : 0; }
 
 int rdb_set_id_offset(rdb_handle* h, int64_t offset) {
   if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
@@ -1296,10 +1408,21 @@ int rdb_last_kernel_ms(rdb_handle* h, float* ms, int* algo, int* nsplits) {
   return RDB_OK;
 }
 
-int64_t rdb_last_uncertified(rdb_handle* h) { return h ? h->last_uncertified : 0; }
+int64_t rdb_last_uncertified(rdb_handle* h) {
+  if (!h) return 0;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  counts_resolve(h, true);             // the counters travel behind the search: wait for them
+  return h->last_uncertified;
+}
 
 int rdb_last_tier1(rdb_handle* h, int64_t* queries, int64_t* uncertified, int* candidates) {
   if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard dg(h->device);
+    counts_resolve(h, true);
+  }
   if (queries) *queries = h->last_tier1_queries;
   if (uncertified) *uncertified = h->last_tier1_uncertified;
   if (candidates) *candidates = h->last_tier1_queries > 0 ? h->last_tier1_kc : 0;
@@ -1331,7 +1454,7 @@ int rdb_release_scratch(rdb_handle* h) {
   if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
   std::lock_guard<std::mutex> lock(h->mu);
   DeviceGuard dg(h->device);
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, host_sync(h));
   for (auto m : kScratch) (h->*m).release();
   if (h->pin) cudaFreeHost(h->pin);
   h->pin = nullptr; h->pin_bytes = 0;
@@ -1347,14 +1470,14 @@ int rdb_truncate(rdb_handle* h, int64_t n_keep) {
   DeviceGuard dg(h->device);
   if (n_keep < 0 || n_keep > h->n) return fail(h, RDB_ERR_INVALID, "truncate: n_keep must be in [0, ntotal]");
   if (n_keep == h->n) return RDB_OK;
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, host_sync(h));
   // forgotten rows must look like never-filled ones: |y|^2 = 0 keeps the group minima a valid (loose) lower bound
   CUDA_TRY(h, cudaMemsetAsync(h->ynorm + n_keep, 0, size_t(h->n - n_keep) * 4, h->stream));
   const int64_t g0 = n_keep / 32, g1 = (h->n - 1) / 32;
   ynorm_min32_kernel<<<unsigned((g1 - g0 + 1 + 7) / 8), 256, 0, h->stream>>>(h->ynorm, g0, g1 - g0 + 1, h->ynmin32);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, host_sync(h));
   h->n = n_keep;                       // labels (if any) no longer match ntotal -> ignored until set again
   return RDB_OK;
 }
@@ -1370,6 +1493,7 @@ int rdb_set_option(rdb_handle* h, const char* name, int64_t value) {
   else if (n == "tc_stages") o.tc_stages = int(value);
   else if (n == "tc_query_stationary") o.tc_query_stationary = int(value);
   else if (n == "tc_pivot") o.tc_pivot = int(value);
+  else if (n == "tc_chunks") o.tc_chunks = int(std::min<int64_t>(std::max<int64_t>(value, 0), 256 / TC_LISTS));
   else if (n == "tier1") o.tier1 = int(value);
   else if (n == "tier1_kc") o.tier1_kc = int(value);
   else if (n == "largek_scorer") o.largek_scorer = int(value);

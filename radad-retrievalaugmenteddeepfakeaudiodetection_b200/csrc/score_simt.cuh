@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(256) score_select_simt_kernel(const T* __restr
                                                                 float* __restrict__ cand_key,
                                                                 int* __restrict__ cand_idx, int kout,
                                                                 float* __restrict__ dump = nullptr,
-                                                                long long dump_pitch = 0, int dump_row0 = 0) {
+                                                                long long dump_pitch = 0, int dump_row0 = 0,
+                                                                const DevPlan* __restrict__ plan = nullptr) {
   extern __shared__ __align__(16) float smem[];
   float* As = smem;                                   // [2][BK][LD]
   float* Bs = As + 2 * SIMT_BK * SIMT_LD;             // [2][BK][LD]
@@ -97,22 +98,27 @@ __global__ void __launch_bounds__(256) score_select_simt_kernel(const T* __restr
   float* Yn = Ss + SIMT_BM * SIMT_SLD;                // [BN]
 
   const int tid = threadIdx.x;
-  const int qtile = blockIdx.x % nqt;
-  const int chunk = blockIdx.x / nqt;
-  const long long q0 = (long long)qtile * SIMT_BM;
-  const int row_begin = (DUMP ? dump_row0 : 0) + chunk * rows_per_chunk;
-  const int row_end = min(N, row_begin + rows_per_chunk);
-
+  // device-sized launch (DevPlan): the grid covers the worst case, the real extent comes from the plan
+  int num_units = nqt * S;
+  if (plan) {
+    nq = __ldcg(&plan->nq); nqt = __ldcg(&plan->s_nqt); S = __ldcg(&plan->s_S); rows_per_chunk = __ldcg(&plan->s_rows);
+    num_units = __ldcg(&plan->s_units);
+    if (nq <= 0) return;
+  }
   const int ty = tid >> 4, tx = tid & 15;
   // loader mapping: two float4 per operand per thread
   const int lrow0 = tid >> 2, lk = (tid & 3) * 4;     // rows lrow0 and lrow0 + 64
-
   // scan mapping: thread -> (query row, column half)
   const int srow = tid >> 1, shalf = tid & 1;
+  const int nk = (D + SIMT_BK - 1) / SIMT_BK;
+  for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+  const int qtile = unit % nqt;
+  const int chunk = unit / nqt;
+  const long long q0 = (long long)qtile * SIMT_BM;
+  const int row_begin = (DUMP ? dump_row0 : 0) + chunk * rows_per_chunk;
+  const int row_end = min(N, row_begin + rows_per_chunk);
   TopK<KT> top;
   top.init();
-
-  const int nk = (D + SIMT_BK - 1) / SIMT_BK;
 
   for (int n0 = row_begin; n0 < row_end; n0 += SIMT_BN) {
     float acc[8][8];
@@ -205,6 +211,8 @@ __global__ void __launch_bounds__(256) score_select_simt_kernel(const T* __restr
 #pragma unroll
     for (int j = 0; j < KT; ++j)
       if (j < kout) { cand_key[base + j] = top.key[j]; cand_idx[base + j] = top.idx[j]; }
+  }
+  __syncthreads();      // the next unit of this block reuses the shared tiles
   }
 }
 

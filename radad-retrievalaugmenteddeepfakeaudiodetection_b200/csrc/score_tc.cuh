@@ -85,6 +85,7 @@ struct TcParams {
   int nstages;              // ring slots used (<= TcCfg::STAGES; option "tc_stages")
   int astat;                // query-stationary form (host: nterms == 1 && D <= 256)
   const int* run_if;        // fallback launch: all CTAs exit at once unless *run_if != 0 (null = always run)
+  const DevPlan* plan;      // device-sized launch (see DevPlan): nq / nqt / S / tiles_per_chunk / num_units come from here
   // k > 128 path (SelectDump): the launch covers rows [row_base, N) only (row_base a multiple of 256; tile t stands
   // for rows row_base + 256 t ...) and writes key(q, row) to dump[q * dump_pitch + row - row_base]
   int row_base;
@@ -259,6 +260,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
   using Cfg = TcCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
   if (p.run_if && __ldcg(p.run_if) == 0) return;     // uniform across the grid (and both CTAs of a pair)
+  // schedule: from the host, or (device-sized launches) from the plan a planning kernel wrote -- uniform either way
+  int s_nq = p.nq, s_nqt = p.nqt, s_S = p.S, s_tpc = p.tiles_per_chunk, s_units = p.num_units;
+  if (p.plan) {
+    s_nq = __ldcg(&p.plan->nq); s_nqt = __ldcg(&p.plan->nqg); s_S = __ldcg(&p.plan->S); s_tpc = __ldcg(&p.plan->tpc);
+    s_units = __ldcg(&p.plan->num_units);
+    if (s_nq <= 0) return;
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -310,17 +318,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
       int stage = 0;
       uint32_t phase = 0, aphase = 0;
       int slot = 0;
-      for (int unit = group; unit < p.num_units; unit += ngroups, ++slot) {
-        const int qtile = (unit % p.nqt) * CG + rank, chunk = unit / p.nqt;
-        const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
+      for (int unit = group; unit < s_units; unit += ngroups, ++slot) {
+        const int qtile = (unit % s_nqt) * CG + rank, chunk = unit / s_nqt;
+        const int t0 = chunk * s_tpc, t1 = min(p.ntiles, t0 + s_tpc);
         // lock-step window: members = units of this slot that run this chunk (a slot of ngroups consecutive units
         // touches at most sync_span = ceil(ngroups / nqt) + 1 chunks)
-        const int u_lo = max(slot * ngroups, chunk * p.nqt);
-        const int u_hi = min(min((slot + 1) * ngroups, (chunk + 1) * p.nqt), p.num_units);
+        const int u_lo = max(slot * ngroups, chunk * s_nqt);
+        const int u_hi = min(min((slot + 1) * ngroups, (chunk + 1) * s_nqt), s_units);
         const uint32_t members = uint32_t(u_hi - u_lo);
         const bool counted = p.sync != nullptr && rank == 0 && members > 1;
         bool waiting = counted && ld_relaxed_u32(p.sync_broken) == 0u;
-        uint32_t* ctr = p.sync + (size_t(slot) * p.sync_span + size_t(chunk - (slot * ngroups) / p.nqt)) * p.sync_groups;
+        uint32_t* ctr = p.sync + (size_t(slot) * p.sync_span + size_t(chunk - (slot * ngroups) / s_nqt)) * p.sync_groups;
         uint32_t seen = 0;
         if (astat) {
           // the unit's query tile: loaded once, after every MMA of the previous unit has retired
@@ -396,9 +404,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
     if (lane == 0 && rank == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0, aphase = 0;
-      for (int unit = group; unit < p.num_units; unit += ngroups) {
-        const int chunk = unit / p.nqt;
-        const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
+      for (int unit = group; unit < s_units; unit += ngroups) {
+        const int chunk = unit / s_nqt;
+        const int t0 = chunk * s_tpc, t1 = min(p.ntiles, t0 + s_tpc);
         if (astat) { mbar_wait(afull_bar, aphase); tc_fence_after(); aphase ^= 1; }
         for (int t = t0; t < t1; ++t) {
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -439,13 +447,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
     const int row = ew * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int unit = group; unit < p.num_units; unit += ngroups) {
-      const int qtile = (unit % p.nqt) * CG + rank, chunk = unit / p.nqt;
-      const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
+    for (int unit = group; unit < s_units; unit += ngroups) {
+      const int qtile = (unit % s_nqt) * CG + rank, chunk = unit / s_nqt;
+      const int t0 = chunk * s_tpc, t1 = min(p.ntiles, t0 + s_tpc);
       const long long q = (long long)qtile * TC_BM + row;
       Sel sel;
-      sel.init(p.kout, (p.gthr && q < p.nq) ? p.gthr + q : nullptr);
-      if constexpr (Sel::kDump) sel.row = (q < p.nq) ? p.dump + q * p.dump_pitch - p.row_base : nullptr;
+      sel.init(p.kout, (p.gthr && q < s_nq) ? p.gthr + q : nullptr);
+      if constexpr (Sel::kDump) sel.row = (q < s_nq) ? p.dump + q * p.dump_pitch - p.row_base : nullptr;
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
@@ -488,8 +496,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      if (q < p.nq) {
-        const long long base = ((q * p.S + chunk) * TC_LISTS + half) * (long long)p.kout;
+      if (q < s_nq) {
+        const long long base = ((q * s_S + chunk) * TC_LISTS + half) * (long long)p.kout;
         sel.finalize(p.kout, p.cand_key + base, p.cand_idx + base);
       }
     }

@@ -123,6 +123,11 @@ class FlatIndex(_ReconstructCache):
     def launch_count(self) -> int:
         return int(self._lib.rdb_launch_count(self._h))
 
+    @property
+    def host_sync_count(self) -> int:
+        """Times a call on this index blocked the host on its stream (device-tensor searches must not)."""
+        return int(self._lib.rdb_host_sync_count(self._h))
+
     # ------------------------------------------------------------------ helpers
     def _check(self, rc):
         _cabi.check(rc, self._h)

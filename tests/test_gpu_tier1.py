@@ -126,3 +126,52 @@ def test_tier1_partial_certification_clustered(pkg, oracle):
     Ds, Is = idx.search(xq, k, algo="simt")
     np.testing.assert_array_equal(I, Is)
     np.testing.assert_allclose(D, Ds, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("scenario", ["clustered", "nothing_certifies", "gaussian_ip"])
+def test_device_path_is_stream_ordered(pkg, oracle, scenario):
+    """Device-tensor searches of fp32 stores never block the host: how many queries each tier must re-search is known on
+    the device only, and every follow-up launch (compaction, three-term pass, exact CUDA-core search, scatter) is sized
+    there from the count (DevPlan) instead of reading it back.  Same answers as the host path, zero host
+    synchronisations inside `search`, also when every query walks all three tiers."""
+    import torch
+    if scenario == "nothing_certifies":
+        rng = np.random.default_rng(3)
+        N, Dm, Q, k, metric = 270_000, 32, 300, 10, pkg.METRIC_L2
+        xb = rng.integers(-2, 3, size=(N, Dm)).astype(np.float32)
+        for j in range(5):
+            xb[10_000 * (j + 1):10_000 * (j + 1) + 200] = xb[j]
+        xq = np.stack([xb[i % 5] for i in range(Q)])
+    elif scenario == "clustered":
+        N, Dm, Q, k, metric = 280_000, 48, 700, 15, pkg.METRIC_L2
+        xb = _gauss(N, Dm, 21)
+        xb[100_000:100_200] = xb[100_000]
+        xq = _gauss(Q, Dm, 22)
+        xq[4] = xb[100_000]
+        xq[9] = xb[100_000] + 1e-4
+        xq[650] = xb[100_007]
+    else:
+        N, Dm, Q, k, metric = 300_000, 96, 1000, 10, pkg.METRIC_IP
+        xb, xq = _gauss(N, Dm, 31), _gauss(Q, Dm, 32)
+    idx = pkg.FlatIndex(Dm, metric, "f32")
+    idx.add(xb)
+    Dh, Ih = idx.search(xq, k)                          # host path (synchronises by contract)
+    uncert_host = idx.last_uncertified
+    t1_host = idx.last_tier1
+    idx2 = pkg.FlatIndex(Dm, metric, "f32")             # fresh adaptive state: same tier decisions as the host run
+    idx2.add(xb)
+    q = torch.from_numpy(xq).cuda()
+    warm = pkg.FlatIndex(Dm, metric, "f32")
+    warm.add(xb[:270_000])
+    warm.search(q, k)                                   # (context / module warm-up only)
+    s0 = idx2.host_sync_count
+    Dd, Id = idx2.search(q, k)
+    assert idx2.host_sync_count == s0, "the device-tensor search blocked the host"
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(Id.cpu().numpy(), Ih)
+    np.testing.assert_array_equal(Dd.cpu().numpy(), Dh)
+    assert idx2.last_tier1 == t1_host and idx2.last_uncertified == uncert_host      # counters arrive behind the batch
+    if scenario == "nothing_certifies":
+        assert t1_host == (Q, Q) and uncert_host == Q
+    if scenario == "clustered":
+        assert uncert_host >= 3

@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 pkg = importlib.import_module("radad-retrievalaugmenteddeepfakeaudiodetection_b200")
 
 
-DEFAULTS = {"tc_cta_group": 0, "tc_lockstep": 8, "tc_lockstep_spins": 4096, "tc_stages": 64, "tc_query_stationary": 1,
+DEFAULTS = {"tc_cta_group": 0, "tc_lockstep": 8, "tc_lockstep_spins": 4096, "tc_stages": 64, "tc_chunks": 0, "tc_query_stationary": 1,
             "tc_pivot": 1, "tc_debug": 0, "tier1": 1, "tier1_kc": 0, "largek_scorer": 0, "largek_rows": 0,
             "largek_sample": 1, "largek_split": 1}
 
