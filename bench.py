@@ -253,6 +253,37 @@ def _percentiles(ms):
     return ms[len(ms) // 2], ms[min(len(ms) - 1, int(len(ms) * 0.99))]
 
 
+def single_process_e2e(torch, np, pkg, ngpus, q_np, steps, ref_ids):
+    """C3 through ONE VectorDatabase whose index is row-sharded over all GPUs of the box by this one process
+    (config.db_devices): pageable host numpy queries in, host numpy results out."""
+    class _Cfg:
+        vector_db_path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"rdb_bench_sp_{os.getpid()}")
+        vector_db_index_type = "IP"
+        top_k = K
+        db_dtype = "bf16"
+        db_devices = list(range(ngpus))
+    vdb = pkg.VectorDatabase(_Cfg())
+    vdb.create_index(DIM)
+    idx = vdb.index
+    idx.reserve(N_DB)
+    dev0 = torch.device("cuda", 0)
+    for c in range(-(-N_DB // GEN_CHUNK)):
+        idx.add(gen_db_chunk(torch, c, dev0), normalize=True)
+    for _ in range(2):
+        Dn, In = vdb.search_batch(q_np, k=K)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        Dn, In = vdb.search_batch(q_np, k=K)
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    out = {"value": NQ / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "n_gpus": ngpus,
+           "shard_rows": idx.shard_sizes, "h2d_bytes_per_step": NQ * DIM * 4, "d2h_bytes_per_step": NQ * K * 16,
+           "note": "one process, one VectorDatabase(db_devices=all GPUs), pageable numpy in/out: every GPU uploads its 1/N "
+                   "slice of the batch from its own host thread, NVLink exchange, per-GPU search, per-GPU slice merge",
+           "ids_equal_sharded_run": float((In[:len(ref_ids)] == ref_ids).all(1).mean()), "queries_compared": int(len(ref_ids))}
+    vdb.cleanup_gpu_resources()
+    return out
+
+
 def secondary_block(torch, np, pkg, orc, dev, q_dev, pk):
     """BASELINE.json configs[1] (C2), configs[3] (C4) and north_star (a) (ingest) on this GPU, in this run."""
     out = {}
@@ -475,6 +506,21 @@ def main():
     except Exception as e:  # noqa: BLE001
         corr["error"] = f"{type(e).__name__}: {e}"
 
+    # ---- N > 1: the same workload through ONE process driving every GPU (how pipeline.py:90 constructs the database):
+    #      rank 0 builds a second, row-sharded copy over all GPUs and times VectorDatabase.search_batch with pageable
+    #      host numpy in / out; the other ranks wait on the CPU (TCP store), so no collective kernel occupies their GPUs
+    sp = None
+    if world > 1 and not args.no_secondary:
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            try:
+                sp = single_process_e2e(torch, np, pkg, world, q_host.numpy(), args.steps, out[1][:4096].cpu().numpy())
+            except Exception as e:  # noqa: BLE001
+                sp = {"error": f"{type(e).__name__}: {e}"}
+            store.set("rdb_bench_sp_done", "1")
+        else:
+            store.wait(["rdb_bench_sp_done"])
+
     t = torch.tensor([ms_dev, ms_e2e, sum(kern_ms) / len(kern_ms)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -513,6 +559,8 @@ def main():
                          "hbm_frac": (rows_local * DIM * 2 / (ms_kern * 1e-3) / 1e9) / pk["hbm"]},
         }
         line["correctness"] = corr
+        if sp is not None:
+            line["e2e_single_process"] = sp
         if world == 1:
             orc = importlib.import_module("oracle.flat_oracle")
             if not args.no_cpu_baseline:

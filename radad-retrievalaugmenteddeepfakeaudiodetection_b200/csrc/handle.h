@@ -11,6 +11,8 @@
 #include <mutex>
 #include <string>
 
+#include "score_stream.cuh"
+
 namespace rdb {
 
 extern thread_local std::string g_err;     // last error of the calling thread (rdb_last_error(NULL))
@@ -93,7 +95,9 @@ struct rdb_handle {
   rdb::DevBuf qext;               // [nq][8] bf16 {1, 1, 1, 0, ...}: query side of the norm slice
   int64_t qext_rows = 0;
   rdb::DevBuf dev_ctl;            // device-side control words of the stream-ordered certified search (counts, flags)
-  void* pin = nullptr;            // pinned host staging of the small-batch path
+  void* pin = nullptr;            // pinned (mapped) host staging of the small-batch path: packed results [+ queries]
+  rdb::StreamParams stream_params = {};   // launch parameters of the small-batch search (carry the inline queries)
+  unsigned int stream_seq = 0;    // sequence number the latency path publishes in mapped host memory
   size_t pin_bytes = 0;
   float* d_ynorm_max = nullptr;   // [0] max |y|^2 over the shard, [1] max |y - y_hi|^2 (device scalars of the re-rank certificate)
   rdb::DevBuf np_tab;             // piece table of numpy's pairwise summation for rows of d floats (ingest.cuh: NpPlan)
@@ -134,8 +138,6 @@ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // ---- launchers exported by the per-family translation units (launch_tc.cu, launch_simt.cu, launch_stream.cu)
 struct TcParams;
-struct StreamParams;
-struct DevPlan;
 struct QueryView {
   const float* qf;    // fp32 [nq, D] (fp32 stores)
   const void* qhi;    // 16-bit [nq, Dp]

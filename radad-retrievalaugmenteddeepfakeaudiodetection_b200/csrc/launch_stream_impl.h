@@ -19,7 +19,7 @@ int launch_stream_kernel(rdb_handle* h, const StreamParams& p, int blocks, size_
 template <typename T, bool L2>
 int launch_stream_mode(rdb_handle* h, const StreamParams& p, int blocks, int mode) {
   const int nqt = p.nq <= 1 ? 1 : (p.nq <= 2 ? 2 : 4);
-  const size_t smem = stream_smem_bytes(nqt, p.ld, mode, p.np.nleaves);
+  const size_t smem = stream_smem_bytes(nqt, p.ld, mode, p.np.nleaves, p.q_raw ? 0 : p.nq * p.D);
 #define STREAM_NQ(MODE)                                                                         \
   (nqt == 1 ? launch_stream_kernel<T, 1, L2, MODE>(h, p, blocks, smem)                          \
             : (nqt == 2 ? launch_stream_kernel<T, 2, L2, MODE>(h, p, blocks, smem)              \

@@ -145,28 +145,30 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
                                                           const int* __restrict__ q_dev = nullptr,
                                                           const int* __restrict__ l_dev = nullptr) {
   const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (q_dev) Q = min(Q, __ldcg(q_dev));        // device-sized launch (DevPlan): the grid covers the worst case
+  if (q_dev) Q = min(Q, __ldcg(q_dev));        // device-sized launch (DevPlan): a small fixed grid walks the queries
   if (l_dev) L = __ldcg(l_dev);
-  if (q >= Q) return;
   if (run_if && __ldcg(run_if) == 0) return;
-  if (stage_bytes_per_warp > 0) {
-    // long merges (many lists x large k): every output rank would otherwise pay a dependent L2 round trip after a list's
-    // second entry.  Copy this query's L x kc candidates to shared memory once (coalesced) and merge from there.
-    extern __shared__ __align__(16) unsigned char merge_smem[];
-    unsigned char* mine = merge_smem + size_t(threadIdx.x >> 5) * stage_bytes_per_warp;
-    const int n = L * kc;
-    IdxT* sidx = reinterpret_cast<IdxT*>(mine);                                     // [n] ids first (8-byte aligned)
-    float* skey = reinterpret_cast<float*>(mine + size_t(n) * sizeof(IdxT));        // [n] keys
-    const long long qbase = (long long)q * n;
-    for (int i = lane; i < n; i += 32) { sidx[i] = __ldcg(idx_in + qbase + i); skey[i] = __ldcg(key_in + qbase + i); }
-    __syncwarp();
-    merge_lists_warp<IdxT, true, LPL>(skey, sidx, lbl_in, q, L, kc, kout, metric_l2, qnorm, id_offset, labels, out_dist,
-                                 out_idx, out_lbl, out_key, lane, nullptr);
-    return;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < Q; q += nwarps) {
+    if (stage_bytes_per_warp > 0) {
+      // long merges (many lists x large k): every output rank would otherwise pay a dependent L2 round trip after a
+      // list's second entry.  Copy this query's L x kc candidates to shared memory once (coalesced) and merge from there.
+      extern __shared__ __align__(16) unsigned char merge_smem[];
+      unsigned char* mine = merge_smem + size_t(threadIdx.x >> 5) * stage_bytes_per_warp;
+      const int n = L * kc;
+      IdxT* sidx = reinterpret_cast<IdxT*>(mine);                                     // [n] ids first (8-byte aligned)
+      float* skey = reinterpret_cast<float*>(mine + size_t(n) * sizeof(IdxT));        // [n] keys
+      const long long qbase = (long long)q * n;
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) { sidx[i] = __ldcg(idx_in + qbase + i); skey[i] = __ldcg(key_in + qbase + i); }
+      __syncwarp();
+      merge_lists_warp<IdxT, true, LPL>(skey, sidx, lbl_in, q, L, kc, kout, metric_l2, qnorm, id_offset, labels, out_dist,
+                                        out_idx, out_lbl, out_key, lane, nullptr);
+    } else {
+      merge_lists_warp<IdxT, false, LPL>(key_in, idx_in, lbl_in, q, L, kc, kout, metric_l2, qnorm, id_offset, labels,
+                                         out_dist, out_idx, out_lbl, out_key, lane, nullptr);
+    }
   }
-  merge_lists_warp<IdxT, false, LPL>(key_in, idx_in, lbl_in, q, L, kc, kout, metric_l2, qnorm, id_offset, labels, out_dist,
-                                     out_idx, out_lbl, out_key, lane, nullptr);
 }
 
 // A single, already sorted list per query (the k > 128 path with one row chunk): nothing to merge -- convert keys to
@@ -539,23 +541,33 @@ static __global__ void scatter_results_kernel(const int* __restrict__ list, int 
 
 // ---- planning kernels of the device-sized launches (DevPlan, common.cuh) -- one thread each ----------------------------
 // same cost model as the host's choose_splits (radad_flat.cu): waves * (tiles per chunk + per-unit overhead)
-__device__ __forceinline__ int plan_choose_splits(long long nqt, long long ntiles, int slots, int max_lists, int min_tiles,
+// (one warp: lane l evaluates S = l + 1, l + 33, ...; 32-bit arithmetic -- a single thread looping over 128 candidates with
+// 64-bit divisions took 39 us)
+__device__ __forceinline__ int plan_choose_splits(int nqt, int ntiles, int slots, int max_lists, int min_tiles,
                                                   float overhead, int* tpc_out) {
-  long long maxS = min((long long)max_lists, ntiles);
-  maxS = min(maxS, max(1ll, ntiles / max(min_tiles, 1)));
+  const int lane = threadIdx.x & 31;
+  int maxS = min(max_lists, ntiles);
+  maxS = min(maxS, max(1, ntiles / max(min_tiles, 1)));
   float best = 3.0e38f;
-  int bestS = 1;
-  long long best_tpc = ntiles;
-  for (long long S = 1; S <= maxS; ++S) {
-    const long long tpc = (ntiles + S - 1) / S;
-    const long long S2 = (ntiles + tpc - 1) / tpc;
-    if (S2 != S) continue;
-    const long long units = nqt * S2;
-    const long long waves = (units + slots - 1) / slots;
+  int bestS = 0x7FFFFFFF;
+  for (int S = lane + 1; S <= maxS; S += 32) {
+    const int tpc = (ntiles + S - 1) / S;
+    if ((ntiles + tpc - 1) / tpc != S) continue;
+    const unsigned units = unsigned(nqt) * unsigned(S);
+    const unsigned waves = (units + unsigned(slots) - 1u) / unsigned(slots);
     const float cost = float(waves) * (float(tpc) + overhead);
-    if (cost < best * 0.999f) { best = cost; bestS = int(S2); best_tpc = tpc; }
+    if (cost < best * 0.999f) { best = cost; bestS = S; }      // ascending S per lane: the host's tie rule (smallest S)
   }
-  *tpc_out = int(best_tpc);
+  // warp arg-min; ties (within 0.1 %) go to the smaller S like the host's ascending scan
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oS = __shfl_xor_sync(0xffffffffu, bestS, o);
+    if (ob < best * 0.999f || (ob <= best * 1.001f && oS < bestS && ob < 3.0e38f)) { best = fminf(ob, best); bestS = oS; }
+  }
+  bestS = __shfl_sync(0xffffffffu, bestS, 0);
+  if (bestS == 0x7FFFFFFF) bestS = 1;
+  *tpc_out = (ntiles + bestS - 1) / bestS;
   return bestS;
 }
 // Tensor-core stage over `*count` queries (clamped to cap): query-tile groups of 128 * cg queries, chunking chosen to
@@ -563,28 +575,36 @@ __device__ __forceinline__ int plan_choose_splits(long long nqt, long long ntile
 static __global__ void plan_tc_kernel(const int* __restrict__ count, int cap, int cg, long long ntiles, int slots,
                                       int max_lists, int min_tiles, float overhead, long long cand_lists_cap,
                                       DevPlan* __restrict__ plan) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;           // one warp
   const int nq = min(max(*count, 0), cap);
-  plan->nq = nq;
-  if (nq == 0) { plan->nqg = 0; plan->S = 1; plan->tpc = int(ntiles); plan->num_units = 0; plan->L = TC_PLAN_LISTS; return; }
+  if (nq == 0) {
+    if (threadIdx.x == 0) { plan->nq = 0; plan->nqg = 0; plan->S = 1; plan->tpc = int(ntiles); plan->num_units = 0; plan->L = TC_PLAN_LISTS; }
+    return;
+  }
   const int nqg = (nq + 128 * cg - 1) / (128 * cg);
   const long long lists_fit = max(1ll, cand_lists_cap / ((long long)nqg * 128 * cg) / TC_PLAN_LISTS);
   int tpc;
-  const int S = plan_choose_splits(nqg, ntiles, slots, int(min((long long)max_lists, lists_fit)), min_tiles, overhead, &tpc);
-  plan->nqg = nqg; plan->S = S; plan->tpc = tpc; plan->num_units = nqg * S; plan->L = S * TC_PLAN_LISTS;
+  const int S = plan_choose_splits(nqg, int(ntiles), slots, int(min((long long)max_lists, lists_fit)), min_tiles, overhead, &tpc);
+  if (threadIdx.x == 0) {
+    plan->nq = nq; plan->nqg = nqg; plan->S = S; plan->tpc = tpc; plan->num_units = nqg * S; plan->L = S * TC_PLAN_LISTS;
+  }
 }
 // CUDA-core stage (exact fallback) over `*count` queries: 128-query tiles x chunks of 128-row tiles, 2 lists per chunk
 static __global__ void plan_simt_kernel(const int* __restrict__ count, int cap, long long ntiles, int slots, int max_lists,
                                         long long cand_lists_cap, DevPlan* __restrict__ plan) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;           // one warp
   const int nq = min(max(*count, 0), cap);
-  plan->nq = nq;
-  if (nq == 0) { plan->s_nqt = 0; plan->s_S = 1; plan->s_rows = 128; plan->s_units = 0; plan->s_L = 2; return; }
+  if (nq == 0) {
+    if (threadIdx.x == 0) { plan->nq = 0; plan->s_nqt = 0; plan->s_S = 1; plan->s_rows = 128; plan->s_units = 0; plan->s_L = 2; }
+    return;
+  }
   const int nqt = (nq + 127) / 128;
   const long long lists_fit = max(1ll, cand_lists_cap / ((long long)nqt * 128) / 2);
   int tpc;
-  const int S = plan_choose_splits(nqt, ntiles, slots, int(min((long long)max_lists, lists_fit)), 2, 2.0f, &tpc);
-  plan->s_nqt = nqt; plan->s_S = S; plan->s_rows = tpc * 128; plan->s_units = nqt * S; plan->s_L = S * 2;
+  const int S = plan_choose_splits(nqt, int(ntiles), slots, int(min((long long)max_lists, lists_fit)), 2, 2.0f, &tpc);
+  if (threadIdx.x == 0) {
+    plan->nq = nq; plan->s_nqt = nqt; plan->s_S = S; plan->s_rows = tpc * 128; plan->s_units = nqt * S; plan->s_L = S * 2;
+  }
 }
 
 // Fused gather + merge over NVLink peer memory (multi-GPU row shards).  Each rank left its [Q][k] candidates

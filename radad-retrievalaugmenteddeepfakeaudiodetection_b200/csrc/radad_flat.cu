@@ -91,6 +91,7 @@ int np_plan_build(rdb_handle* h) {
   std::vector<int> offs, lens, ops;
   bool balanced = true;
   np_plan_rec(0, h->d, offs, lens, ops, &balanced);
+  for (size_t i = 1; i < lens.size(); ++i) balanced = balanced && lens[i] == lens[0];      // ... of EQUAL pieces
   h->np_balanced = balanced ? 1 : 0;
   std::vector<int> tab(offs);
   tab.insert(tab.end(), lens.begin(), lens.end());
@@ -100,7 +101,7 @@ int np_plan_build(rdb_handle* h) {
   h->np_nleaves = int(offs.size()); h->np_nops = int(ops.size() / 2);
   return RDB_OK;
 }
-NpPlan np_plan(rdb_handle* h) { return NpPlan{h->np_tab.as<int>(), h->np_nleaves, h->np_nops, h->np_balanced}; }
+NpPlan np_plan(rdb_handle* h) { return NpPlan{h->np_tab.as<int>(), h->np_nleaves, h->np_nops, h->np_balanced, h->d}; }
 
 // launch the fused ingest kernel (also used to prepare queries)
 int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int norm_of_hi, float* master, void* hi,
@@ -312,8 +313,11 @@ bool stream_filter_ok(int k, int sample_mul) {
   return k > 32 && sample_mul >= 4 && stream_pivot_rank(k, sample_mul) <= 128;
 }
 
-// The whole nq <= 4 search.  Host buffers go through one pinned staging area: one H2D copy of the queries, the
-// launches, ONE D2H copy of the packed results.
+// The whole nq <= 4 search.  Host buffers (the `predict()` latency path) never touch a copy engine when the queries fit
+// the kernel parameters (nq * D <= STREAM_QINLINE floats): the queries ride in the launch itself, the kernel writes the
+// packed results straight into mapped pinned host memory and publishes a sequence number there; the host spins on it.
+// One launch, no cudaMemcpy, no stream synchronisation: ~10 us of host overhead instead of ~29 us.  Larger inputs use
+// one pinned staging area: one H2D copy of the queries, the launches, ONE D2H copy of the packed results.
 int search_stream(rdb_handle* h, const float* q, int nq, int k, int mem, int normalize, bool shard_mode, float* out_a,
                   int64_t* out_idx, float* out_lbl, float* out_qnorm) {
   const int D = h->d;
@@ -333,10 +337,12 @@ int search_stream(rdb_handle* h, const float* q, int nq, int k, int mem, int nor
     CUDA_TRY(h, h->stream_ctl.ensure(sizeof(StreamCtl)));
     CUDA_TRY(h, cudaMemsetAsync(h->stream_ctl.p, 0, sizeof(StreamCtl), s));
   }
-  // packed device outputs (host path): [a nq*k f32][lbl nq*k f32][qnorm 4 f32][idx nq*k i64]
+  // packed outputs (host path): [a nq*k f32][lbl nq*k f32][qnorm 4 f32][idx nq*k i64][flag u32 ...]
   const size_t nk = size_t(nq) * k;
-  const size_t off_l = nk * 4, off_qn = 2 * nk * 4, off_i = 2 * nk * 4 + 16, pack_bytes = off_i + nk * 8;
+  const size_t off_l = nk * 4, off_qn = 2 * nk * 4, off_i = 2 * nk * 4 + 16, off_flag = off_i + nk * 8;
+  const size_t pack_bytes = off_flag + 16;
   const size_t q_bytes = size_t(nq) * D * 4;
+  const bool zero_copy = host && size_t(nq) * D <= size_t(STREAM_QINLINE);
   float* d_a = out_a; int64_t* d_i = out_idx; float* d_l = out_lbl; float* d_qn = out_qnorm;
   const float* qsrc = q;
   if (host) {
@@ -344,52 +350,93 @@ int search_stream(rdb_handle* h, const float* q, int nq, int k, int mem, int nor
       if (h->pin) cudaFreeHost(h->pin);
       h->pin = nullptr; h->pin_bytes = 0;
       const size_t want = std::max<size_t>(pack_bytes + q_bytes, 1 << 16);
-      CUDA_TRY(h, cudaHostAlloc(&h->pin, want, cudaHostAllocDefault));
+      CUDA_TRY(h, cudaHostAlloc(&h->pin, want, cudaHostAllocMapped));
       h->pin_bytes = want;
+      memset(h->pin, 0, want);
     }
-    CUDA_TRY(h, h->q_stage.ensure(q_bytes));
-    CUDA_TRY(h, h->o_dist.ensure(pack_bytes));
-    memcpy(static_cast<char*>(h->pin) + pack_bytes, q, q_bytes);
-    CUDA_TRY(h, cudaMemcpyAsync(h->q_stage.p, static_cast<char*>(h->pin) + pack_bytes, q_bytes, cudaMemcpyHostToDevice, s));
-    qsrc = h->q_stage.as<float>();
-    char* base = static_cast<char*>(h->o_dist.p);
+    char* base;
+    if (zero_copy) {
+      // the kernel writes the packed results into the pinned block itself (unified addressing: same pointer)
+      base = static_cast<char*>(h->pin);
+      qsrc = nullptr;
+    } else {
+      CUDA_TRY(h, h->q_stage.ensure(q_bytes));
+      CUDA_TRY(h, h->o_dist.ensure(pack_bytes));
+      memcpy(static_cast<char*>(h->pin) + pack_bytes, q, q_bytes);
+      CUDA_TRY(h, cudaMemcpyAsync(h->q_stage.p, static_cast<char*>(h->pin) + pack_bytes, q_bytes, cudaMemcpyHostToDevice, s));
+      qsrc = h->q_stage.as<float>();
+      base = static_cast<char*>(h->o_dist.p);
+    }
     d_a = reinterpret_cast<float*>(base);
     d_l = out_lbl ? reinterpret_cast<float*>(base + off_l) : nullptr;
     d_qn = reinterpret_cast<float*>(base + off_qn);
     d_i = reinterpret_cast<int64_t*>(base + off_i);
   }
-  StreamParams p;
-  memset(&p, 0, sizeof(p));
+  // one StreamParams is reused for every launch of the search (it carries up to 8 KB of inline queries)
+  StreamParams& p = h->stream_params;
   p.ynorm = h->ynorm; p.N = int(h->n);
   p.q_raw = qsrc; p.nq = nq; p.D = D; p.normalize = normalize; p.np = np_plan(h);
+  if (zero_copy) memcpy(p.qin, q, q_bytes);
   p.rows_per_block = rpb; p.kout = k; p.step_mul = 1;
   p.cand_key = h->cand_key.as<float>(); p.cand_idx = h->cand_idx.as<int>();
+  p.fkey = nullptr; p.fidx = nullptr;
   p.ctl = h->stream_ctl.as<StreamCtl>();
+  p.use_pivot_out = 0; p.run_if_fallback = 0;
   p.id_offset = h->id_offset; p.labels = labels;
   p.out_dist = shard_mode ? nullptr : d_a; p.out_key = shard_mode ? d_a : nullptr;
   p.out_idx = reinterpret_cast<long long*>(d_i); p.out_lbl = d_l; p.out_qnorm = d_qn;
+  p.host_flag = nullptr; p.flag_seq = 0;
+  volatile unsigned int* flag = nullptr;
+  unsigned int seq = 0;
+  if (zero_copy) {
+    flag = reinterpret_cast<volatile unsigned int*>(static_cast<char*>(h->pin) + off_flag);
+    seq = ++h->stream_seq;
+    if (seq == 0) seq = ++h->stream_seq;
+    *flag = 0u;
+  }
   int rc;
   cudaEventRecord(h->ev0, s);
   if (mode == STREAM_FILTER) {
     CUDA_TRY(h, h->fkey.ensure(size_t(4) * STREAM_FCAP * 4));
     CUDA_TRY(h, h->fidx.ensure(size_t(4) * STREAM_FCAP * 4));
     p.fkey = h->fkey.as<float>(); p.fidx = h->fidx.as<int>();
-    StreamParams ps = p;                       // 1) pivot from a strided 1/64 sample (LIST, k = 16)
-    ps.kout = pivot_rank; ps.step_mul = sample_mul; ps.use_pivot_out = 1;
-    ps.out_dist = nullptr; ps.out_key = nullptr; ps.out_idx = nullptr; ps.out_lbl = nullptr; ps.out_qnorm = nullptr;
-    if ((rc = launch_stream(h, ps, S, pivot_rank <= 32 ? STREAM_LIST1 : STREAM_LIST4))) return rc;
+    // 1) pivot from a strided 1/64 sample (LIST, k = 16)
+    float* sv_dist = p.out_dist; float* sv_key = p.out_key; long long* sv_idx = p.out_idx; float* sv_lbl = p.out_lbl;
+    float* sv_qn = p.out_qnorm;
+    p.kout = pivot_rank; p.step_mul = sample_mul; p.use_pivot_out = 1;
+    p.out_dist = nullptr; p.out_key = nullptr; p.out_idx = nullptr; p.out_lbl = nullptr; p.out_qnorm = nullptr;
+    if ((rc = launch_stream(h, p, S, pivot_rank <= 32 ? STREAM_LIST1 : STREAM_LIST4))) return rc;
+    p.kout = k; p.step_mul = 1; p.use_pivot_out = 0;
+    p.out_dist = sv_dist; p.out_key = sv_key; p.out_idx = sv_idx; p.out_lbl = sv_lbl; p.out_qnorm = sv_qn;
     if ((rc = launch_stream(h, p, S, STREAM_FILTER))) return rc;      // 2) full pass: append key >= pivot, rank, emit
-    StreamParams pf = p;                       // 3) exits at once unless the FILTER pass raised the fallback flag
-    pf.run_if_fallback = 1;
-    if ((rc = launch_stream(h, pf, S, STREAM_LIST4))) return rc;
+    p.run_if_fallback = 1;                     // 3) exits at once unless the FILTER pass raised the fallback flag
+    p.host_flag = const_cast<unsigned int*>(flag); p.flag_seq = seq;   //    ... and publishes the results either way
+    if ((rc = launch_stream(h, p, S, STREAM_LIST4))) return rc;
   } else {
+    p.host_flag = const_cast<unsigned int*>(flag); p.flag_seq = seq;
     if ((rc = launch_stream(h, p, S, mode))) return rc;
   }
   cudaEventRecord(h->ev1, s);
   h->ev_valid = true; h->last_algo = RDB_ALGO_STREAM; h->last_S = S;
   if (host) {
-    CUDA_TRY(h, cudaMemcpyAsync(h->pin, h->o_dist.p, pack_bytes, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(h, host_sync(h));
+    if (zero_copy) {
+      // spin on the sequence number the last block publishes (bounded: fall back to the stream if nothing arrives)
+      unsigned long long spins = 0;
+      while (*flag != seq) {
+        if ((++spins & 0xFFFFF) == 0) {                         // every ~1M polls: is the stream dead?
+          const cudaError_t e = cudaStreamQuery(s);
+          if (e == cudaSuccess) { if (*flag == seq) break; return fail(h, RDB_ERR_CUDA, "stream search: results never published"); }
+          if (e != cudaErrorNotReady) { cudaGetLastError(); return fail(h, RDB_ERR_CUDA, std::string("stream search: ") + cudaGetErrorString(e)); }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    } else {
+      CUDA_TRY(h, cudaMemcpyAsync(h->pin, h->o_dist.p, pack_bytes, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(h, host_sync(h));
+    }
     const char* base = static_cast<const char*>(h->pin);
     memcpy(out_a, base, nk * 4);
     if (out_lbl) memcpy(out_lbl, base + off_l, nk * 4);
@@ -545,7 +592,7 @@ int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float*
                     const int* run_if = nullptr, const int* q_dev = nullptr, const int* l_dev = nullptr) {
   if (q_dev) {
     // device-sized launch (DevPlan): nq is the grid capacity, the real query / list counts are read on the device
-    dim3 grid((nq + 3) / 4), block(128);
+    dim3 grid(std::min((nq + 3) / 4, h->num_sms * 8)), block(128);
     merge_lists_kernel<int, MERGE_LPL><<<grid, block, 0, h->stream>>>(
         h->cand_key.as<float>(), h->cand_idx.as<int>(), nullptr, nq, L, kc, kout, h->metric == RDB_METRIC_L2 ? 1 : 0, qnorm,
         id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l, shard_mode ? d_a : raw_key,
@@ -637,7 +684,7 @@ int certified_pass(rdb_handle* h, const QueryView& v, int k, int kc, int nterms,
   const float eps = (nterms == 3 ? 3.02f * 3.814697265625e-06f /*2^-18*/
                                  : 0.00390625f /*2 * 2^-9*/ + 3.814697265625e-06f /*2^-18*/) + accum;
   const int warps = 4;
-  dim3 grid((nb + warps - 1) / warps), block(32 * warps);
+  dim3 grid(plan ? std::min((nb + warps - 1) / warps, h->num_sms * 8) : (nb + warps - 1) / warps), block(32 * warps);
   dim3 rgrid(plan ? std::min(nb, h->num_sms * 8) : nb), rblock(RERANK_THREADS);     // re-rank: one block per query
   if (l2) rerank_exact_kernel<true><<<rgrid, rblock, 0, s>>>(
       h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, v.qf, h->master, h->ynorm, D, eps, v.qnorm,

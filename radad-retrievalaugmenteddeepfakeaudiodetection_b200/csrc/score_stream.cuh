@@ -37,17 +37,17 @@ constexpr int STREAM_WARPS = STREAM_THREADS / 32;
 template <typename T> struct StreamVec;
 template <> struct StreamVec<float> {
   static constexpr int EPV = 4;   // elements per 128-bit load
-  static constexpr int R = 4;     // rows in flight per warp
-  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-  }
+  static constexpr int R = 4;     // rows in flight per lane group
+  using Raw = float4;
+  __device__ static __forceinline__ Raw load_raw(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ static __forceinline__ void unpack(const Raw& x, float (&v)[4]) { v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; }
 };
 template <> struct StreamVec<__nv_bfloat16> {
   static constexpr int EPV = 8;
   static constexpr int R = 8;
-  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
-    const uint4 x = __ldg(reinterpret_cast<const uint4*>(p));
+  using Raw = uint4;
+  __device__ static __forceinline__ Raw load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ static __forceinline__ void unpack(const Raw& x, float (&v)[8]) {
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
@@ -56,8 +56,9 @@ template <> struct StreamVec<__nv_bfloat16> {
 template <> struct StreamVec<__half> {
   static constexpr int EPV = 8;
   static constexpr int R = 8;
-  __device__ static __forceinline__ void load(const __half* p, float (&v)[8]) {
-    const uint4 x = __ldg(reinterpret_cast<const uint4*>(p));
+  using Raw = uint4;
+  __device__ static __forceinline__ Raw load_raw(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ static __forceinline__ void unpack(const Raw& x, float (&v)[8]) {
     const __half2* h = reinterpret_cast<const __half2*>(&x);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
@@ -106,6 +107,7 @@ struct WarpList {
 enum { STREAM_LIST1 = 0, STREAM_LIST4 = 1, STREAM_FILTER = 2 };
 constexpr int STREAM_FCAP = 4096;       // FILTER: candidate slots per query
 constexpr int STREAM_SAMPLE = 64;       // FILTER: the pivot pass reads every 64th warp step of the rows
+constexpr int STREAM_QINLINE = 2048;    // floats of query data a launch can carry in its parameters (8 KB: 2 x 768 ... 1 x 2048)
 constexpr int STREAM_PIVOT_RANK = 16;   // FILTER: minimum pivot rank in the sample (host raises it for thin samples)
 
 struct StreamCtl {                      // device control block owned by the handle (zero-initialised once)
@@ -127,6 +129,11 @@ struct StreamParams {
   int run_if_fallback;                                    // fallback launch: exit at once unless ctl->fallback != 0
   int metric_l2; long long id_offset; const float* labels;
   float* out_dist; long long* out_idx; float* out_lbl; float* out_key; float* out_qnorm;
+  // Latency path with HOST buffers: the queries travel inside the kernel parameters (q_raw == null: no host-to-device
+  // copy), the outputs point into mapped pinned host memory, and the last thing the search does is publish `flag_seq`
+  // in *host_flag (system-scope fence first) -- the host spins on it instead of a device-to-host copy + stream sync.
+  unsigned int* host_flag; unsigned int flag_seq;
+  float qin[STREAM_QINLINE];
 };
 
 template <> __device__ __forceinline__ float to16<float>(float v) { return v; }
@@ -140,7 +147,7 @@ __device__ __forceinline__ float stream_prep_query(const float* __restrict__ xr,
                                                    float* __restrict__ dst, int lane, const NpPlan& np, float* lv) {
   const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(xr) & 15) == 0);
   float denom = 1.0f;
-  if (normalize) denom = __fsqrt_rn(np_sumsq_global(xr, np, lv, lane)) + 1e-12f;   // numpy order: see NpPlan
+  if (normalize) denom = __fsqrt_rn(np_sumsq_global<false>(xr, np, lv, lane)) + 1e-12f;   // numpy order: see NpPlan
   float acc = 0.f;
   if (vec4) {
     const float4* x4 = reinterpret_cast<const float4*>(xr);
@@ -172,7 +179,7 @@ __device__ __forceinline__ float stream_prep_query(const float* __restrict__ xr,
 // Y [N, ld] stored rows (T = fp32 master or the 16-bit store), ld multiple of EPV, columns [D, ld) zero (16-bit) --
 // D itself must be a multiple of EPV for fp32 (checked by the host; otherwise another scorer is used).
 template <typename T, int NQ, bool L2, int MODE>
-__global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(const StreamParams p) {
+__global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(const __grid_constant__ StreamParams p) {
   constexpr int KL = (MODE == STREAM_LIST4) ? 4 : 1;
   extern __shared__ __align__(16) float sm[];
   __shared__ float s_qnorm[NQ];
@@ -182,12 +189,36 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ld = p.ld, nq = p.nq, kout = p.kout, N = p.N;
   const T* __restrict__ Y = reinterpret_cast<const T*>(p.Y);
-  if (p.run_if_fallback && __ldcg(&p.ctl->fallback) == 0) return;
+  if (p.run_if_fallback && __ldcg(&p.ctl->fallback) == 0) {
+    // nothing to redo: the FILTER pass (previous launch, complete) already wrote the results
+    if (p.host_flag && blockIdx.x == 0 && threadIdx.x == 0) { __threadfence_system(); *p.host_flag = p.flag_seq; }
+    return;
+  }
 
+  // ---- the first rows of this block's slice start travelling HBM -> L2 while the queries are prepared
+  {
+    const int row_begin0 = blockIdx.x * p.rows_per_block;
+    const int rows0 = min(N, row_begin0 + p.rows_per_block) - row_begin0;
+    const long long bytes = (long long)max(rows0, 0) * ld * (long long)sizeof(T);
+    const char* base = reinterpret_cast<const char*>(Y + (long long)row_begin0 * ld);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long off = ((long long)threadIdx.x + (long long)i * STREAM_THREADS) * 128;
+      if (off < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    }
+  }
   // ---- query prep (every block, redundantly: nq * D elements)
+  const float* qsrc = p.q_raw;
+  if (qsrc == nullptr) {
+    // queries inside the kernel parameters -> staged behind the prepared queries in shared memory
+    float* stage = sm + ((NQ * ld + NQ * p.np.nleaves + 3) & ~3);     // 16-byte aligned
+    for (int i = threadIdx.x; i < nq * p.D; i += STREAM_THREADS) stage[i] = p.qin[i];
+    __syncthreads();
+    qsrc = stage;
+  }
   if (warp < NQ) {
     if (warp < nq) {
-      const float n2 = stream_prep_query<T>(p.q_raw + (long long)warp * p.D, p.D, ld, p.normalize, qs + warp * ld, lane, p.np,
+      const float n2 = stream_prep_query<T>(qsrc + (long long)warp * p.D, p.D, ld, p.normalize, qs + warp * ld, lane, p.np,
                                                sm + NQ * ld + warp * p.np.nleaves);
       if (lane == 0) {
         s_qnorm[warp] = n2;
@@ -222,6 +253,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
   const int lpr = 1 << lpr_log2, G = 32 >> lpr_log2;
   const int grp = lane >> lpr_log2, l = lane & (lpr - 1);
   const int RW = R * G;
+  // (A manually double-buffered form of this loop -- next slice's loads issued before the current one is consumed -- was
+  // measured SLOWER: fp32 0.479 -> 0.596 ms, bf16 0.272 -> 0.281 ms at C4; the compiler's own schedule of the plain loop
+  // keeps more independent loads in flight than two conditional sets of R.)
   for (int r0 = row_begin + warp * RW; r0 < row_end; r0 += STREAM_WARPS * RW * p.step_mul) {
     float acc[R][NQ];
 #pragma unroll
@@ -233,15 +267,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int row = min(r0 + grp * R + r, row_end - 1);   // clamp: duplicates are discarded below
-        StreamVec<T>::load(Y + (long long)row * ld + c * EPV, y[r]);
+        StreamVec<T>::unpack(StreamVec<T>::load_raw(Y + (long long)row * ld + c * EPV), y[r]);
       }
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         float qv[EPV];
 #pragma unroll
         for (int e = 0; e < EPV; e += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(qs + q * ld + c * EPV + e);
-          qv[e] = t.x; qv[e + 1] = t.y; qv[e + 2] = t.z; qv[e + 3] = t.w;
+          const float4 t4 = *reinterpret_cast<const float4*>(qs + q * ld + c * EPV + e);
+          qv[e] = t4.x; qv[e + 1] = t4.y; qv[e + 2] = t4.z; qv[e + 3] = t4.w;
         }
 #pragma unroll
         for (int r = 0; r < R; ++r)
@@ -421,10 +455,17 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
     if (threadIdx.x < 4) p.ctl->fcount[threadIdx.x] = 0;
   }
   if (threadIdx.x == 0) p.ctl->ticket = 0;
+  if (p.host_flag && !p.use_pivot_out) {
+    // results live in mapped host memory: make every thread's writes visible system-wide, then publish
+    // (the block barrier orders every thread's result writes before thread 0's fence: fences are cumulative)
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence_system(); *reinterpret_cast<volatile unsigned int*>(p.host_flag) = p.flag_seq; }
+  }
 }
 
-constexpr size_t stream_smem_bytes(int nq_t, int ld, int mode, int np_leaves) {
-  const size_t a = size_t(nq_t) * ld * 4 + size_t(nq_t) * np_leaves * 4;   // queries + leaf sums of the norm
+constexpr size_t stream_smem_bytes(int nq_t, int ld, int mode, int np_leaves, int inline_floats) {
+  // prepared queries + leaf sums of the norm + (queries that arrived inside the kernel parameters) their raw copy
+  const size_t a = size_t(nq_t) * ld * 4 + size_t(nq_t) * np_leaves * 4 + size_t(inline_floats ? inline_floats + 4 : 0) * 4;
   const size_t b = (mode == STREAM_FILTER) ? size_t(STREAM_FCAP) * 8
                                            : size_t(nq_t) * STREAM_WARPS * 32 * (mode == STREAM_LIST4 ? 4 : 1) * 8;
   return a > b ? a : b;

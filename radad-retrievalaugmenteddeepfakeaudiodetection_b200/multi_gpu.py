@@ -52,8 +52,10 @@ class MultiGpuFlatIndex(_ReconstructCache):
         self._d, self._metric = int(d), int(metric)
         self.shards: List[FlatIndex] = [FlatIndex(d, metric, store, device=g, keep_f32_master=keep_f32_master)
                                         for g in self.devices]
-        for g in self.devices[1:]:
-            self.shards[0].enable_peer_access(g)        # the merge kernel on the primary reads every shard's lists
+        for a, ga in enumerate(self.devices):           # every GPU merges its slice of the queries from every shard's lists
+            for gb in self.devices:
+                if gb != ga:
+                    self.shards[a].enable_peer_access(gb)
         self.nprobe = 1
         self._ntotal = 0
         self._pool = None                               # host threads driving the shards (fp32 stores only)
@@ -209,69 +211,128 @@ class MultiGpuFlatIndex(_ReconstructCache):
         return shard[j], gid + delta[j]
 
     # ------------------------------------------------------------------ search
+    def _workers(self):
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=len(self.shards), thread_name_prefix="rdb-shard")
+        return self._pool
+
     def search(self, q, k: int, normalize: bool = False, algo=ALGO_AUTO, return_labels: bool = False):
         """index.search(q, k) -> (distances float32[nq,k], ids int64[nq,k]) best-first (vector_database.py:181);
-        numpy in -> numpy out, torch CUDA in -> torch CUDA out (on the queries' device)."""
+        numpy in -> numpy out, torch CUDA in -> torch CUDA out (on the queries' device).
+
+        Every GPU is driven by its own host thread (ctypes / torch release the GIL inside the driver calls):
+          1. input   numpy: GPU g uploads only ITS 1/G slice of the batch over its own PCIe link, in parallel with the
+                     others (a single upload to one GPU was 15 ms of a 99 ms step at C3 on 8 GPUs); CUDA tensor: one event
+                     orders the workers behind the caller's stream;
+          2. gather  the slices are exchanged GPU -> GPU over NVLink (P2P copies) so every GPU holds the whole batch;
+          3. search  every GPU runs the fused score+select kernels over its row shard, local ids -> global ids;
+          4. merge   GPU g merges ONLY the queries of its slice, loading the G candidate lists straight from the peers'
+                     memory (the fused gather+merge kernel), and writes its slice of the result to the caller's buffers.
+        """
+        import threading
         import torch
         k = int(k)
         cuda_in = _is_cuda_tensor(q)
-        prim = torch.device("cuda", self.devices[0])
         if cuda_in:
-            out_dev = q.device
-            qp = q.detach().to(prim, torch.float32, non_blocking=True).contiguous()
+            qsrc = q.detach().to(torch.float32).contiguous()
+            if qsrc.dim() != 2 or qsrc.shape[1] != self._d:
+                raise RuntimeError(f"expected float32 [nq, {self._d}], got {tuple(qsrc.shape)}")
         else:
-            qh = np.ascontiguousarray(q, dtype=np.float32)
-            if qh.ndim != 2 or qh.shape[1] != self._d:
-                raise RuntimeError(f"expected float32 [nq, {self._d}], got {qh.shape}")
-            qp = torch.from_numpy(qh).to(prim, non_blocking=True)
-        if qp.dim() != 2 or qp.shape[1] != self._d:
-            raise RuntimeError(f"expected float32 [nq, {self._d}], got {tuple(qp.shape)}")
-        nq = qp.shape[0]
+            qsrc = np.ascontiguousarray(q, dtype=np.float32)
+            if qsrc.ndim != 2 or qsrc.shape[1] != self._d:
+                raise RuntimeError(f"expected float32 [nq, {self._d}], got {qsrc.shape}")
+        nq = int(qsrc.shape[0])
         live = [g for g, s in enumerate(self.shards) if s.ntotal > 0]
         if not live:
             raise RuntimeError("search on an empty index")
-        # 1) broadcast the queries first: torch runs a cross-device copy on the SOURCE device's stream, so a copy issued
-        #    after the primary's own search had been enqueued would wait for it and serialise the GPUs
-        qs, streams = {}, {}
-        for g in live:
-            dev = torch.device("cuda", self.devices[g])
-            qs[g] = qp if dev == prim else qp.to(dev, non_blocking=True)        # P2P over NVLink
-            streams[g] = torch.cuda.current_stream(dev)     # the caller's stream (current streams are thread-local)
-        # 2) every GPU searches its shard concurrently.  16-bit stores are fully asynchronous (the launches return at
-        #    once); the certified fp32 path reads one counter back per batch, so each shard is driven from its own
-        #    host thread (ctypes releases the GIL inside the C call) and no GPU waits for another one's round trip.
-        def run(g):
-            with torch.cuda.device(self.devices[g]), torch.cuda.stream(streams[g]):
-                key, lid, lab, qn = self.shards[g].search_shard(qs[g], k, normalize=normalize)
-                gid = self._local_to_global(g, lid)
-                ev = torch.cuda.Event()
-                ev.record()
-            return key, gid, lab, qn, ev
-        if len(live) > 1 and self.store == "f32":
-            if self._pool is None:
-                from concurrent.futures import ThreadPoolExecutor
-                self._pool = ThreadPoolExecutor(max_workers=len(self.shards), thread_name_prefix="rdb-shard")
-            results = list(self._pool.map(run, live))
-        else:
-            results = [run(g) for g in live]
-        keys, gids, labs = [r[0] for r in results], [r[1] for r in results], [r[2] for r in results]
-        events, qn_first = [r[4] for r in results], results[0][3]
-        with torch.cuda.device(prim):
-            ps = torch.cuda.current_stream()
-            for ev in events:
-                ps.wait_event(ev)
-            for t in keys + gids + labs:
-                t.record_stream(ps)                 # read by the merge kernel on the primary's stream
-            qn0 = qn_first if qn_first.device == prim else qn_first.to(prim, non_blocking=True)
-            # ONE kernel: list g is loaded straight from GPU g's memory (P2P over NVLink) while merging
-            D, I, L = self.shards[0].merge_shards_peer([t.data_ptr() for t in keys], [t.data_ptr() for t in gids],
-                                                       [t.data_ptr() for t in labs], nq, k, qn0)
+        G = len(live)
+        per = -(-nq // G) if nq else 0
+        bounds = [(min(nq, t * per), min(nq, (t + 1) * per)) for t in range(G)]
         if cuda_in:
-            D, I, L = D.to(out_dev), I.to(out_dev), L.to(out_dev)
-            return (D, I, L) if return_labels else (D, I)
-        Dn, In, Ln = D.cpu().numpy(), I.cpu().numpy(), L.cpu().numpy()
-        self._rc_note_search(In)
-        return (Dn, In, Ln) if return_labels else (Dn, In)
+            outD = torch.empty((nq, k), dtype=torch.float32, device=qsrc.device)
+            outI = torch.empty((nq, k), dtype=torch.int64, device=qsrc.device)
+            outL = torch.empty((nq, k), dtype=torch.float32, device=qsrc.device)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(qsrc.device))          # the queries are final behind this event
+        else:
+            outD = np.empty((nq, k), dtype=np.float32)
+            outI = np.empty((nq, k), dtype=np.int64)
+            outL = np.empty((nq, k), dtype=np.float32)
+            ready = None
+        if nq == 0:
+            return (outD, outI, outL) if return_labels else (outD, outI)
+        barrier = threading.Barrier(G)
+        slices, fulls, cands, events, errors = [None] * G, [None] * G, [None] * G, [None] * G, []
+
+        def work(t):
+            g = live[t]
+            dev = torch.device("cuda", self.devices[g])
+            lo, hi = bounds[t]
+            try:
+                with torch.cuda.device(dev):
+                    st = torch.cuda.current_stream(dev)
+                    # 1) this GPU's slice of the queries
+                    if cuda_in:
+                        st.wait_event(ready)
+                        slices[t] = qsrc[lo:hi].to(dev, non_blocking=True)
+                    else:
+                        slices[t] = torch.from_numpy(qsrc[lo:hi]).to(dev)          # pageable: returns when copied
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    events[t] = ev
+                    barrier.wait()
+                    # 2) the whole batch on this GPU: peers' slices over NVLink
+                    if G == 1:
+                        full = slices[t]
+                    else:
+                        full = torch.empty((nq, self._d), dtype=torch.float32, device=dev)
+                        for u in range(G):
+                            a, b = bounds[u]
+                            if b > a:
+                                st.wait_event(events[u])
+                                full[a:b].copy_(slices[u], non_blocking=True)
+                    fulls[t] = full
+                    # 3) search the shard
+                    key, lid, lab, qn = self.shards[g].search_shard(full, k, normalize=normalize)
+                    gid = self._local_to_global(g, lid)
+                    ev2 = torch.cuda.Event()
+                    ev2.record(st)
+                    cands[t] = (key, gid, lab, qn, ev2)
+                    barrier.wait()
+                    # 4) merge this GPU's slice of the queries from every shard's lists (P2P loads), hand it back
+                    if hi > lo:
+                        for u in range(G):
+                            st.wait_event(cands[u][4])
+                        esz = k
+                        D, I, L = self.shards[g].merge_shards_peer(
+                            [cands[u][0].data_ptr() + lo * esz * 4 for u in range(G)],
+                            [cands[u][1].data_ptr() + lo * esz * 8 for u in range(G)],
+                            [cands[u][2].data_ptr() + lo * esz * 4 for u in range(G)], hi - lo, k, qn[lo:hi])
+                        if cuda_in:
+                            outD[lo:hi].copy_(D, non_blocking=True)
+                            outI[lo:hi].copy_(I, non_blocking=True)
+                            outL[lo:hi].copy_(L, non_blocking=True)
+                        else:
+                            torch.from_numpy(outD[lo:hi]).copy_(D)
+                            torch.from_numpy(outI[lo:hi]).copy_(I)
+                            torch.from_numpy(outL[lo:hi]).copy_(L)
+                    st.synchronize()               # the peers' lists must stay alive until every merge has read them
+                    barrier.wait()
+            except BaseException as e:  # noqa: BLE001 - a failing worker must not leave the others at a barrier
+                errors.append(e)
+                barrier.abort()
+
+        if G == 1:
+            work(0)
+        else:
+            list(self._workers().map(work, range(G)))
+        real = [e for e in errors if not isinstance(e, threading.BrokenBarrierError)]
+        if real or errors:
+            raise (real or errors)[0]
+        if not cuda_in:
+            self._rc_note_search(outI)
+        return (outD, outI, outL) if return_labels else (outD, outI)
 
     # ------------------------------------------------------------------ reconstruct
     def reconstruct(self, i: int) -> np.ndarray:

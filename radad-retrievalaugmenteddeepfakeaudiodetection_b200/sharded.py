@@ -160,8 +160,26 @@ class ShardedFlatIndex:
             # stream-ordered barrier: completes on this stream only after every rank's shard search has finished
             dist.all_reduce(self._barrier_token, group=self.group)
             planes = [self._planes(p, cap, half) for p in ptrs]
-            return self.local.merge_shards_peer([p[0] for p in planes], [p[1] for p in planes],
-                                                [p[2] for p in planes], nq, k, qn)
+            # Every rank merges only ITS 1/G slice of the queries (G lists each, loaded straight from the peers' memory)
+            # and the finished slices are all-gathered: G x less merge work and P2P traffic per rank than merging all nq
+            # queries everywhere; the all-gather moves nq * k * 16 / G bytes per rank.
+            per = -(-nq // self.world)
+            lo, hi = min(nq, self.rank * per), min(nq, (self.rank + 1) * per)
+            D = torch.empty((per * self.world, k), dtype=torch.float32, device=q.device)
+            I = torch.empty((per * self.world, k), dtype=torch.int64, device=q.device)
+            L = torch.empty((per * self.world, k), dtype=torch.float32, device=q.device)
+            mine = [t[self.rank * per:(self.rank + 1) * per] for t in (D, I, L)]
+            if hi > lo:
+                d, i, l = self.local.merge_shards_peer([p[0] + lo * k * 4 for p in planes], [p[1] + lo * k * 8 for p in planes],
+                                                       [p[2] + lo * k * 4 for p in planes], hi - lo, k, qn[lo:hi])
+                mine[0][:hi - lo].copy_(d)
+                mine[1][:hi - lo].copy_(i)
+                mine[2][:hi - lo].copy_(l)
+            works = [dist.all_gather_into_tensor(full, part, group=self.group, async_op=True)
+                     for full, part in zip((D, I, L), mine)]
+            for w in works:
+                w.wait()
+            return D[:nq], I[:nq], L[:nq]
         key, gid, lab, qn = self.local.search_shard(q, k, normalize=normalize)
         if self.world == 1:
             return self.local.merge_shards(key.unsqueeze(1), gid.unsqueeze(1), lab.unsqueeze(1), qn)

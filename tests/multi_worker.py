@@ -48,6 +48,18 @@ def main():
         assert (L.cpu().numpy() == Lf).all()
         if metric == pkg.METRIC_L2 and store == "bf16":
             assert If[0, 0] == 3 and If[0, 1] == 20000
+    # odd nq * k beyond the minimum buffer size: the int64 id plane of the peer buffer must stay 8-byte aligned
+    sh = pkg.ShardedFlatIndex(Dm, pkg.METRIC_L2, "bf16", device=local, exchange="peer")
+    s, e = sh.set_shard(N)
+    sh.add_local(xb[s:e])
+    q2 = torch.from_numpy(np.random.default_rng(99).standard_normal((1001, Dm)).astype(np.float32)).to(dev)
+    for rep in range(2):
+        D, I, L = sh.search(q2, 5)
+    torch.cuda.synchronize()
+    full = pkg.FlatIndex(Dm, pkg.METRIC_L2, "bf16", device=local)
+    full.add(xb)
+    Df, If = full.search(q2, 5)
+    assert torch.equal(I, If) and torch.equal(D, Df), f"rank {rank}: odd nq*k case differs"
     dist.barrier()
     if rank == 0:
         print(f"MULTI_OK world={world}")

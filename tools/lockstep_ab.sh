@@ -4,7 +4,7 @@
 # VARIANTS: space-separated RDB_* assignments (comma-joined inside one variant); "" = defaults.
 set -u
 N=${RDB_BENCH_N:-10000000}
-VARIANTS=${VARIANTS:-"RDB_TC_LOCKSTEP=0 RDB_TC_LOCKSTEP_SPINS=256 RDB_TC_LOCKSTEP_SPINS=4096 RDB_TC_LOCKSTEP_SPINS=65536"}
+VARIANTS=${VARIANTS:-"tc_lockstep=0 tc_lockstep_spins=256 tc_lockstep_spins=4096 tc_lockstep_spins=65536"}
 AB_ROUNDS=${AB_ROUNDS:-3} python tools/ab_knobs.py $N 768 65536 10 bf16 IP $VARIANTS
 for v in $VARIANTS; do
   tag=$(echo "$v" | tr '=,' '__')
