@@ -54,8 +54,8 @@ if _CFG != "C3":
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this exact workload (profiles/r01_ncu_c3_traffic.json); None if it does not match."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_c3_traffic.json")
+    `ncu --set full` capture of this exact workload (profiles/r02_ncu_c3_traffic.json); None if it does not match."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_c3_traffic.json")
     try:
         with open(p) as f:
             j = json.load(f)
@@ -546,13 +546,17 @@ def main():
                              "each rank uploads 1/N of the pageable host batch (total = h2d_bytes_per_step), NVLink "
                              "all-gather, sharded search, every rank reads the merged result back")},
             "gpu_launches": int(launches),
+            "step_breakdown_ms": {"scorer_kernel": ms_kern, "rest_of_step": ms_dev - ms_kern,
+                                  "note": "rest = query prep + candidate merge (+ at N > 1: barrier all-reduce, per-rank slice "
+                                          "merge over peer memory, all-gather of the result slices); max over ranks"},
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": ach / pk["bf16_sustained"], "traffic": ncu_traffic() if world == 1 else None,
                          "traffic_note": "dram read+write bytes/launch from the committed ncu --set full capture of this "
-                                         "workload (profiles/r01_ncu_c3_traffic.json): 4.5-6 database volumes across "
-                                         "captures -- the schedule streams the 15.36 GB database once per wave of 74 "
-                                         "query-tile pairs (3.5 waves); ~2% of DRAM bandwidth, not the bound",
+                                         "workload (profiles/r02_ncu_c3_traffic.json): 81.3 GB read = 5.3 database volumes "
+                                         "(each 15.36 GB chunk pass is shared by the 74 CTA pairs of a scheduling slot; 256 "
+                                         "query-tile pairs x 13 chunks touch 4.5 slots per chunk), 0.30 GB written (the "
+                                         "candidate lists); ~2 % of DRAM bandwidth, not the bound",
                          "kernel": "score_select_tc_kernel", "kernel_ms": ms_kern,
                          "flops_per_launch": flops, "peak_source": pk["src"] + " sustained bf16",
                          "frac_of_burst": ach / pk["bf16_burst"],

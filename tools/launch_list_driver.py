@@ -14,6 +14,8 @@ elif which == "c2cos":
     N, D, Q, k, store, met = 1000000, 768, 10000, 10, "f32", pkg.METRIC_IP
 elif which == "largek":
     N, D, Q, k, store, met = 1000000, 768, 1000, 1000, "bf16", pkg.METRIC_IP
+elif which.startswith("mid"):          # mid-batch regime (the reference's own batch size is 256): mid128 / mid256 / mid512
+    N, D, Q, k, store, met = 1000000, 768, int(which[3:]), 15, "bf16", pkg.METRIC_IP
 elif which == "c1":
     N, D, Q, k, store, met = 20000, 768, 1000, 10, "f32", pkg.METRIC_IP
 else:
