@@ -46,12 +46,14 @@ struct rdb_options {
   int tc_pivot = 1;              // sampled admission bound for 32 < k <= 128
   int tc_chunks = 0;             // 0 = cost model, else force the number of database chunks per query tile (A/B)
   int tc_debug = 0;              // RDB_PROFILING builds only: 1 = skip the selection work (results invalid)
+  int64_t stream_prof = 0;       // RDB_PROFILING builds only: device address of [blocks][8] u64 phase stamps of the streaming scorer
   int tier1 = 1;                 // fp32 stores: one-term certified pass first
   int tier1_kc = 0;              // 0 = auto, else force 32 | 64 | 128 candidates
   int largek_scorer = 0;         // 0 = auto, 1 = CUDA-core keys, 2 = tensor-core keys
   int64_t largek_rows = 0;       // rows per dense key chunk (0 = default 1M)
   int largek_sample = 1;         // sampled-pivot fast path of the radix select
   int largek_split = 1;          // fp32 stores: split-precision tensor-core keys + certificate for k > 128
+  int host_pipeline = 1;         // host-buffer searches upload large query batches in pieces behind the running search
 };
 
 struct rdb_handle {
@@ -68,6 +70,9 @@ struct rdb_handle {
   void* yext = nullptr;           // [cap][8] bf16: -|y|^2 in three exact bf16 parts (norm slice of the tcgen05 scorer; L2, bf16 operands)
   float cur_hscale = 1.0f;        // scale of the 16-bit query copies of the search in flight (2 = norm-slice scorer)
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // pipelined host-buffer search: second stream for the uploads, two staging buffers, 'uploaded' / 'buffer free' events
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_stage_free[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
   int last_algo = 0, last_S = 0;
@@ -79,7 +84,7 @@ struct rdb_handle {
   std::string err;
   std::mutex mu;
   // scratch
-  rdb::DevBuf add_stage, q_stage, qf, qhi, qlo, qnorm, cand_key, cand_idx, o_dist, o_idx, o_lbl, ids_stage, rec_stage;
+  rdb::DevBuf add_stage, q_stage, q_stage2, qf, qhi, qlo, qnorm, cand_key, cand_idx, o_dist, o_idx, o_lbl, ids_stage, rec_stage;
   rdb::DevBuf rr_key, rr_idx, rr_key2, rr_idx2, uncert, fb_qf, fb_qnorm, fb_a, fb_i, fb_l, gthr, tcsync, stream_ctl, fkey, fidx;
   rdb::DevBuf uncert1, t2_qf, t2_qhi, t2_qlo, t2_qnorm, t2_a, t2_i, t2_l;   // fp32 stores: tier-1 list + tier-2 sub-batch
   int t1_level = 0, t1_hold = 0;  // adaptive tier-1 level (exact_split_search) and batches until it decays

@@ -279,6 +279,9 @@ constexpr int64_t kQueryBatch = 65536;
 constexpr int kMaxK = 128;          // fused selectors (register list / reservoir / streaming lists)
 constexpr int kMaxKLarge = SELK_MAXK;   // 128 < k <= 2048: dense keys + radix select (run_largek); faiss-gpu's own limit
 constexpr int64_t kQueryBatchLargeK = 4096;
+// host-buffer searches at least this large upload their queries in pieces behind the running search (search_impl)
+constexpr int64_t kPipeMinQueries = 4096;
+constexpr size_t kPipeMinBytes = size_t(8) << 20;
 constexpr int kLargeKQueryBlock = 256;                // queries per dense key block (two SIMT query tiles)
 constexpr int64_t kLargeKRowsDefault = 1 << 20;       // rows per chunk: 256 x 1M x 4 B = 1 GiB of keys
 constexpr int kMaxKTc = 128;       // k <= 32: register-resident list; 32 < k <= 128: local-memory reservoir
@@ -295,6 +298,15 @@ constexpr int kTcPivotMinTiles = 1024; // >= 16 sampled tiles (N >= 262144)
 // `sample_mul`-th warp step (each warp must own at least that many steps) and its rank-r key becomes the pivot.
 // Expected rows above the pivot = r * sample_mul, chosen >= 4k (k of them exist with overwhelming probability) and
 // << STREAM_FCAP; r <= 128 (what the LIST policies hold), so a sample of at most 1/4 of the rows is needed.
+// warp steps per dynamically claimed row chunk of the streaming scorer: 4 (~48 KB per claim) once every warp gets at
+// least four chunks, single steps on small shards so that the rows still spread over all warps of the grid
+int stream_chunk_steps(rdb_handle* h, int blocks) {
+  const int nvec = (h->store == RDB_STORE_F32) ? h->d / 4 : h->dp / 8;
+  const int lpr_log2 = nvec >= 96 ? 5 : (nvec >= 48 ? 4 : 3);
+  const int rw = ((h->store == RDB_STORE_F32) ? 4 : 8) * (32 >> lpr_log2);
+  const int64_t steps = (h->n + rw - 1) / rw;
+  return int(std::min<int64_t>(4, std::max<int64_t>(1, steps / (int64_t(blocks) * STREAM_WARPS * 4))));
+}
 int stream_rows_per_block(rdb_handle* h) {
   const int blocks0 = int(std::min<int64_t>(h->num_sms, (h->n + 31) / 32));
   return int(round_up((h->n + blocks0 - 1) / blocks0, 32));
@@ -377,7 +389,7 @@ int search_stream(rdb_handle* h, const float* q, int nq, int k, int mem, int nor
   p.ynorm = h->ynorm; p.N = int(h->n);
   p.q_raw = qsrc; p.nq = nq; p.D = D; p.normalize = normalize; p.np = np_plan(h);
   if (zero_copy) memcpy(p.qin, q, q_bytes);
-  p.rows_per_block = rpb; p.kout = k; p.step_mul = 1;
+  p.rows_per_block = rpb; p.kout = k; p.step_mul = 1; p.chunk_steps = stream_chunk_steps(h, S);
   p.cand_key = h->cand_key.as<float>(); p.cand_idx = h->cand_idx.as<int>();
   p.fkey = nullptr; p.fidx = nullptr;
   p.ctl = h->stream_ctl.as<StreamCtl>();
@@ -386,6 +398,10 @@ int search_stream(rdb_handle* h, const float* q, int nq, int k, int mem, int nor
   p.out_dist = shard_mode ? nullptr : d_a; p.out_key = shard_mode ? d_a : nullptr;
   p.out_idx = reinterpret_cast<long long*>(d_i); p.out_lbl = d_l; p.out_qnorm = d_qn;
   p.host_flag = nullptr; p.flag_seq = 0;
+  p.prof = nullptr;
+#ifdef RDB_PROFILING
+  p.prof = reinterpret_cast<unsigned long long*>(h->opt.stream_prof);
+#endif
   volatile unsigned int* flag = nullptr;
   unsigned int seq = 0;
   if (zero_copy) {
@@ -403,10 +419,10 @@ int search_stream(rdb_handle* h, const float* q, int nq, int k, int mem, int nor
     // 1) pivot from a strided 1/64 sample (LIST, k = 16)
     float* sv_dist = p.out_dist; float* sv_key = p.out_key; long long* sv_idx = p.out_idx; float* sv_lbl = p.out_lbl;
     float* sv_qn = p.out_qnorm;
-    p.kout = pivot_rank; p.step_mul = sample_mul; p.use_pivot_out = 1;
+    p.kout = pivot_rank; p.step_mul = sample_mul; p.use_pivot_out = 1; p.chunk_steps = 1;
     p.out_dist = nullptr; p.out_key = nullptr; p.out_idx = nullptr; p.out_lbl = nullptr; p.out_qnorm = nullptr;
     if ((rc = launch_stream(h, p, S, pivot_rank <= 32 ? STREAM_LIST1 : STREAM_LIST4))) return rc;
-    p.kout = k; p.step_mul = 1; p.use_pivot_out = 0;
+    p.kout = k; p.step_mul = 1; p.use_pivot_out = 0; p.chunk_steps = stream_chunk_steps(h, S);
     p.out_dist = sv_dist; p.out_key = sv_key; p.out_idx = sv_idx; p.out_lbl = sv_lbl; p.out_qnorm = sv_qn;
     if ((rc = launch_stream(h, p, S, STREAM_FILTER))) return rc;      // 2) full pass: append key >= pivot, rank, emit
     p.run_if_fallback = 1;                     // 3) exits at once unless the FILTER pass raised the fallback flag
@@ -990,52 +1006,120 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   if (algo == RDB_ALGO_STREAM)
     return search_stream(h, q, int(nq), k, mem, normalize, shard_mode, out_a, out_idx, out_lbl, out_qnorm);
 
+  // Work list.  Device buffers: one piece per query batch.  HOST buffers: the batch is cut into a few pieces whose
+  // host-to-device copies run on a second stream into two alternating staging buffers, so the (pageable) upload of
+  // piece i + 1 overlaps the search of piece i -- C3: 201 MB of queries per step, ~15 ms that used to sit in front of
+  // the scorer -- and the results of all pieces go back with one set of copies at the end.
   const int64_t qbatch = largek ? kQueryBatchLargeK : kQueryBatch;
+  // (16-bit stores only: the certified fp32 search reads its counters back once per piece, which serialises the pieces
+  // on the host -- measured 6 % slower at C2 -- and has nothing to gain from a cut.)
+  const bool piped = host && !largek && !split && !out_qnorm && h->opt.host_pipeline && nq >= kPipeMinQueries &&
+                     size_t(std::min<int64_t>(nq, qbatch)) * D * 4 >= kPipeMinBytes;
+  if (piped && !h->copy_stream) {
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_stage_free[i], cudaEventDisableTiming));
+    }
+  }
   for (int64_t b0 = 0; b0 < nq; b0 += qbatch) {
     const int nb = int(std::min<int64_t>(qbatch, nq - b0));
-    const float* qsrc = q + b0 * D;
-    if (host) {
-      CUDA_TRY(h, h->q_stage.ensure(size_t(nb) * D * 4));
-      CUDA_TRY(h, cudaMemcpyAsync(h->q_stage.p, qsrc, size_t(nb) * D * 4, cudaMemcpyHostToDevice, s));
-      qsrc = h->q_stage.as<float>();
-    }
-    // ---- query prep: normalise, |q|^2, convert (same fused kernel as ingest)
-    CUDA_TRY(h, h->qnorm.ensure(size_t(nb) * 4));
-    int rc;
-    QueryView qv{nullptr, nullptr, nullptr, h->qnorm.as<float>(), nb};
-    if (sixteen) {
-      CUDA_TRY(h, h->qhi.ensure(size_t(nb) * Dp * 2));
-      if ((rc = launch_ingest(h, qsrc, nb, normalize, 1, nullptr, h->qhi.p, nullptr, h->qnorm.as<float>(), h->cur_hscale)))
-        return rc;
-      qv.qhi = h->qhi.p;
-    } else {
-      CUDA_TRY(h, h->qf.ensure(size_t(nb) * D * 4));
-      if (split) {
-        CUDA_TRY(h, h->qhi.ensure(size_t(nb) * Dp * 2));
-        CUDA_TRY(h, h->qlo.ensure(size_t(nb) * Dp * 2));
-        CUDA_TRY(h, h->qres.ensure(size_t(nb) * 4));
+    // ---- pieces of this batch (offset, count)
+    std::vector<std::pair<int, int>> pieces;
+    if (piped && nb >= kPipeMinQueries) {
+      // Copy-bound searches (small shards) take four equal pieces (the last piece's search is what stays exposed).
+      // Compute-bound ones (large shards) want a small first piece -- its upload is the only one exposed -- and as few
+      // pieces as possible after it, because every extra launch of the persistent scorer pays its own ramp and tail
+      // (C3 cut 4096 / 16384 / 45056 lost as much as the overlap won): piece i + 1 may be r times piece i, r = how many
+      // times faster a query uploads than it is searched (~ rows / 0.25 M at D = 768-class shapes, halved for safety),
+      // two pieces when r >= 8, three otherwise.
+      const bool compute_bound = h->n >= 400000;
+      const double r = std::min(32.0, std::max(2.0, double(h->n) / 0.5e6));
+      const double parts = r >= 8.0 ? 1.0 + r : 1.0 + r + r * r;
+      int p0 = compute_bound ? std::max(1024, int(double(nb) / parts) / 256 * 256) : std::max(1024, (nb / 4 + 255) / 256 * 256);
+      int off = 0, cur = p0;
+      while (off < nb) {
+        int take = std::min(cur, nb - off);
+        if (nb - off - take < 1024) take = nb - off;        // no tiny tail piece
+        pieces.emplace_back(off, take);
+        off += take;
+        if (compute_bound) cur = int(std::min<double>(double(cur) * r, double(nb)));
       }
-      if ((rc = launch_ingest(h, qsrc, nb, normalize, 0, h->qf.as<float>(), split ? h->qhi.p : nullptr,
-                              split ? h->qlo.p : nullptr, h->qnorm.as<float>(), h->cur_hscale,
-                              split ? h->qres.as<float>() : nullptr))) return rc;
-      qv.qf = h->qf.as<float>(); qv.qhi = h->qhi.p; qv.qlo = h->qlo.p;
+    } else {
+      pieces.emplace_back(0, nb);
     }
-    // ---- output views (device scratch when the caller's buffers are on the host)
-    float* d_a = out_a + b0 * k;
-    int64_t* d_i = out_idx + b0 * k;
-    float* d_l = out_lbl ? out_lbl + b0 * k : nullptr;
+    const bool overlap = pieces.size() > 1;
+    int max_piece = 0;
+    for (auto& pc : pieces) max_piece = std::max(max_piece, pc.second);
+    // ---- output views (device scratch for the whole batch when the caller's buffers are on the host)
+    float* b_a = out_a + b0 * k;
+    int64_t* b_i = out_idx + b0 * k;
+    float* b_l = out_lbl ? out_lbl + b0 * k : nullptr;
     if (host) {
       CUDA_TRY(h, h->o_dist.ensure(size_t(nb) * k * 4));
       CUDA_TRY(h, h->o_idx.ensure(size_t(nb) * k * 8));
       if (out_lbl) CUDA_TRY(h, h->o_lbl.ensure(size_t(nb) * k * 4));
-      d_a = h->o_dist.as<float>(); d_i = h->o_idx.as<int64_t>(); d_l = out_lbl ? h->o_lbl.as<float>() : nullptr;
+      b_a = h->o_dist.as<float>(); b_i = h->o_idx.as<int64_t>(); b_l = out_lbl ? h->o_lbl.as<float>() : nullptr;
+      CUDA_TRY(h, h->q_stage.ensure(size_t(max_piece) * D * 4));
+      if (overlap) CUDA_TRY(h, h->q_stage2.ensure(size_t(max_piece) * D * 4));
     }
+    // upload of piece i (host path): plain copy on the search stream, or -- overlapped form -- on the copy stream into
+    // staging buffer i & 1 once the query prep that last read that buffer is done
+    auto stage_of = [&](size_t i) { return (overlap && (i & 1)) ? h->q_stage2.as<float>() : h->q_stage.as<float>(); };
+    auto upload = [&](size_t i) -> cudaError_t {
+      const float* src = q + (b0 + pieces[i].first) * D;
+      const size_t bytes = size_t(pieces[i].second) * D * 4;
+      if (!overlap) return cudaMemcpyAsync(stage_of(i), src, bytes, cudaMemcpyHostToDevice, s);
+      cudaError_t e = cudaSuccess;
+      if (i >= 2) e = cudaStreamWaitEvent(h->copy_stream, h->ev_stage_free[i & 1], 0);
+      else if (i == 0) {
+        // the staging buffers may still be read by work queued earlier on the search stream
+        e = cudaEventRecord(h->ev_stage_free[0], s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->copy_stream, h->ev_stage_free[0], 0);
+      }
+      if (e == cudaSuccess) e = cudaMemcpyAsync(stage_of(i), src, bytes, cudaMemcpyHostToDevice, h->copy_stream);
+      if (e == cudaSuccess) e = cudaEventRecord(h->ev_h2d[i & 1], h->copy_stream);
+      return e;
+    };
+    if (host) CUDA_TRY(h, upload(0));
+    for (size_t pi = 0; pi < pieces.size(); ++pi) {
+    const int p_off = pieces[pi].first, pn = pieces[pi].second;
+    const float* qsrc = q + (b0 + p_off) * D;
+    if (host) {
+      qsrc = stage_of(pi);
+      if (overlap) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_h2d[pi & 1], 0));
+    }
+    // ---- query prep: normalise, |q|^2, convert (same fused kernel as ingest)
+    CUDA_TRY(h, h->qnorm.ensure(size_t(pn) * 4));
+    int rc;
+    QueryView qv{nullptr, nullptr, nullptr, h->qnorm.as<float>(), pn};
+    if (sixteen) {
+      CUDA_TRY(h, h->qhi.ensure(size_t(pn) * Dp * 2));
+      if ((rc = launch_ingest(h, qsrc, pn, normalize, 1, nullptr, h->qhi.p, nullptr, h->qnorm.as<float>(), h->cur_hscale)))
+        return rc;
+      qv.qhi = h->qhi.p;
+    } else {
+      CUDA_TRY(h, h->qf.ensure(size_t(pn) * D * 4));
+      if (split) {
+        CUDA_TRY(h, h->qhi.ensure(size_t(pn) * Dp * 2));
+        CUDA_TRY(h, h->qlo.ensure(size_t(pn) * Dp * 2));
+        CUDA_TRY(h, h->qres.ensure(size_t(pn) * 4));
+      }
+      if ((rc = launch_ingest(h, qsrc, pn, normalize, 0, h->qf.as<float>(), split ? h->qhi.p : nullptr,
+                              split ? h->qlo.p : nullptr, h->qnorm.as<float>(), h->cur_hscale,
+                              split ? h->qres.as<float>() : nullptr))) return rc;
+      qv.qf = h->qf.as<float>(); qv.qhi = h->qhi.p; qv.qlo = h->qlo.p;
+    }
+    if (overlap) CUDA_TRY(h, cudaEventRecord(h->ev_stage_free[pi & 1], s));   // the prep was the staging buffer's last reader
+    float* d_a = b_a + size_t(p_off) * k;
+    int64_t* d_i = b_i + size_t(p_off) * k;
+    float* d_l = b_l ? b_l + size_t(p_off) * k : nullptr;
     int L = 0;
     if (!split) {
       // ---- score + select, then merge
       h->tc_pivoted = false;
       if (h->n > 0 && (rc = largek ? run_largek(h, qv, k, &L) : run_scorer(h, algo, 1, qv, k, &L, true))) return rc;
-      if ((rc = run_merge_local(h, nb, L, k, k, qv.qnorm, shard_mode, d_a, d_i, d_l, h->id_offset, labels, nullptr)))
+      if ((rc = run_merge_local(h, pn, L, k, k, qv.qnorm, shard_mode, d_a, d_i, d_l, h->id_offset, labels, nullptr)))
         return rc;
       if (h->tc_pivoted) {
         // every query must have found min(k, n) rows above its sampled pivot; otherwise (flag) the two launches below
@@ -1043,12 +1127,12 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
         CUDA_TRY(h, h->uncert.ensure(8));
         int* flag = h->uncert.as<int>();
         CUDA_TRY(h, cudaMemsetAsync(flag, 0, 4, s));
-        check_complete_kernel<<<(nb + 255) / 256, 256, 0, s>>>(reinterpret_cast<const long long*>(d_i), nb, k,
+        check_complete_kernel<<<(pn + 255) / 256, 256, 0, s>>>(reinterpret_cast<const long long*>(d_i), pn, k,
                                                               int(std::min<int64_t>(k, h->n)), h->gthr.as<uint32_t>(), flag);
         h->launches++;
-        if ((rc = launch_tc(h, qv.qhi, qv.qlo, nb, k, h->tc_cg, h->tc_nqg, h->tc_S, h->tc_tpc, h->tc_ntiles, 1,
+        if ((rc = launch_tc(h, qv.qhi, qv.qlo, pn, k, h->tc_cg, h->tc_nqg, h->tc_S, h->tc_tpc, h->tc_ntiles, 1,
                             h->cand_key.as<float>(), h->cand_idx.as<int>(), 1, true, flag))) return rc;
-        if ((rc = run_merge_local(h, nb, L, k, k, qv.qnorm, shard_mode, d_a, d_i, d_l, h->id_offset, labels, nullptr,
+        if ((rc = run_merge_local(h, pn, L, k, k, qv.qnorm, shard_mode, d_a, d_i, d_l, h->id_offset, labels, nullptr,
                                   flag))) return rc;
       }
     } else {
@@ -1056,13 +1140,17 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
       if ((rc = lk_split ? largek_split_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels)
                          : exact_split_search(h, qv, k, shard_mode, d_a, d_i, d_l, labels))) return rc;
     }
+    // the next piece's upload is issued BEHIND this piece's launches: the host blocks in it (pageable memory is staged
+    // by the driver) while the GPU searches
+    if (host && pi + 1 < pieces.size()) CUDA_TRY(h, upload(pi + 1));
+    }  // pieces
     if (out_qnorm)
       CUDA_TRY(h, cudaMemcpyAsync(out_qnorm + b0, h->qnorm.p, size_t(nb) * 4,
                                   host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
     if (host) {
-      CUDA_TRY(h, cudaMemcpyAsync(out_a + b0 * k, d_a, size_t(nb) * k * 4, cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(h, cudaMemcpyAsync(out_idx + b0 * k, d_i, size_t(nb) * k * 8, cudaMemcpyDeviceToHost, s));
-      if (out_lbl) CUDA_TRY(h, cudaMemcpyAsync(out_lbl + b0 * k, d_l, size_t(nb) * k * 4, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(h, cudaMemcpyAsync(out_a + b0 * k, b_a, size_t(nb) * k * 4, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(h, cudaMemcpyAsync(out_idx + b0 * k, b_i, size_t(nb) * k * 8, cudaMemcpyDeviceToHost, s));
+      if (out_lbl) CUDA_TRY(h, cudaMemcpyAsync(out_lbl + b0 * k, b_l, size_t(nb) * k * 4, cudaMemcpyDeviceToHost, s));
       CUDA_TRY(h, host_sync(h));   // scratch is reused by the next batch
       counts_resolve(h, true);
     }
@@ -1073,7 +1161,7 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
 // every grow-only search scratch buffer of a handle (released by rdb_release_scratch / rdb_destroy, counted by rdb_mem_info)
 using DevBufMember = DevBuf rdb_handle::*;
 const DevBufMember kScratch[] = {
-    &rdb_handle::add_stage, &rdb_handle::q_stage, &rdb_handle::qf, &rdb_handle::qhi, &rdb_handle::qlo, &rdb_handle::qnorm,
+    &rdb_handle::add_stage, &rdb_handle::q_stage, &rdb_handle::q_stage2, &rdb_handle::qf, &rdb_handle::qhi, &rdb_handle::qlo, &rdb_handle::qnorm,
     &rdb_handle::cand_key, &rdb_handle::cand_idx, &rdb_handle::o_dist, &rdb_handle::o_idx, &rdb_handle::o_lbl,
     &rdb_handle::ids_stage, &rdb_handle::rec_stage, &rdb_handle::rr_key, &rdb_handle::rr_idx, &rdb_handle::rr_key2,
     &rdb_handle::rr_idx2, &rdb_handle::uncert, &rdb_handle::fb_qf, &rdb_handle::fb_qnorm, &rdb_handle::fb_a,
@@ -1143,6 +1231,11 @@ int rdb_destroy(rdb_handle* h) {
     if (h->ev_counts) cudaEventDestroy(h->ev_counts);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int i = 0; i < 2; ++i) {
+      if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+      if (h->ev_stage_free[i]) cudaEventDestroy(h->ev_stage_free[i]);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     cudaGetLastError();
   }
@@ -1547,8 +1640,10 @@ int rdb_set_option(rdb_handle* h, const char* name, int64_t value) {
   else if (n == "largek_rows") o.largek_rows = value;
   else if (n == "largek_sample") o.largek_sample = int(value);
   else if (n == "largek_split") o.largek_split = int(value);
+  else if (n == "host_pipeline") o.host_pipeline = int(value);
 #ifdef RDB_PROFILING
   else if (n == "tc_debug") o.tc_debug = int(value);
+  else if (n == "stream_prof") o.stream_prof = value;
 #endif
   else return fail(h, RDB_ERR_INVALID, "set_option: unknown option '" + n + "'");
   return RDB_OK;

@@ -104,6 +104,42 @@ struct WarpList {
   }
 };
 
+
+// ---- sorted 32-entry lists as one packed word per lane (lane j = rank j; key desc, id asc; 0 = empty slot) ----------
+__device__ __forceinline__ unsigned long long stream_pack(float key, int idx) {
+  return idx >= 0 ? pack_cand(key, uint32_t(idx)) : 0ull;
+}
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
+  const uint32_t lo = __shfl_sync(0xffffffffu, uint32_t(v), src);
+  const uint32_t hi = __shfl_sync(0xffffffffu, uint32_t(v >> 32), src);
+  return (static_cast<unsigned long long>(hi) << 32) | lo;
+}
+// best 32 of the union of two sorted lists, sorted: reverse one, lane-wise max (a bitonic sequence holding the best 32),
+// five compare-exchange stages.  12 shuffles instead of 32 rounds of a warp arg-max.
+__device__ __forceinline__ unsigned long long merge32(unsigned long long a, unsigned long long b, int lane) {
+  const unsigned long long br = shfl64(b, 31 - lane);
+  unsigned long long m = a > br ? a : br;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long x = shfl64(m, lane ^ o);
+    const bool keep_small = (lane & o) != 0;
+    m = ((m < x) == keep_small) ? m : x;
+  }
+  return m;
+}
+// 16 warp-held lists -> one (valid in warp 0 afterwards), four levels through shared memory sx [STREAM_WARPS][32];
+// the caller separates successive uses of sx with a block barrier.
+__device__ __forceinline__ unsigned long long block_tree_merge32(unsigned long long m, unsigned long long* sx, int warp,
+                                                                 int lane) {
+#pragma unroll
+  for (int s = 1; s < STREAM_WARPS; s <<= 1) {
+    if ((warp & (2 * s - 1)) == s) sx[warp * 32 + lane] = m;
+    __syncthreads();
+    if ((warp & (2 * s - 1)) == 0) m = merge32(m, sx[(warp + s) * 32 + lane], lane);
+  }
+  return m;
+}
+
 enum { STREAM_LIST1 = 0, STREAM_LIST4 = 1, STREAM_FILTER = 2 };
 constexpr int STREAM_FCAP = 4096;       // FILTER: candidate slots per query
 constexpr int STREAM_SAMPLE = 64;       // FILTER: the pivot pass reads every 64th warp step of the rows
@@ -115,13 +151,15 @@ struct StreamCtl {                      // device control block owned by the han
   int fallback;                         // FILTER pass could not produce the result -> the LIST launch must run
   int fcount[4];                        // FILTER: appended candidates per query (self-resetting)
   float pivot[4];                       // FILTER: per-query pivot key from the sample pass
+  unsigned int next;                    // row chunks handed out beyond every warp's first one (self-resetting)
 };
 
 struct StreamParams {
   const void* Y; int ld; const float* ynorm; int N;       // stored rows [N, ld] (T), |y|^2
   const float* q_raw; int nq, D, normalize;               // raw fp32 queries [nq, D] (device)
   NpPlan np;                                              // numpy summation order of the row norm (ingest.cuh)
-  int rows_per_block, kout, lpr_log2, step_mul;           // step_mul > 1: strided sample pass
+  int rows_per_block, kout, lpr_log2, step_mul;           // step_mul > 1: strided sample pass (every step_mul-th warp step)
+  int chunk_steps;                                        // warp steps per claimed row chunk (see the main loop)
   float* cand_key; int* cand_idx;                         // LIST: block lists [nq][gridDim.x][kout]
   float* fkey; int* fidx;                                 // FILTER: candidates [nq][STREAM_FCAP]
   StreamCtl* ctl;
@@ -133,8 +171,22 @@ struct StreamParams {
   // copy), the outputs point into mapped pinned host memory, and the last thing the search does is publish `flag_seq`
   // in *host_flag (system-scope fence first) -- the host spins on it instead of a device-to-host copy + stream sync.
   unsigned int* host_flag; unsigned int flag_seq;
+  unsigned long long* prof;   // RDB_PROFILING builds: [gridDim.x][8] globaltimer stamps per block (option "stream_prof"), else null
   float qin[STREAM_QINLINE];
 };
+
+#ifdef RDB_PROFILING
+#define STREAM_STAMP(i)                                                                                   \
+  do {                                                                                                    \
+    if (p.prof && threadIdx.x == 0) {                                                                     \
+      unsigned long long t_;                                                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                              \
+      p.prof[blockIdx.x * 8 + (i)] = t_;                                                                  \
+    }                                                                                                     \
+  } while (0)
+#else
+#define STREAM_STAMP(i) do {} while (0)
+#endif
 
 template <> __device__ __forceinline__ float to16<float>(float v) { return v; }
 template <> __device__ __forceinline__ float from16<float>(float v) { return v; }
@@ -195,17 +247,36 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
     return;
   }
 
-  // ---- the first rows of this block's slice start travelling HBM -> L2 while the queries are prepared
-  {
-    const int row_begin0 = blockIdx.x * p.rows_per_block;
-    const int rows0 = min(N, row_begin0 + p.rows_per_block) - row_begin0;
-    const long long bytes = (long long)max(rows0, 0) * ld * (long long)sizeof(T);
-    const char* base = reinterpret_cast<const char*>(Y + (long long)row_begin0 * ld);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long off = ((long long)threadIdx.x + (long long)i * STREAM_THREADS) * 128;
-      if (off < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
-    }
+  STREAM_STAMP(0);
+  // Lane groups of `lpr` lanes own rows (short rows: 8 or 16 lanes per row, so the shuffle reduction is amortised over
+  // several rows per warp step).  Per step a warp takes RW = R * G consecutive rows: group g rows r0 + g*R .. + R.
+  constexpr int R = StreamVec<T>::R;
+  const int lpr_log2 = p.lpr_log2;
+  const int lpr = 1 << lpr_log2, G = 32 >> lpr_log2;
+  const int grp = lane >> lpr_log2, l = lane & (lpr - 1);
+  const int RW = R * G;
+  // Rows are handed out in chunks of CH warp steps (CH * RW rows, ~48 KB at D = 768): every warp owns chunk
+  // blockIdx.x * 16 + warp to begin with and claims further ones from a global counter, so no SM sits idle while
+  // another still has a long static slice left (ncu on the static partition: SMs active 88 % of the kernel's duration
+  // while the active part already ran at 97 % of the HBM copy peak).  The next claim is issued before the current chunk
+  // is processed, so its latency hides behind ~48 KB of loads.  The sample pass (step_mul > 1) visits every
+  // step_mul-th step: chunk v, step j -> rows (v * CH + j) * step_mul * RW ...
+  const int CH = p.chunk_steps;
+  const long long rows_per_step = (long long)RW * p.step_mul;
+  const int total_steps = int((N + rows_per_step - 1) / rows_per_step);
+  // the first 7/8 of the steps go out in chunks of CH, the rest one step at a time: a warp streams ~2.8 GB/s, so a
+  // 48 KB chunk is 17 us of work and whole chunks to the end would leave that much imbalance between the SMs
+  const int big_chunks = (CH > 1) ? int(((long long)total_steps * 7 / 8) / CH) : 0;
+  const int steps_big = big_chunks * CH;
+  const int total_chunks = big_chunks + (total_steps - steps_big);
+  const int first_chunk = blockIdx.x * STREAM_WARPS + warp;
+  // ---- the first rows of this warp's first chunk start travelling HBM -> L2 while the queries are prepared
+  if (first_chunk < total_chunks) {
+    const long long row0 = (first_chunk < big_chunks ? (long long)first_chunk * CH : (long long)steps_big + (first_chunk - big_chunks)) * rows_per_step;
+    const long long bytes = min((long long)(N - row0), (long long)2 * RW) * ld * (long long)sizeof(T);
+    const char* base = reinterpret_cast<const char*>(Y + row0 * ld);
+    for (long long off = (long long)lane * 128; off < bytes; off += 32 * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
   }
   // ---- query prep (every block, redundantly: nq * D elements)
   const float* qsrc = p.q_raw;
@@ -230,11 +301,11 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
     }
   }
   __syncthreads();
+  STREAM_STAMP(1);
 
   constexpr int EPV = StreamVec<T>::EPV;
   const int nvec = ld / EPV;                             // 128-bit vectors per row
-  const int row_begin = blockIdx.x * p.rows_per_block;
-  const int row_end = min(N, row_begin + p.rows_per_block);
+  const int row_end = N;
 
   WarpList<KL> top[NQ];
   float thr[NQ];
@@ -246,41 +317,61 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
     if (MODE == STREAM_FILTER) thr[q] = (q < nq) ? floor_from_gthr(ordered_f32(s_pivot[q])) : CUDART_INF_F;
   }
 
-  // Lane groups of `lpr` lanes own rows (short rows: 8 or 16 lanes per row, so the shuffle reduction is amortised over
-  // several rows per warp step).  Per step a warp takes RW = R * G consecutive rows: group g rows r0 + g*R .. + R.
-  constexpr int R = StreamVec<T>::R;
-  const int lpr_log2 = p.lpr_log2;
-  const int lpr = 1 << lpr_log2, G = 32 >> lpr_log2;
-  const int grp = lane >> lpr_log2, l = lane & (lpr - 1);
-  const int RW = R * G;
-  // (A manually double-buffered form of this loop -- next slice's loads issued before the current one is consumed -- was
-  // measured SLOWER: fp32 0.479 -> 0.596 ms, bf16 0.272 -> 0.281 ms at C4; the compiler's own schedule of the plain loop
-  // keeps more independent loads in flight than two conditional sets of R.)
-  for (int r0 = row_begin + warp * RW; r0 < row_end; r0 += STREAM_WARPS * RW * p.step_mul) {
+  // (A manually double-buffered form of the step loop -- next slice's loads issued before the current one is consumed --
+  // was measured SLOWER: fp32 0.479 -> 0.596 ms, bf16 0.272 -> 0.281 ms at C4; the compiler's own schedule of the plain
+  // loop keeps more independent loads in flight than two conditional sets of R.)
+  const unsigned int claim_base = gridDim.x * STREAM_WARPS;
+  for (int chunk = first_chunk; chunk < total_chunks;) {
+    unsigned int nxt = 0;
+    if (lane == 0) nxt = atomicAdd(&p.ctl->next, 1u);    // claim for the NEXT round; consumed after this chunk
+    const int s_begin = chunk < big_chunks ? chunk * CH : steps_big + (chunk - big_chunks);
+    const int s_end = chunk < big_chunks ? s_begin + CH : s_begin + 1;
+  for (int st = s_begin; st < s_end; ++st) {
+    const int r0 = int((long long)st * rows_per_step);
     float acc[R][NQ];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int q = 0; q < NQ; ++q) acc[r][q] = 0.f;
-    for (int c = l; c < nvec; c += lpr) {
-      float y[R][EPV];
+    // U slices of R rows are loaded before any of them is consumed: R * U independent 128-bit loads per lane (8 KB per
+    // warp with one or two queries).  Left to the compiler the slice loop was unrolled or not depending on the code
+    // around it (fp32 C4: 12 loads in flight per lane in one build, 4 in the next: 0.48 vs 0.56 ms).
+    constexpr int U = ((NQ <= 2) ? 16 : 8) / R;
+    for (int c = l; c < nvec; c += lpr * U) {
+      typename StreamVec<T>::Raw raw[U][R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int row = min(r0 + grp * R + r, row_end - 1);   // clamp: duplicates are discarded below
-        StreamVec<T>::unpack(StreamVec<T>::load_raw(Y + (long long)row * ld + c * EPV), y[r]);
+      for (int u = 0; u < U; ++u) {
+        const int cc = c + u * lpr;
+        if (cc < nvec) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int row = min(r0 + grp * R + r, row_end - 1);   // clamp: duplicates are discarded below
+            raw[u][r] = StreamVec<T>::load_raw(Y + (long long)row * ld + cc * EPV);
+          }
+        }
       }
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        float qv[EPV];
+      for (int u = 0; u < U; ++u) {
+        const int cc = c + u * lpr;
+        if (cc < nvec) {
+          float qv[NQ][EPV];
 #pragma unroll
-        for (int e = 0; e < EPV; e += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(qs + q * ld + c * EPV + e);
-          qv[e] = t4.x; qv[e + 1] = t4.y; qv[e + 2] = t4.z; qv[e + 3] = t4.w;
+          for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int e = 0; e < EPV; e += 4) {
+              const float4 t4 = *reinterpret_cast<const float4*>(qs + q * ld + cc * EPV + e);
+              qv[q][e] = t4.x; qv[q][e + 1] = t4.y; qv[q][e + 2] = t4.z; qv[q][e + 3] = t4.w;
+            }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            float y[EPV];
+            StreamVec<T>::unpack(raw[u][r], y);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+              for (int e = 0; e < EPV; ++e) acc[r][q] = fmaf(qv[q][e], y[e], acc[r][q]);
+          }
         }
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int e = 0; e < EPV; ++e) acc[r][q] = fmaf(qv[e], y[r][e], acc[r][q]);
       }
     }
     for (int o = lpr >> 1; o > 0; o >>= 1)
@@ -332,10 +423,28 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
       }
     }
   }
+    chunk = int(claim_base + __shfl_sync(0xffffffffu, nxt, 0));
+  }
 
   // ---- LIST: in-block merge, 16 warp lists -> 1 list per query in global memory
   __syncthreads();                                       // queries no longer needed: reuse smem
-  if (MODE != STREAM_FILTER) {
+  STREAM_STAMP(2);
+  if (MODE != STREAM_FILTER && KL == 1) {
+    // k <= 32: the 16 warp lists fold pairwise (4 levels of merge32) instead of k rounds of a 16-way arg-best
+    unsigned long long* sx = reinterpret_cast<unsigned long long*>(sm);     // [STREAM_WARPS][32]
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      if (q < nq) {                                      // uniform
+        const unsigned long long m = block_tree_merge32(stream_pack(top[q].key[0], top[q].idx[0]), sx, warp, lane);
+        if (warp == 0 && lane < kout) {
+          const long long o = ((long long)q * gridDim.x + blockIdx.x) * kout + lane;
+          p.cand_key[o] = m ? unordered_f32(uint32_t(m >> 32)) : -CUDART_INF_F;
+          p.cand_idx[o] = m ? int(0xFFFFFFFFu - uint32_t(m)) : -1;
+        }
+        __syncthreads();
+      }
+    }
+  } else if (MODE != STREAM_FILTER) {
     constexpr int LW = 32 * KL;                          // entries per warp list
     float* lk = sm;                                      // [NQ][STREAM_WARPS][LW]
     int* li = reinterpret_cast<int*>(sm + NQ * STREAM_WARPS * LW);
@@ -378,14 +487,54 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
   }
 
   // ---- the last block to finish produces the final result
+  STREAM_STAMP(3);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_ticket = atomicAdd(&p.ctl->ticket, 1u);
   __syncthreads();
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
+  STREAM_STAMP(4);
 
-  if (MODE != STREAM_FILTER) {
+  if (MODE != STREAM_FILTER && KL == 1) {
+    // k <= 32: every warp folds its share of the gridDim.x block lists (all loads issued up-front, one merge32 per
+    // list), the 16 partial lists fold through shared memory, warp 0 emits -- ~3 us instead of ~15 us for 148 lists
+    unsigned long long* sx = reinterpret_cast<unsigned long long*>(sm);
+    const int L = int(gridDim.x);
+    for (int q = 0; q < nq; ++q) {
+      unsigned long long acc = 0ull;
+      for (int l0 = warp; l0 < L; l0 += STREAM_WARPS * 5) {
+        float kk[5]; int ii[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int li = l0 + STREAM_WARPS * j;
+          const bool ok = li < L && lane < kout;
+          const long long o = ((long long)q * L + (ok ? li : 0)) * kout + (ok ? lane : 0);
+          kk[j] = __ldcg(p.cand_key + o); ii[j] = ok ? __ldcg(p.cand_idx + o) : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) acc = merge32(acc, stream_pack(kk[j], ii[j]), lane);
+      }
+      const unsigned long long m = block_tree_merge32(acc, sx, warp, lane);
+      if (warp == 0) {
+        const float kv = m ? unordered_f32(uint32_t(m >> 32)) : -CUDART_INF_F;
+        const int mi = m ? int(0xFFFFFFFFu - uint32_t(m)) : -1;
+        if (p.use_pivot_out) {
+          // sample pass: only the pivot (key of rank kout - 1, -inf if the sample holds fewer rows)
+          if (lane == kout - 1) p.ctl->pivot[q] = kv;
+        } else if (lane < kout) {
+          const long long o = (long long)q * kout + lane;
+          if (p.out_dist) p.out_dist[o] = mi < 0 ? (p.metric_l2 ? CUDART_INF_F : -CUDART_INF_F)
+                                                 : (p.metric_l2 ? fmaxf(0.f, s_qnorm[q] - kv) : kv);
+          if (p.out_idx) p.out_idx[o] = mi < 0 ? -1ll : (long long)mi + p.id_offset;
+          if (p.out_key) p.out_key[o] = kv;
+          if (p.out_lbl) p.out_lbl[o] = (mi >= 0 && p.labels) ? __ldg(p.labels + mi) : 0.f;
+        }
+      }
+      __syncthreads();
+    }
+    if (p.run_if_fallback && threadIdx.x == 0) p.ctl->fallback = 0;
+  } else if (MODE != STREAM_FILTER) {
     if (warp < nq) {
       if (p.use_pivot_out) {
         // sample pass: only the pivot (key of rank STREAM_PIVOT_RANK, -inf if the sample holds fewer rows)
@@ -454,7 +603,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
     if (threadIdx.x == 0) p.ctl->fallback = failed ? 1 : 0;
     if (threadIdx.x < 4) p.ctl->fcount[threadIdx.x] = 0;
   }
-  if (threadIdx.x == 0) p.ctl->ticket = 0;
+  if (threadIdx.x == 0) { p.ctl->ticket = 0; p.ctl->next = 0; }
+  STREAM_STAMP(5);
   if (p.host_flag && !p.use_pivot_out) {
     // results live in mapped host memory: make every thread's writes visible system-wide, then publish
     // (the block barrier orders every thread's result writes before thread 0's fence: fences are cumulative)
