@@ -603,6 +603,7 @@ int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out, int nterms
 }
 
 // fold the local candidate lists: final form (dist or key, global id, label)
+constexpr int kMergeTreeMaxQueries = 2048;   // above this the one-warp-per-query merge has the better throughput
 int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float* qnorm, bool shard_mode, float* d_a,
                     int64_t* d_i, float* d_l, long long id_offset, const float* labels, float* raw_key,
                     const int* run_if = nullptr, const int* q_dev = nullptr, const int* l_dev = nullptr) {
@@ -623,6 +624,16 @@ int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float*
     finalize_sorted_list_kernel<<<unsigned((total + 255) / 256), 256, 0, h->stream>>>(
         h->cand_key.as<float>(), h->cand_idx.as<int>(), nq, kout, h->metric == RDB_METRIC_L2 ? 1 : 0, qnorm, id_offset,
         labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l, shard_mode ? d_a : raw_key);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return RDB_OK;
+  }
+  if (kc <= 32 && kout <= 32 && L >= 8 && nq <= kMergeTreeMaxQueries) {
+    // few queries, many short lists: one block per query, lists folded by merge32 trees (merge.cuh)
+    merge_lists_tree_kernel<<<nq, MERGE_TREE_WARPS * 32, 0, h->stream>>>(
+        h->cand_key.as<float>(), h->cand_idx.as<int>(), nq, L, kc, kout, h->metric == RDB_METRIC_L2 ? 1 : 0, qnorm,
+        id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l, shard_mode ? d_a : raw_key,
+        run_if);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return RDB_OK;

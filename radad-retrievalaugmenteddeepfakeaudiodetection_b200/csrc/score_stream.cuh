@@ -105,40 +105,6 @@ struct WarpList {
 };
 
 
-// ---- sorted 32-entry lists as one packed word per lane (lane j = rank j; key desc, id asc; 0 = empty slot) ----------
-__device__ __forceinline__ unsigned long long stream_pack(float key, int idx) {
-  return idx >= 0 ? pack_cand(key, uint32_t(idx)) : 0ull;
-}
-__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
-  const uint32_t lo = __shfl_sync(0xffffffffu, uint32_t(v), src);
-  const uint32_t hi = __shfl_sync(0xffffffffu, uint32_t(v >> 32), src);
-  return (static_cast<unsigned long long>(hi) << 32) | lo;
-}
-// best 32 of the union of two sorted lists, sorted: reverse one, lane-wise max (a bitonic sequence holding the best 32),
-// five compare-exchange stages.  12 shuffles instead of 32 rounds of a warp arg-max.
-__device__ __forceinline__ unsigned long long merge32(unsigned long long a, unsigned long long b, int lane) {
-  const unsigned long long br = shfl64(b, 31 - lane);
-  unsigned long long m = a > br ? a : br;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long x = shfl64(m, lane ^ o);
-    const bool keep_small = (lane & o) != 0;
-    m = ((m < x) == keep_small) ? m : x;
-  }
-  return m;
-}
-// 16 warp-held lists -> one (valid in warp 0 afterwards), four levels through shared memory sx [STREAM_WARPS][32];
-// the caller separates successive uses of sx with a block barrier.
-__device__ __forceinline__ unsigned long long block_tree_merge32(unsigned long long m, unsigned long long* sx, int warp,
-                                                                 int lane) {
-#pragma unroll
-  for (int s = 1; s < STREAM_WARPS; s <<= 1) {
-    if ((warp & (2 * s - 1)) == s) sx[warp * 32 + lane] = m;
-    __syncthreads();
-    if ((warp & (2 * s - 1)) == 0) m = merge32(m, sx[(warp + s) * 32 + lane], lane);
-  }
-  return m;
-}
 
 enum { STREAM_LIST1 = 0, STREAM_LIST4 = 1, STREAM_FILTER = 2 };
 constexpr int STREAM_FCAP = 4096;       // FILTER: candidate slots per query
@@ -435,7 +401,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       if (q < nq) {                                      // uniform
-        const unsigned long long m = block_tree_merge32(stream_pack(top[q].key[0], top[q].idx[0]), sx, warp, lane);
+        const unsigned long long m = block_tree_merge32<STREAM_WARPS>(pack_entry(top[q].key[0], top[q].idx[0]), sx, warp, lane);
         if (warp == 0 && lane < kout) {
           const long long o = ((long long)q * gridDim.x + blockIdx.x) * kout + lane;
           p.cand_key[o] = m ? unordered_f32(uint32_t(m >> 32)) : -CUDART_INF_F;
@@ -513,9 +479,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) score_select_stream_kernel(
           kk[j] = __ldcg(p.cand_key + o); ii[j] = ok ? __ldcg(p.cand_idx + o) : -1;
         }
 #pragma unroll
-        for (int j = 0; j < 5; ++j) acc = merge32(acc, stream_pack(kk[j], ii[j]), lane);
+        for (int j = 0; j < 5; ++j) acc = merge32(acc, pack_entry(kk[j], ii[j]), lane);
       }
-      const unsigned long long m = block_tree_merge32(acc, sx, warp, lane);
+      const unsigned long long m = block_tree_merge32<STREAM_WARPS>(acc, sx, warp, lane);
       if (warp == 0) {
         const float kv = m ? unordered_f32(uint32_t(m >> 32)) : -CUDART_INF_F;
         const int mi = m ? int(0xFFFFFFFFu - uint32_t(m)) : -1;

@@ -64,6 +64,8 @@ class MultiGpuFlatIndex(_ReconstructCache):
         self._seg: List[List[Tuple[int, int, int]]] = [[] for _ in self.devices]
         self._seg_dev = [None] * len(self.devices)      # device copies (local_starts, deltas), rebuilt lazily
         self._glob = None                               # global routing table (starts, shard, delta), rebuilt lazily
+        self.phase_probe = False                        # profiling aid: per-GPU host time of each search phase (syncs the streams)
+        self.last_phases = None
 
     # ------------------------------------------------------------------ properties (FlatIndex duck type)
     @property
@@ -264,11 +266,22 @@ class MultiGpuFlatIndex(_ReconstructCache):
             return (outD, outI, outL) if return_labels else (outD, outI)
         barrier = threading.Barrier(G)
         slices, fulls, cands, events, errors = [None] * G, [None] * G, [None] * G, [None] * G, []
+        probe = bool(self.phase_probe)
+        phases = [dict() for _ in range(G)]
 
         def work(t):
             g = live[t]
             dev = torch.device("cuda", self.devices[g])
             lo, hi = bounds[t]
+            import time as _time
+            t_last = [_time.perf_counter()]
+
+            def mark(name, st):
+                if probe:
+                    st.synchronize()
+                    now = _time.perf_counter()
+                    phases[t][name] = (now - t_last[0]) * 1e3
+                    t_last[0] = now
             try:
                 with torch.cuda.device(dev):
                     st = torch.cuda.current_stream(dev)
@@ -281,7 +294,9 @@ class MultiGpuFlatIndex(_ReconstructCache):
                     ev = torch.cuda.Event()
                     ev.record(st)
                     events[t] = ev
+                    mark("upload", st)
                     barrier.wait()
+                    mark("barrier1", st)
                     # 2) the whole batch on this GPU: peers' slices over NVLink
                     if G == 1:
                         full = slices[t]
@@ -293,13 +308,16 @@ class MultiGpuFlatIndex(_ReconstructCache):
                                 st.wait_event(events[u])
                                 full[a:b].copy_(slices[u], non_blocking=True)
                     fulls[t] = full
+                    mark("gather", st)
                     # 3) search the shard
                     key, lid, lab, qn = self.shards[g].search_shard(full, k, normalize=normalize)
                     gid = self._local_to_global(g, lid)
                     ev2 = torch.cuda.Event()
                     ev2.record(st)
                     cands[t] = (key, gid, lab, qn, ev2)
+                    mark("search", st)
                     barrier.wait()
+                    mark("barrier2", st)
                     # 4) merge this GPU's slice of the queries from every shard's lists (P2P loads), hand it back
                     if hi > lo:
                         for u in range(G):
@@ -318,7 +336,9 @@ class MultiGpuFlatIndex(_ReconstructCache):
                             torch.from_numpy(outI[lo:hi]).copy_(I)
                             torch.from_numpy(outL[lo:hi]).copy_(L)
                     st.synchronize()               # the peers' lists must stay alive until every merge has read them
+                    mark("merge_download", st)
                     barrier.wait()
+                    mark("barrier3", st)
             except BaseException as e:  # noqa: BLE001 - a failing worker must not leave the others at a barrier
                 errors.append(e)
                 barrier.abort()
@@ -330,6 +350,8 @@ class MultiGpuFlatIndex(_ReconstructCache):
         real = [e for e in errors if not isinstance(e, threading.BrokenBarrierError)]
         if real or errors:
             raise (real or errors)[0]
+        if probe:
+            self.last_phases = phases
         if not cuda_in:
             self._rc_note_search(outI)
         return (outD, outI, outL) if return_labels else (outD, outI)

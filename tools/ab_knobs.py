@@ -18,7 +18,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-pkg = importlib.import_module("radad-retrievalaugmenteddeepfakeaudiodetection_b200")
+PKG = "radad-retrievalaugmenteddeepfakeaudiodetection_b200"
+if os.environ.get("AB_PROF_LIB"):      # profiling build (make RDB_PROFILING=1 OBJDIR=build_prof OUT=../libradad_flat_prof.so)
+    _cabi = importlib.import_module(PKG + "._cabi")
+    _cabi.LIB_PATH = os.path.join(ROOT, PKG, "libradad_flat_prof.so")
+pkg = importlib.import_module(PKG)
 
 
 DEFAULTS = {"tc_cta_group": 0, "tc_lockstep": 8, "tc_lockstep_spins": 4096, "tc_stages": 64, "tc_chunks": 0, "tc_query_stationary": 1,

@@ -62,6 +62,15 @@ def main():
         Dd, Id = idx.search(qd, K, normalize=True)
     torch.cuda.synchronize(0)
     dt_dev = (time.perf_counter() - t0) / STEPS
+    phases = None
+    if hasattr(idx, "phase_probe"):
+        idx.phase_probe = True
+        t0 = time.perf_counter()
+        vdb.search_batch(q, k=K)
+        probe_ms = (time.perf_counter() - t0) * 1e3
+        phases = {"total_ms_with_probe": probe_ms, "per_gpu": idx.last_phases}
+        idx.phase_probe = False
+    print(json.dumps({"phases": phases}))
     print(json.dumps({"what": "single-process multi-GPU VectorDatabase.search_batch (host numpy in/out)",
                       "workload": f"{N}x{D} {DTYPE}, {Q} queries, k={K}, cosine", "n_gpus": G,
                       "shard_sizes": idx.shard_sizes if hasattr(idx, "shard_sizes") else [idx.ntotal],
