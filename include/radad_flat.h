@@ -116,6 +116,13 @@ int rdb_merge_shards_peer(rdb_handle* h, const void* const* key_ptrs, const void
  * No reference counterpart. */
 int rdb_enable_peer_access(rdb_handle* h, int peer_device);
 
+/* Stream-ordered copy of `bytes` bytes between two device buffers, either of which may live on a peer GPU (after
+ * rdb_enable_peer_access), enqueued on THIS handle's stream and device -- a pull by the destination's worker.  The
+ * single-process multi-GPU search exchanges the query slices with it: a framework-level cross-device tensor copy is
+ * enqueued on the SOURCE device's stream, where it queues up behind that GPU's own 90 ms search (measured on 8 GPUs:
+ * two of the eight workers started their search only after a peer had finished its own).  No reference counterpart. */
+int rdb_copy_async(rdb_handle* h, void* dst, const void* src, size_t bytes);
+
 /* Replaces index.reconstruct(i) -- pipeline.py:503.  `out` is a HOST float32[d]. */
 int rdb_reconstruct(rdb_handle* h, int64_t id, float* out);
 

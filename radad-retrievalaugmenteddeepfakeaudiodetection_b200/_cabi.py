@@ -47,6 +47,7 @@ SIGNATURES = {
     "rdb_merge_shards_peer": (c_int, [_h, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int, c_int64,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdb_enable_peer_access": (c_int, [_h, c_int]),
+    "rdb_copy_async": (c_int, [_h, c_void_p, c_void_p, c_size_t]),
     "rdb_reconstruct": (c_int, [_h, c_int64, c_void_p]),
     "rdb_reconstruct_batch": (c_int, [_h, c_void_p, c_int64, c_int, c_void_p]),
     "rdb_filter_first_k": (c_int, [_h, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int,

@@ -1169,6 +1169,13 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
   return RDB_OK;
 }
 
+// stream-ordered copy by the SMs of the launching device (rdb_copy_async): either side may be peer memory
+template <typename V>
+__global__ void __launch_bounds__(256) copy_bytes_kernel(V* __restrict__ dst, const V* __restrict__ src, size_t n) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
 // every grow-only search scratch buffer of a handle (released by rdb_release_scratch / rdb_destroy, counted by rdb_mem_info)
 using DevBufMember = DevBuf rdb_handle::*;
 const DevBufMember kScratch[] = {
@@ -1663,6 +1670,26 @@ int rdb_set_option(rdb_handle* h, const char* name, int64_t value) {
 // ---- faiss IndexFlat on-disk layout (faiss/impl/index_write.cpp, v1.10): u32 fourcc, i32 d, i64 ntotal,
 //      i64 dummy, i64 dummy, u8 is_trained, i32 metric_type (0 = IP, 1 = L2), u64 count (= ntotal * d floats), data.
 static uint32_t fourcc(const char* s) { return uint32_t(uint8_t(s[0])) | uint32_t(uint8_t(s[1])) << 8 | uint32_t(uint8_t(s[2])) << 16 | uint32_t(uint8_t(s[3])) << 24; }
+
+int rdb_copy_async(rdb_handle* h, void* dst, const void* src, size_t bytes) {
+  if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");
+  if (bytes == 0) return RDB_OK;
+  if (!dst || !src) return fail(h, RDB_ERR_INVALID, "copy_async: null buffer");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard dg(h->device);
+  // A copy KERNEL on this device (peer memory is read with plain loads over NVLink), not cudaMemcpyAsync: a peer DMA
+  // copy is ordered by the driver against the SOURCE device's legacy default stream as well, so a pull from a GPU
+  // whose worker had already enqueued its 90 ms search waited for that search (8 GPUs: steps of 99 or 150-180 ms
+  // depending on which host thread got there first).
+  const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | bytes) & 15) == 0;
+  const size_t units = vec ? bytes / 16 : bytes;
+  const int blocks = int(std::min<size_t>((units + 255) / 256, size_t(h->num_sms) * 8));
+  if (vec) copy_bytes_kernel<uint4><<<blocks, 256, 0, h->stream>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), units);
+  else copy_bytes_kernel<unsigned char><<<blocks, 256, 0, h->stream>>>(static_cast<unsigned char*>(dst), static_cast<const unsigned char*>(src), units);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return RDB_OK;
+}
 
 int rdb_enable_peer_access(rdb_handle* h, int peer_device) {
   if (!h) return fail(nullptr, RDB_ERR_INVALID, "null handle");

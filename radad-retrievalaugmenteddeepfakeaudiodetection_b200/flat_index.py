@@ -347,6 +347,21 @@ class FlatIndex(_ReconstructCache):
         self._check(self._lib.rdb_enable_peer_access(self._h, int(peer_device)))
 
     @_locked
+    def copy_async(self, dst, src, on=None) -> None:
+        """Stream-ordered copy ``dst <- src`` (contiguous CUDA tensors of equal byte size) by a kernel on THIS index's GPU
+        and the calling thread's current stream of it (``rdb_copy_async``); either tensor may live on a peer GPU.  ``on`` =
+        this index's torch device (default: ``dst.device``, i.e. the destination pulls; pass ``src.device`` for a push).
+        A cross-device ``dst.copy_(src)`` is a DMA copy ordered against the source GPU's default stream instead."""
+        import torch
+        nbytes = dst.numel() * dst.element_size()
+        if not (dst.is_contiguous() and src.is_contiguous()) or nbytes != src.numel() * src.element_size():
+            raise RuntimeError("copy_async: contiguous tensors of equal byte size expected")
+        with torch.cuda.device(dst.device if on is None else on):
+            self._use_torch_stream(torch)
+            self._check(self._lib.rdb_copy_async(self._h, ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(src.data_ptr()),
+                                                 ctypes.c_size_t(nbytes)))
+
+    @_locked
     def filter_first_k(self, idx, dist, lab, row_codes, excl_sorted, K: int, ntotal: Optional[int] = None):
         """Device-side rank-ordered exclusion + first-K compaction (pipeline.py:491-520); torch CUDA in/out.  ``ntotal`` =
         rows of the WHOLE database (row shards pass the global count; default: this index's own rows + id offset)."""

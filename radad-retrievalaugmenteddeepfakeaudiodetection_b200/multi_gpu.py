@@ -264,9 +264,12 @@ class MultiGpuFlatIndex(_ReconstructCache):
             ready = None
         if nq == 0:
             return (outD, outI, outL) if return_labels else (outD, outI)
+        peer_ok = cuda_in and qsrc.device.index in self.devices     # the shards' GPUs have each other's memory mapped
         barrier = threading.Barrier(G)
         slices, fulls, cands, events, errors = [None] * G, [None] * G, [None] * G, [None] * G, []
         probe = bool(self.phase_probe)
+        import time as _time0
+        t_start = _time0.perf_counter()
         phases = [dict() for _ in range(G)]
 
         def work(t):
@@ -277,7 +280,13 @@ class MultiGpuFlatIndex(_ReconstructCache):
             t_last = [_time.perf_counter()]
 
             def mark(name, st):
-                if probe:
+                # phase_probe = True / "sync": host time per phase with the stream drained at every phase boundary;
+                # "events": no extra synchronisation -- host time stamps + CUDA events on the stream, resolved at the end
+                if probe and self.phase_probe == "events":
+                    ev_ = torch.cuda.Event(enable_timing=True)
+                    ev_.record(st)
+                    phases[t].setdefault("_ev", []).append((name, ev_, (_time.perf_counter() - t_start) * 1e3))
+                elif probe:
                     st.synchronize()
                     now = _time.perf_counter()
                     phases[t][name] = (now - t_last[0]) * 1e3
@@ -285,10 +294,20 @@ class MultiGpuFlatIndex(_ReconstructCache):
             try:
                 with torch.cuda.device(dev):
                     st = torch.cuda.current_stream(dev)
+                    mark("start", st)
                     # 1) this GPU's slice of the queries
                     if cuda_in:
                         st.wait_event(ready)
-                        slices[t] = qsrc[lo:hi].to(dev, non_blocking=True)
+                        if qsrc.device == dev:
+                            slices[t] = qsrc[lo:hi]
+                        elif not peer_ok:
+                            slices[t] = qsrc[lo:hi].to(dev, non_blocking=True)     # a GPU outside the index: no peer mapping
+                        else:
+                            # pulled by THIS worker on its own stream (a tensor .to() is enqueued on the source GPU's
+                            # stream, behind whatever that GPU's worker has already launched)
+                            slices[t] = torch.empty((hi - lo, self._d), dtype=torch.float32, device=dev)
+                            if hi > lo:
+                                self.shards[g].copy_async(slices[t], qsrc[lo:hi])
                     else:
                         slices[t] = torch.from_numpy(qsrc[lo:hi]).to(dev)          # pageable: returns when copied
                     ev = torch.cuda.Event()
@@ -306,7 +325,7 @@ class MultiGpuFlatIndex(_ReconstructCache):
                             a, b = bounds[u]
                             if b > a:
                                 st.wait_event(events[u])
-                                full[a:b].copy_(slices[u], non_blocking=True)
+                                self.shards[g].copy_async(full[a:b], slices[u])
                     fulls[t] = full
                     mark("gather", st)
                     # 3) search the shard
@@ -327,10 +346,15 @@ class MultiGpuFlatIndex(_ReconstructCache):
                             [cands[u][0].data_ptr() + lo * esz * 4 for u in range(G)],
                             [cands[u][1].data_ptr() + lo * esz * 8 for u in range(G)],
                             [cands[u][2].data_ptr() + lo * esz * 4 for u in range(G)], hi - lo, k, qn[lo:hi])
-                        if cuda_in:
+                        if cuda_in and (outD.device == dev or not peer_ok):
                             outD[lo:hi].copy_(D, non_blocking=True)
                             outI[lo:hi].copy_(I, non_blocking=True)
                             outL[lo:hi].copy_(L, non_blocking=True)
+                        elif cuda_in:
+                            # pushed by this worker's GPU into the caller's tensors over NVLink (see copy_async)
+                            self.shards[g].copy_async(outD[lo:hi], D, on=dev)
+                            self.shards[g].copy_async(outI[lo:hi], I, on=dev)
+                            self.shards[g].copy_async(outL[lo:hi], L, on=dev)
                         else:
                             torch.from_numpy(outD[lo:hi]).copy_(D)
                             torch.from_numpy(outI[lo:hi]).copy_(I)
@@ -351,6 +375,12 @@ class MultiGpuFlatIndex(_ReconstructCache):
         if real or errors:
             raise (real or errors)[0]
         if probe:
+            for ph in phases:
+                evs = ph.pop("_ev", None)
+                if evs:
+                    first = evs[0][1]
+                    ph["host_ms_at_mark"] = {n: round(h, 3) for n, _, h in evs}
+                    ph["gpu_ms_at_mark"] = {n: round(first.elapsed_time(e), 3) for n, e, _ in evs}
             self.last_phases = phases
         if not cuda_in:
             self._rc_note_search(outI)

@@ -69,6 +69,10 @@ def main():
         vdb.search_batch(q, k=K)
         probe_ms = (time.perf_counter() - t0) * 1e3
         phases = {"total_ms_with_probe": probe_ms, "per_gpu": idx.last_phases}
+        idx.phase_probe = "events"
+        t0 = time.perf_counter()
+        vdb.search_batch(q, k=K)
+        phases["events_probe"] = {"total_ms": (time.perf_counter() - t0) * 1e3, "per_gpu": idx.last_phases}
         idx.phase_probe = False
     print(json.dumps({"phases": phases}))
     print(json.dumps({"what": "single-process multi-GPU VectorDatabase.search_batch (host numpy in/out)",
