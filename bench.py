@@ -370,8 +370,55 @@ def secondary_block(torch, np, pkg, orc, dev, q_dev, pk):
                      "hbm_floor_ms": floor, "p50_frac_of_floor": floor / p50, "kernel_frac_of_floor": floor / kms,
                      "qps_single_stream": 1e3 / p50}
         vdb.index = None
+    # ---- mid-size batches (the reference's own batch is 256 segments, k_search = top_k + 10 = 15; pipeline.py:449-478):
+    #      1M x 768 bf16, device in/out.  Floor = the slower of the tensor term at the sustained bf16 peak and the
+    #      database bytes at the HBM copy peak.
+    for qn_ in (128, 256, 512):
+        q = q_dev[:qn_]
+        for _ in range(5):
+            bf.search(q, 15, normalize=True)
+        torch.cuda.synchronize()
+        kms, wall = [], []
+        for _ in range(20):
+            t0 = time.perf_counter()
+            bf.search(q, 15, normalize=True)
+            torch.cuda.synchronize()
+            wall.append((time.perf_counter() - t0) * 1e3)
+            kms.append(bf.last_kernel_ms()[0])
+        kmed, wmed = sorted(kms)[len(kms) // 2], sorted(wall)[len(wall) // 2]
+        floor = max(2.0 * qn_ * n2 * DIM / (pk["bf16_sustained"] * 1e12), n2 * DIM * 2 / (pk["hbm"] * 1e9)) * 1e3
+        out[f"midbatch_q{qn_}"] = {"workload": f"{n2}x{DIM} bf16 store, {qn_}-query batch, k=15, cosine, device in/out",
+                                   "search_ms_median": wmed, "scorer_kernel_ms_median": kmed, "floor_ms": floor,
+                                   "kernel_frac_of_floor": floor / kmed, "search_frac_of_floor": floor / wmed,
+                                   "qps": qn_ / (wmed * 1e-3)}
     for idx in list(vdbs.values()) + [bf]:
         idx.close()
+    # ---- reference scale (the shapes the reference itself runs: 25 423 stored segments x 5376 features, batches of 256,
+    #      top_k = 5 (+10 for self-exclusion); pipeline.py:449-532): retrieve_similar_vectors = search + exclusion filter +
+    #      row gather + labels, device in/out, fp32 store (bit-exact rows) and bf16 store
+    nr, dr, br = 25_423, 5376, 256
+    g = torch.Generator(device=dev)
+    g.manual_seed(99)
+    xr = torch.randn((nr, dr), generator=g, device=dev)
+    qr = torch.randn((br, dr), generator=g, device=dev)
+    qpaths = [f"/data/train/p{i}" for i in range(br)]          # the batch's own files are excluded from its neighbours
+    for dtype in ("f32", "bf16"):
+        vdb = pkg.VectorDatabase(_Cfg("L2", dtype))
+        vdb.create_index(dr)
+        vdb.add_vectors(xr, [f"p{i}" for i in range(nr)], [i & 1 for i in range(nr)], {})
+        for _ in range(3):
+            pkg.retrieve_similar_vectors(vdb, qr, 5, query_paths=qpaths)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            vec, lbl = pkg.retrieve_similar_vectors(vdb, qr, 5, query_paths=qpaths)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / 20
+        out[f"refscale_retrieve_{dtype}"] = {
+            "workload": f"retrieve_similar_vectors: {nr}x{dr} {dtype} store, {br} queries, top_k=5 (+10), L2, device in/out",
+            "ms_per_batch": ms, "batches_per_s": 1e3 / ms, "search_kernel_ms": vdb.index.last_kernel_ms()[0],
+            "neighbour_tensor_shape": list(vec.shape)}
+        vdb.cleanup_gpu_resources()
     return out
 
 
