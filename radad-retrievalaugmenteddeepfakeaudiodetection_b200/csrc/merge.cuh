@@ -316,8 +316,8 @@ inline size_t merge_stage_bytes(int L, int kc, int kout) {
 //   cert[q] = 1  iff  exact_key[kout-1] > approx_worst + B        (or the candidate set holds every row).
 // Uncertified queries are appended to `uncert_list` (count in uncert_count) for the exact fallback.
 constexpr int RERANK_MAX_KC = 128;
-constexpr int RERANK_THREADS = 128;
-// One BLOCK (4 warps) per query: the warps share the candidates (each exact dot product runs 4 independent 128-bit
+constexpr int RERANK_THREADS = 256;   // 8 warps share a query's candidates (4 rows each at kc = 32)
+// One BLOCK (8 warps) per query: the warps share the candidates (each exact dot product runs 4 / 8 independent 128-bit
 // loads per lane deep, so long rows -- the reference's D = 5376 -- are bandwidth- not latency-bound), then the block
 // ranks the kc exact keys by counting and thread 0 evaluates the certificate.
 template <bool L2>
@@ -360,6 +360,24 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_exact_kernel(const long
       const int n4 = D >> 2;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       int c = lane;
+      // long rows (the reference's D = 5376): eight independent 128-bit loads per lane and round trip; the four
+      // accumulators receive their elements in the same order as in the 4-deep loop below, so keys are bit-identical
+      for (; c + 224 < n4; c += 256) {
+        float4 y[8], x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) y[u] = __ldg(y4 + c + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = q4[c + 32 * u];
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          const float4 y0 = y[4 * hlf], y1 = y[4 * hlf + 1], y2 = y[4 * hlf + 2], y3 = y[4 * hlf + 3];
+          const float4 x0 = x[4 * hlf], x1 = x[4 * hlf + 1], x2 = x[4 * hlf + 2], x3 = x[4 * hlf + 3];
+          a0 = fmaf(x0.x, y0.x, a0); a0 = fmaf(x0.y, y0.y, a0); a0 = fmaf(x0.z, y0.z, a0); a0 = fmaf(x0.w, y0.w, a0);
+          a1 = fmaf(x1.x, y1.x, a1); a1 = fmaf(x1.y, y1.y, a1); a1 = fmaf(x1.z, y1.z, a1); a1 = fmaf(x1.w, y1.w, a1);
+          a2 = fmaf(x2.x, y2.x, a2); a2 = fmaf(x2.y, y2.y, a2); a2 = fmaf(x2.z, y2.z, a2); a2 = fmaf(x2.w, y2.w, a2);
+          a3 = fmaf(x3.x, y3.x, a3); a3 = fmaf(x3.y, y3.y, a3); a3 = fmaf(x3.z, y3.z, a3); a3 = fmaf(x3.w, y3.w, a3);
+        }
+      }
       for (; c + 96 < n4; c += 128) {
         const float4 y0 = __ldg(y4 + c), y1 = __ldg(y4 + c + 32), y2 = __ldg(y4 + c + 64), y3 = __ldg(y4 + c + 96);
         const float4 x0 = q4[c], x1 = q4[c + 32], x2 = q4[c + 64], x3 = q4[c + 96];

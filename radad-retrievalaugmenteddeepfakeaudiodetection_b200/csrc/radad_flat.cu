@@ -109,9 +109,11 @@ int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int n
   if (n <= 0) return RDB_OK;
   const int D = h->d, Dp = h->dp;
   const bool vec4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  const int warps_per_block = 8;
+  // one warp per row; few rows (a batch of 256 queries of 5376 floats is 32 blocks of 8 warps: 28 us on 32 SMs) are
+  // spread over the SMs with fewer warps per block
+  const int warps_per_block = n >= int64_t(h->num_sms) * 8 ? 8 : int(std::max<int64_t>(1, (n + h->num_sms - 1) / h->num_sms));
   int64_t blocks = std::min<int64_t>((n + warps_per_block - 1) / warps_per_block, int64_t(h->num_sms) * 16);
-  dim3 grid((unsigned)blocks), block(256);
+  dim3 grid((unsigned)blocks), block(32 * warps_per_block);
   cudaStream_t s = h->stream;
   // rows of 128 * NC floats with a store layout the specialised kernel knows: hi only / master + hi + lo / master + hi
   {
@@ -119,7 +121,6 @@ int launch_ingest(rdb_handle* h, const float* x, int64_t n, int normalize, int n
                      : ((master && hi && !lo && norm_of_hi) ? 2 : -1));
     if (vec4 && mode >= 0 && norm2 && D == Dp && D % 128 == 0 && D <= 1024) {
       const int ncf = D / 128;
-      dim3 grid((unsigned)blocks), block(256);
 #define FAST_LAUNCH(T16, NC, NORM, MODE)                                                                                  \
       ingest_fast_kernel<T16, NC, NORM, MODE><<<grid, block, NORM ? warps_per_block * FastShape<NC>::WARP_FLOATS * 4 : 0, \
                                                 h->stream>>>(x, n, master, (T16*)hi, (T16*)lo, norm2, hscale, res2, n_dev)
@@ -848,6 +849,10 @@ int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mod
   // kTier1Hold batches, so a change of the data is picked up again.  The counters arrive asynchronously, so a level
   // change takes effect one batch late.
   if (h->t1_hold > 0 && --h->t1_hold == 0 && h->t1_level > 0) { h->t1_level--; h->t1_hold = h->t1_level > 0 ? kTier1Hold : 0; }
+  // (Shards below 262 144 rows stay on the three-term pass: the 32-candidate form would run there, but with the few
+  // query tiles such shards see, re-searching even a handful of uncertified queries costs another pass over the whole
+  // database -- measured at the reference's own shapes, 25 423 x 5376 with 256 queries: 0.74 ms with tier 1 on clustered
+  // data (19 of 256 queries uncertified), 0.48 ms without; profiles/r02_refscale_probe.jsonl.)
   const bool tier1 = k <= kTier1MaxK && ntiles >= kTcPivotMinTiles && h->t1_level < 2 && h->opt.tier1;
   const int* ucount2 = nullptr;
   if (!tier1) {

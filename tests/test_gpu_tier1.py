@@ -175,3 +175,4 @@ def test_device_path_is_stream_ordered(pkg, oracle, scenario):
         assert t1_host == (Q, Q) and uncert_host == Q
     if scenario == "clustered":
         assert uncert_host >= 3
+
