@@ -336,7 +336,16 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_exact_kernel(const long
                                                                       const float* __restrict__ yres_max = nullptr,
                                                                       float accum_eps = 0.f,
                                                                       const int* __restrict__ q_dev = nullptr,
-                                                                      const int* __restrict__ qmap = nullptr) {
+                                                                      const int* __restrict__ qmap = nullptr,
+                                                                      // final form of the first kout ranks, written by
+                                                                      // this kernel (was a separate one-list merge launch):
+                                                                      // distances / global ids / labels / raw keys
+                                                                      float* __restrict__ fin_dist = nullptr,
+                                                                      long long* __restrict__ fin_idx = nullptr,
+                                                                      float* __restrict__ fin_lbl = nullptr,
+                                                                      float* __restrict__ fin_key = nullptr,
+                                                                      long long id_offset = 0,
+                                                                      const float* __restrict__ labels = nullptr) {
   __shared__ uint32_t s_ok[RERANK_MAX_KC];     // ordered exact keys (0 = empty slot)
   __shared__ long long s_id[RERANK_MAX_KC];
   __shared__ float s_kth;
@@ -425,6 +434,15 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_exact_kernel(const long
     }
     out_key[(long long)q * kc + pos] = empty ? -CUDART_INF_F : unordered_f32(mok);
     out_idx[(long long)q * kc + pos] = empty ? -1 : mid;
+    if (pos < kout) {
+      // same conventions as merge_lists_warp: missing results are id -1, +inf (L2) / -inf (IP), label 0, key -inf
+      const long long o = (long long)q * kout + pos;
+      const float kv = unordered_f32(mok);
+      if (fin_dist) fin_dist[o] = empty ? (L2 ? CUDART_INF_F : -CUDART_INF_F) : (L2 ? fmaxf(0.f, qnorm[q] - kv) : kv);
+      if (fin_idx) fin_idx[o] = empty ? -1ll : mid + id_offset;
+      if (fin_lbl) fin_lbl[o] = (!empty && labels) ? __ldg(labels + mid) : 0.f;
+      if (fin_key) fin_key[o] = empty ? -CUDART_INF_F : kv;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -786,41 +804,45 @@ static __global__ void __launch_bounds__(128) merge_peer_lists_kernel(const Peer
 
 // Rank-ordered self-exclusion + first-K-survivors compaction (pipeline.py:491-520) on the device.
 //   idx/dist/lbl [B][ks] best-first search results; row_code[ntotal] = int code of each row's file basename;
-//   excl [ne] sorted ascending = codes to skip.  One thread per query walks its ks results in rank order, skips
-//   excluded rows (binary search), keeps the first K; pads with id -1 / label 0 / distance NaN.
-static __global__ void filter_first_k_kernel(const long long* __restrict__ idx, const float* __restrict__ dist,
-                                      const float* __restrict__ lbl, int B, int ks,
-                                      const long long* __restrict__ row_code, long long ntotal,
-                                      const long long* __restrict__ excl, int ne, int K,
-                                      long long* __restrict__ out_idx, float* __restrict__ out_dist,
-                                      float* __restrict__ out_lbl) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+//   excl [ne] sorted ascending = codes to skip.  One WARP per query: lane j tests result j (row code lookup + binary
+//   search of the exclusion list run for 32 results at once -- one thread per query walked them one after the other, a
+//   chain of ~10 dependent loads per result: 15 us for a batch of 256), a ballot keeps the rank order, the first K
+//   survivors are written; pads with id -1 / label 0 / distance NaN.
+static __global__ void __launch_bounds__(128) filter_first_k_kernel(
+    const long long* __restrict__ idx, const float* __restrict__ dist, const float* __restrict__ lbl, int B, int ks,
+    const long long* __restrict__ row_code, long long ntotal, const long long* __restrict__ excl, int ne, int K,
+    long long* __restrict__ out_idx, float* __restrict__ out_dist, float* __restrict__ out_lbl) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
-  int n = 0;
-  for (int j = 0; j < ks && n < K; ++j) {
-    const long long id = idx[(long long)b * ks + j];
-    if (id < 0 || id >= ntotal) continue;
-    bool skip = false;
-    if (ne > 0) {
+  int n = 0;                                              // survivors so far (warp-uniform)
+  for (int j0 = 0; j0 < ks && n < K; j0 += 32) {
+    const int j = j0 + lane;
+    const long long id = j < ks ? idx[(long long)b * ks + j] : -1;
+    bool keep = id >= 0 && id < ntotal;
+    if (keep && ne > 0) {
       const long long code = row_code[id];
       int lo = 0, hi = ne - 1;
       while (lo <= hi) {
         const int mid = (lo + hi) >> 1;
         const long long v = excl[mid];
-        if (v == code) { skip = true; break; }
+        if (v == code) { keep = false; break; }
         if (v < code) lo = mid + 1; else hi = mid - 1;
       }
     }
-    if (skip) continue;
-    out_idx[(long long)b * K + n] = id;
-    out_dist[(long long)b * K + n] = dist[(long long)b * ks + j];
-    out_lbl[(long long)b * K + n] = lbl ? lbl[(long long)b * ks + j] : 0.f;
-    ++n;
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    const int pos = n + __popc(mask & ((1u << lane) - 1u));
+    if (keep && pos < K) {
+      out_idx[(long long)b * K + pos] = id;
+      out_dist[(long long)b * K + pos] = dist[(long long)b * ks + j];
+      out_lbl[(long long)b * K + pos] = lbl ? lbl[(long long)b * ks + j] : 0.f;
+    }
+    n += __popc(mask);
   }
-  for (; n < K; ++n) {
-    out_idx[(long long)b * K + n] = -1;
-    out_dist[(long long)b * K + n] = __int_as_float(0x7FC00000);   // NaN (pipeline.py:515)
-    out_lbl[(long long)b * K + n] = 0.f;
+  for (int p = min(n, K) + lane; p < K; p += 32) {
+    out_idx[(long long)b * K + p] = -1;
+    out_dist[(long long)b * K + p] = __int_as_float(0x7FC00000);   // NaN (pipeline.py:515)
+    out_lbl[(long long)b * K + p] = 0.f;
   }
 }
 

@@ -711,24 +711,18 @@ int certified_pass(rdb_handle* h, const QueryView& v, int k, int kc, int nterms,
   const float* qres = (nterms == 1 && v.qf == h->qf.as<float>()) ? h->qres.as<float>() : nullptr;
   const float eps = (nterms == 3 ? 3.02f * 3.814697265625e-06f /*2^-18*/
                                  : 0.00390625f /*2 * 2^-9*/ + 3.814697265625e-06f /*2^-18*/) + accum;
-  const int warps = 4;
-  dim3 grid(plan ? std::min((nb + warps - 1) / warps, h->num_sms * 8) : (nb + warps - 1) / warps), block(32 * warps);
   dim3 rgrid(plan ? std::min(nb, h->num_sms * 8) : nb), rblock(RERANK_THREADS);     // re-rank: one block per query
+  // the kernel also writes the final form of the first k ranks (distances / global ids / labels, or raw keys for a shard)
+  float* f_dist = shard_mode ? nullptr : o_a;
+  float* f_key = shard_mode ? o_a : nullptr;
   if (l2) rerank_exact_kernel<true><<<rgrid, rblock, 0, s>>>(
       h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, v.qf, h->master, h->ynorm, D, eps, v.qnorm,
       h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount, qres, h->d_ynorm_max + 1,
-      accum, q_dev);
+      accum, q_dev, nullptr, f_dist, reinterpret_cast<long long*>(o_i), o_l, f_key, h->id_offset, labels);
   else rerank_exact_kernel<false><<<rgrid, rblock, 0, s>>>(
       h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, v.qf, h->master, h->ynorm, D, eps, v.qnorm,
       h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount, qres, h->d_ynorm_max + 1,
-      accum, q_dev);
-  h->launches++;
-  CUDA_TRY(h, cudaGetLastError());
-  // exact list (L = 1, already sorted) -> final form
-  merge_lists_kernel<long long><<<grid, block, 0, s>>>(
-      h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), nullptr, nb, 1, kc, k, l2 ? 1 : 0, v.qnorm, h->id_offset,
-      labels, shard_mode ? nullptr : o_a, reinterpret_cast<long long*>(o_i), o_l, shard_mode ? o_a : nullptr, nullptr, 0,
-      q_dev, nullptr);
+      accum, q_dev, nullptr, f_dist, reinterpret_cast<long long*>(o_i), o_l, f_key, h->id_offset, labels);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return RDB_OK;
@@ -1513,7 +1507,7 @@ int rdb_filter_first_k(rdb_handle* h, const int64_t* idx, const float* dist, con
       (n_excl > 0 && (!row_code || !excl_sorted)))
     return fail(h, RDB_ERR_INVALID, "filter_first_k: bad arguments");
   if (nq == 0) return RDB_OK;
-  filter_first_k_kernel<<<unsigned((nq + 127) / 128), 128, 0, h->stream>>>(
+  filter_first_k_kernel<<<unsigned((nq + 3) / 4), 128, 0, h->stream>>>(      // one warp per query
       reinterpret_cast<const long long*>(idx), dist, labels, int(nq), ks, reinterpret_cast<const long long*>(row_code),
       (long long)ntotal, reinterpret_cast<const long long*>(excl_sorted), n_excl, K,
       reinterpret_cast<long long*>(out_idx), out_dist, out_labels);
