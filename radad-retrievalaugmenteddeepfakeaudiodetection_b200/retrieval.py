@@ -58,18 +58,11 @@ def retrieve_similar_vectors(vector_db, query_vectors, top_k: int, dim: Optional
         return _pack(torch.zeros(B, K, D, device=dev), torch.zeros(B, K, device=dev),
                      [[""] * K for _ in range(B)], torch.full((B, K), float("nan"), device=dev))
 
-    k_search = K + (10 if exclude_self else 0)                                      # pipeline.py:478
-    try:
-        dists, idxs, labs = vector_db.search_batch_with_labels(q, k=k_search)
-    except Exception:  # noqa: BLE001 - pipeline.py:479-483: any search failure -> empty neighbours
-        dists = torch.zeros(B, 0, device=q.device)
-        idxs = torch.zeros(B, 0, dtype=torch.int64, device=q.device)
-        labs = torch.zeros(B, 0, device=q.device)
-    ks = idxs.shape[1]
-
-    # exclusion set -> sorted integer codes on the device (basenames are coded once per database, cached)
+    # exclusion set -> sorted integer codes on the device (basenames are coded once per database, cached).  Prepared BEFORE
+    # the search is launched: the host-to-device copy of the codes blocks the host on the stream, and behind the search it
+    # would hold the filter / gather launches back until the search had finished
     row_codes = excl = None
-    if exclude_self and ks > 0:
+    if exclude_self:
         codes_np, table = _basename_codes(vector_db)
         if query_paths is not None:
             names = {os.path.basename(p) for p in query_paths}
@@ -83,7 +76,16 @@ def retrieve_similar_vectors(vector_db, query_vectors, top_k: int, dim: Optional
                 vector_db._basename_codes_dev = cache
             row_codes = cache[1]
             excl = torch.from_numpy(np.sort(ex)).to(q.device)
-    # first K survivors in rank order (pipeline.py:491-520): one CUDA kernel, one thread per query
+    k_search = K + (10 if exclude_self else 0)                                      # pipeline.py:478
+    try:
+        dists, idxs, labs = vector_db.search_batch_with_labels(q, k=k_search)
+    except Exception:  # noqa: BLE001 - pipeline.py:479-483: any search failure -> empty neighbours
+        dists = torch.zeros(B, 0, device=q.device)
+        idxs = torch.zeros(B, 0, dtype=torch.int64, device=q.device)
+        labs = torch.zeros(B, 0, device=q.device)
+    ks = idxs.shape[1]
+
+    # first K survivors in rank order (pipeline.py:491-520): one CUDA kernel, one warp per query
     idx_k, dst_k, lbl_k = vector_db.index.filter_first_k(idxs, dists, labs, row_codes, excl, K)
     vec = vector_db.index.reconstruct_batch(idx_k)                                  # [B, K, D], zero rows for -1
     if vec.shape[2] != D:
