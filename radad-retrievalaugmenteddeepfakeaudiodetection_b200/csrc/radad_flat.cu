@@ -1050,7 +1050,8 @@ int search_impl(rdb_handle* h, const float* q, int64_t nq, int k, int mem, int n
       int off = 0, cur = p0;
       while (off < nb) {
         int take = std::min(cur, nb - off);
-        if (nb - off - take < 1024) take = nb - off;        // no tiny tail piece
+        // no small tail piece (compute-bound C3: 3072 + 62464, not ... + 1024: a 1024-query launch of the scorer is inefficient)
+        if (nb - off - take < (compute_bound ? std::max(4096, take / 4) : 1024)) take = nb - off;
         pieces.emplace_back(off, take);
         off += take;
         if (compute_bound) cur = int(std::min<double>(double(cur) * r, double(nb)));
