@@ -65,16 +65,24 @@ __device__ __forceinline__ float floor_from_gthr(uint32_t g) {
   return (g >= 2u) ? unordered_f32(g - 1u) : -CUDART_INF_F;
 }
 
-template <int KT>
+// SHARE = 2 ("two-list cover", tier 1 of the certified fp32 search): the merged lists must contain the global best 2 KT
+// keys while every unit keeps only KT.  gthr[q] is then a PAIR (hi word = largest, lo word = second largest bound any
+// unit has published; one 64-bit CAS): the two largest published local KT-th keys come from two different units with
+// disjoint rows, each holding KT rows at or above its own bound, so 2 KT rows reach the SECOND largest bound -- a lower
+// bound of the global (2 KT)-th best key, and the admission floor of this mode.  A row of the global best 2 KT then
+// passes every floor and can only be lost by a unit that holds KT better rows of its own: the merge flags queries where
+// a full list was consumed entirely (merge_lists_*: `sat`), and those queries are not certified.
+template <int KT, int SHARE = 1>
 struct SelectSmall {
   static constexpr bool kDump = false;
+  static constexpr int kGthrWords = SHARE;
   TopK<KT> top;
   float floor_;
   uint32_t* gq;
   __device__ __forceinline__ void init(int, uint32_t* gthr_q) {
     top.init();
     gq = gthr_q;
-    floor_ = gq ? floor_from_gthr(__ldcg(gq)) : -CUDART_INF_F;
+    floor_ = gq ? floor_from_gthr(__ldcg(gq)) : -CUDART_INF_F;      // SHARE == 2: word 0 = the second largest bound
   }
   __device__ __forceinline__ float threshold() const { return fmaxf(top.worst(), floor_); }
   __device__ __forceinline__ void offer(float v, int id) { if (v > threshold()) top.insert(v, id); }
@@ -89,7 +97,25 @@ struct SelectSmall {
     for (int j = 0; j < KT; ++j) {
       if (j < kout) { ck[j] = top.key[j]; ci[j] = top.idx[j]; kth = fminf(kth, top.key[j]); }
     }
-    if (gq && kth > -CUDART_INF_F && kth < CUDART_INF_F) atomicMax(gq, ordered_f32(kth));
+    if (gq && kth > -CUDART_INF_F && kth < CUDART_INF_F) {
+      if (SHARE == 1) {
+        atomicMax(gq, ordered_f32(kth));
+      } else {
+        unsigned long long* g = reinterpret_cast<unsigned long long*>(gq);
+        const unsigned long long v = ordered_f32(kth);
+        unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(g);
+        while (true) {
+          const unsigned long long m1 = old >> 32, m2 = old & 0xFFFFFFFFull;
+          unsigned long long nw;
+          if (v > m1) nw = (v << 32) | m1;
+          else if (v > m2) nw = (m1 << 32) | v;
+          else break;
+          const unsigned long long prev = atomicCAS(g, old, nw);
+          if (prev == old) break;
+          old = prev;
+        }
+      }
+    }
   }
 };
 
@@ -101,6 +127,7 @@ struct SelectSmall {
 template <int CAP>
 struct SelectReservoir {
   static constexpr bool kDump = false;
+  static constexpr int kGthrWords = 1;
   static constexpr int B = 16;   // entries loaded per batch: independent local-memory loads in flight per thread
   uint32_t okey[CAP];   // ordered_f32(key); 0 = never a valid key of a finite score
   int idx[CAP];
@@ -209,6 +236,7 @@ struct SelectReservoir {
 // the query tile) and select_dense_kernel (select_large.cuh) picks the best k afterwards.
 struct SelectDump {
   static constexpr bool kDump = true;
+  static constexpr int kGthrWords = 1;
   float* row;          // &dump[q][0] - row_base, so row[global row id] is this query's slot for that row
   __device__ __forceinline__ void init(int, uint32_t*) { row = nullptr; }
   __device__ __forceinline__ float threshold() const { return -CUDART_INF_F; }

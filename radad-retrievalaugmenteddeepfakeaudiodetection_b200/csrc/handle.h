@@ -53,6 +53,7 @@ struct rdb_options {
   int64_t largek_rows = 0;       // rows per dense key chunk (0 = default 1M)
   int largek_sample = 1;         // sampled-pivot fast path of the radix select
   int largek_split = 1;          // fp32 stores: split-precision tensor-core keys + certificate for k > 128
+  int tier1_share2 = 1;          // tier 1 with 32 candidates: two-list cover of 16-entry lists (0 = 32-entry lists)
   int host_pipeline = 1;         // host-buffer searches upload large query batches in pieces behind the running search
 };
 
@@ -96,6 +97,7 @@ struct rdb_handle {
   bool counts_pending = false, pending_tier1 = false;
   int pending_nb = 0, pending_kc1 = 0;
   rdb::DevBuf lk_scores;          // large-k path: dense keys of one (query block x row chunk)
+  rdb::DevBuf sat;                // per query: a candidate list was consumed entirely (two-list cover of tier 1)
   rdb::DevBuf qres, res_stage;    // |q - q_hi|^2 per query / per-row residuals of the rows being added (fp32 stores)
   rdb::DevBuf qext;               // [nq][8] bf16 {1, 1, 1, 0, ...}: query side of the norm slice
   int64_t qext_rows = 0;

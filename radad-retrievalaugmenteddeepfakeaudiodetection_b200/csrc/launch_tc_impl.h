@@ -42,6 +42,8 @@ int launch_tc_cg_t(rdb_handle* h, TcParams& p, int k) {
   const int groups = std::min(p.num_units, h->num_sms / CG);
   const bool l2 = h->metric == RDB_METRIC_L2 && !p.ext;     // norm slice: the accumulator already is the L2 key
   if (p.dump)       return l2 ? launch_tc_kernel<SelectDump, true, CG>(h, p, groups) : launch_tc_kernel<SelectDump, false, CG>(h, p, groups);
+  if (p.share2 && k <= 16)
+    return l2 ? launch_tc_kernel<SelectSmall<16, 2>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<16, 2>, false, CG>(h, p, groups);
   if (k <= 16)      return l2 ? launch_tc_kernel<SelectSmall<16>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<16>, false, CG>(h, p, groups);
   else if (k <= 32) return l2 ? launch_tc_kernel<SelectSmall<32>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<32>, false, CG>(h, p, groups);
   return l2 ? launch_tc_kernel<SelectReservoir<kReservoirCap>, true, CG>(h, p, groups)

@@ -33,7 +33,10 @@ template <typename IdxT, bool STAGED = false, int LPL = MERGE_LPL>
 __device__ __forceinline__ void merge_lists_warp(const float* key_in, const IdxT* idx_in, const float* lbl_in, int q, int L,
                                                  int kc, int kout, int metric_l2, const float* qnorm, long long id_offset,
                                                  const float* labels, float* out_dist, long long* out_idx,
-                                                 float* out_lbl, float* out_key, int lane, float* kth_out) {
+                                                 float* out_lbl, float* out_key, int lane, float* kth_out,
+                                                 int* sat_out = nullptr) {
+  // sat_out (optional): 1 iff some list was consumed entirely (all kc entries valid and taken) -- the two-list cover of
+  // the certified search (common.cuh, SelectSmall<KT, 2>) cannot vouch for rows such a list may have dropped
   // STAGED: key_in / idx_in point at this query's lists copied to shared memory (plain loads, base 0)
   const long long qbase = STAGED ? 0ll : (long long)q * L * kc;
   auto ld_idx = [&](long long o) -> long long { return STAGED ? (long long)idx_in[o] : (long long)__ldcg(idx_in + o); };
@@ -128,6 +131,13 @@ __device__ __forceinline__ void merge_lists_warp(const float* key_in, const IdxT
     }
   }
   if (kth_out) *kth_out = kth;
+  if (sat_out) {
+    bool full = false;
+#pragma unroll
+    for (int i = 0; i < LPL; ++i) full = full || (kc > 0 && ptr[i] >= kc);
+    const bool any = __any_sync(0xffffffffu, full);
+    if (lane == 0) *sat_out = any ? 1 : 0;
+  }
 }
 
 // ---- sorted 32-entry lists as one packed word per lane (lane j = rank j; key desc, id asc; 0 = empty slot) ----------
@@ -189,12 +199,13 @@ static __global__ void __launch_bounds__(MERGE_TREE_WARPS * 32) merge_lists_tree
     const float* __restrict__ key_in, const int* __restrict__ idx_in, int Q, int L, int kc, int kout, int metric_l2,
     const float* __restrict__ qnorm, long long id_offset, const float* __restrict__ labels, float* __restrict__ out_dist,
     long long* __restrict__ out_idx, float* __restrict__ out_lbl, float* __restrict__ out_key,
-    const int* __restrict__ run_if) {
+    const int* __restrict__ run_if, int* __restrict__ sat = nullptr) {
   __shared__ unsigned long long sx[MERGE_TREE_WARPS * 32];
+  __shared__ unsigned long long s_last[MERGE_TREE_WARPS];   // per warp: best LAST entry of its full lists (sat)
   if (run_if && __ldcg(run_if) == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = blockIdx.x; q < Q; q += gridDim.x) {
-    unsigned long long acc = 0ull;
+    unsigned long long acc = 0ull, best_last = 0ull;
     for (int l0 = warp; l0 < L; l0 += MERGE_TREE_WARPS * 4) {
       float kk[4]; int ii[4];
 #pragma unroll
@@ -210,10 +221,20 @@ static __global__ void __launch_bounds__(MERGE_TREE_WARPS * 32) merge_lists_tree
         // merge32 needs (key desc, id asc) order; a producer that emits equal keys in another order gets its list sorted
         const unsigned long long nx = shfl64(e, min(lane + 1, 31));
         if (__any_sync(0xffffffffu, e < nx)) e = sort32(e, lane);
+        const unsigned long long last = shfl64(e, kc - 1);          // non-zero iff the list is full
+        best_last = last > best_last ? last : best_last;
         acc = merge32(acc, e, lane);
       }
     }
+    if (lane == 0) s_last[warp] = best_last;
     const unsigned long long m = block_tree_merge32<MERGE_TREE_WARPS>(acc, sx, warp, lane);
+    if (sat && warp == 0) {
+      // a full list whose last entry made it into the result was consumed entirely (entries are distinct words)
+      const unsigned long long thr = shfl64(m, kout - 1);
+      const unsigned long long bl = lane < MERGE_TREE_WARPS ? s_last[lane] : 0ull;
+      const bool any = __any_sync(0xffffffffu, bl != 0ull && bl >= thr);
+      if (lane == 0) sat[q] = any ? 1 : 0;
+    }
     if (warp == 0 && lane < kout) {
       const float kv = m ? unordered_f32(uint32_t(m >> 32)) : -CUDART_INF_F;
       const int mi = m ? int(0xFFFFFFFFu - uint32_t(m)) : -1;
@@ -241,7 +262,8 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
                                                           const int* __restrict__ run_if = nullptr,
                                                           int stage_bytes_per_warp = 0,
                                                           const int* __restrict__ q_dev = nullptr,
-                                                          const int* __restrict__ l_dev = nullptr) {
+                                                          const int* __restrict__ l_dev = nullptr,
+                                                          int* __restrict__ sat = nullptr) {
   const int lane = threadIdx.x & 31;
   if (q_dev) Q = min(Q, __ldcg(q_dev));        // device-sized launch (DevPlan): a small fixed grid walks the queries
   if (l_dev) L = __ldcg(l_dev);
@@ -261,10 +283,10 @@ __global__ void __launch_bounds__(128) merge_lists_kernel(const float* __restric
       for (int i = lane; i < n; i += 32) { sidx[i] = __ldcg(idx_in + qbase + i); skey[i] = __ldcg(key_in + qbase + i); }
       __syncwarp();
       merge_lists_warp<IdxT, true, LPL>(skey, sidx, lbl_in, q, L, kc, kout, metric_l2, qnorm, id_offset, labels, out_dist,
-                                        out_idx, out_lbl, out_key, lane, nullptr);
+                                        out_idx, out_lbl, out_key, lane, nullptr, sat ? sat + q : nullptr);
     } else {
       merge_lists_warp<IdxT, false, LPL>(key_in, idx_in, lbl_in, q, L, kc, kout, metric_l2, qnorm, id_offset, labels,
-                                         out_dist, out_idx, out_lbl, out_key, lane, nullptr);
+                                         out_dist, out_idx, out_lbl, out_key, lane, nullptr, sat ? sat + q : nullptr);
     }
   }
 }
@@ -345,7 +367,10 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_exact_kernel(const long
                                                                       float* __restrict__ fin_lbl = nullptr,
                                                                       float* __restrict__ fin_key = nullptr,
                                                                       long long id_offset = 0,
-                                                                      const float* __restrict__ labels = nullptr) {
+                                                                      const float* __restrict__ labels = nullptr,
+                                                                      // two-list cover: 1 = a candidate list was
+                                                                      // consumed entirely -> never certified
+                                                                      const int* __restrict__ sat = nullptr) {
   __shared__ uint32_t s_ok[RERANK_MAX_KC];     // ordered exact keys (0 = empty slot)
   __shared__ long long s_id[RERANK_MAX_KC];
   __shared__ float s_kth;
@@ -464,7 +489,7 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_exact_kernel(const long
     bound *= (L2 ? 2.0f : 1.0f);
     // L2 keys taken from the accumulator (norm slice) also carry the accumulation rounding of the -|y|^2 parts
     if (L2) bound += 4.0f * 1.1920928955078125e-07f * (*ynorm_max);
-    const bool ok = (nvalid >= ntotal) || (nvalid == kc && has && kth_key > approx_worst + bound);
+    const bool ok = (nvalid >= ntotal) || (!(sat && sat[q]) && nvalid == kc && has && kth_key > approx_worst + bound);
     // uncertified queries are listed by their ORIGINAL query index when the batch is itself a compacted sub-batch
     if (!ok) uncert_list[atomicAdd(uncert_count, 1)] = qmap ? qmap[q] : q;
   }

@@ -213,7 +213,7 @@ int tc_cta_group(const rdb_handle* h, int nq, int nterms, int d) {
 int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, int cg, int nqg, int S, int tiles_per_chunk,
               int ntiles, int nterms, float* ck, int* ci, int tile_step = 1, bool keep_gthr = false,
               const int* run_if = nullptr, float* dump = nullptr, long long dump_pitch = 0, int row_base = 0,
-              int row_end = 0, const DevPlan* plan = nullptr) {
+              int row_end = 0, const DevPlan* plan = nullptr, int share2 = 0) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -221,8 +221,10 @@ int launch_tc(rdb_handle* h, const void* qhi, const void* qlo, int nq, int k, in
   if (nterms == 3) { if ((rc = encode_2d(h, &p.tmap_q[1], qlo, nq, h->d, h->dp, TC_BM))) return rc; }
   else p.tmap_q[1] = p.tmap_q[0];
   p.ynorm = h->ynorm; p.ynmin32 = h->ynmin32; p.cand_key = ck; p.cand_idx = ci;
-  CUDA_TRY(h, h->gthr.ensure(size_t(nq) * 4));
-  if (!keep_gthr) CUDA_TRY(h, cudaMemsetAsync(h->gthr.p, 0, size_t(nq) * 4, h->stream));
+  const size_t gthr_bytes = size_t(nq) * 4 * (share2 ? 2 : 1);
+  CUDA_TRY(h, h->gthr.ensure(gthr_bytes));
+  if (!keep_gthr) CUDA_TRY(h, cudaMemsetAsync(h->gthr.p, 0, gthr_bytes, h->stream));
+  p.share2 = (share2 && k <= 16) ? 1 : 0;
   p.tile_step = tile_step; p.run_if = run_if; p.plan = plan;
   p.nstages = std::max(2, h->opt.tc_stages);
   // norm slice (L2 keys straight from the accumulator): the queries of this search were staged as 2 q (search_impl)
@@ -464,7 +466,7 @@ int search_stream(rdb_handle* h, const float* q, int nq, int k, int mem, int nor
 }
 
 // score + select over the local shard into h->cand_key / h->cand_idx; *L_out = lists per query (width kc each)
-int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc, int* L_out, bool timed) {
+int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc, int* L_out, bool timed, int share2 = 0) {
   int rc, S, tpc;
   const int nqt = (qv.nq + 127) / 128;
   cudaStream_t s = h->stream;
@@ -513,7 +515,7 @@ int run_scorer(rdb_handle* h, int algo, int nterms, const QueryView& qv, int kc,
       }
     }
     if ((rc = launch_tc(h, qv.qhi, qv.qlo, qv.nq, kc, cg, nqg, S, tpc, ntiles, nterms, h->cand_key.as<float>(),
-                        h->cand_idx.as<int>(), 1, pivoted))) return rc;
+                        h->cand_idx.as<int>(), 1, pivoted, nullptr, nullptr, 0, 0, 0, nullptr, share2))) return rc;
     if (timed) cudaEventRecord(h->ev1, s);
     h->tc_pivoted = pivoted; h->tc_cg = cg; h->tc_nqg = nqg; h->tc_S = S; h->tc_tpc = tpc; h->tc_ntiles = ntiles;
     *L_out = S * TC_LISTS;
@@ -607,7 +609,7 @@ int run_largek(rdb_handle* h, const QueryView& qv, int k, int* L_out, int nterms
 constexpr int kMergeTreeMaxQueries = 2048;   // above this the one-warp-per-query merge has the better throughput
 int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float* qnorm, bool shard_mode, float* d_a,
                     int64_t* d_i, float* d_l, long long id_offset, const float* labels, float* raw_key,
-                    const int* run_if = nullptr, const int* q_dev = nullptr, const int* l_dev = nullptr) {
+                    const int* run_if = nullptr, const int* q_dev = nullptr, const int* l_dev = nullptr, int* sat = nullptr) {
   if (q_dev) {
     // device-sized launch (DevPlan): nq is the grid capacity, the real query / list counts are read on the device
     dim3 grid(std::min((nq + 3) / 4, h->num_sms * 8)), block(128);
@@ -634,7 +636,7 @@ int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float*
     merge_lists_tree_kernel<<<nq, MERGE_TREE_WARPS * 32, 0, h->stream>>>(
         h->cand_key.as<float>(), h->cand_idx.as<int>(), nq, L, kc, kout, h->metric == RDB_METRIC_L2 ? 1 : 0, qnorm,
         id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l, shard_mode ? d_a : raw_key,
-        run_if);
+        run_if, sat);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return RDB_OK;
@@ -647,7 +649,7 @@ int run_merge_local(rdb_handle* h, int nq, int L, int kc, int kout, const float*
   merge_lists_kernel<int, LPL><<<grid, block, stage * warps, h->stream>>>(                                       \
       h->cand_key.as<float>(), h->cand_idx.as<int>(), nullptr, nq, L, kc, kout, h->metric == RDB_METRIC_L2 ? 1 : 0, \
       qnorm, id_offset, labels, shard_mode ? nullptr : d_a, reinterpret_cast<long long*>(d_i), d_l,              \
-      shard_mode ? d_a : raw_key, run_if, int(stage))
+      shard_mode ? d_a : raw_key, run_if, int(stage), nullptr, nullptr, sat)
   if (L <= 32) MERGE_LOCAL(1); else if (L <= 64) MERGE_LOCAL(2); else if (L <= 128) MERGE_LOCAL(4); else MERGE_LOCAL(8);
 #undef MERGE_LOCAL
   h->launches++;
@@ -677,14 +679,22 @@ int64_t planned_lists_cap(int cap) { return std::max<int64_t>(round_up(cap, 256)
 // device-side count); every launch is enqueued unconditionally and returns at once when the plan holds no query.
 int certified_pass(rdb_handle* h, const QueryView& v, int k, int kc, int nterms, bool shard_mode, float* o_a,
                    int64_t* o_i, float* o_l, const float* labels, int* ucount, int* ulist, bool timed,
-                   const DevPlan* plan = nullptr) {
+                   const DevPlan* plan = nullptr, int list_k = 0) {
+  // list_k != 0 (host-sized tier 1 only): two-list cover -- the scorer keeps lists of list_k = kc / 2 entries whose
+  // union covers the best kc keys (SelectSmall<16, 2>, common.cuh); the merge flags the queries it cannot vouch for
   const int nb = v.nq, D = h->d;
   const bool l2 = h->metric == RDB_METRIC_L2;
   cudaStream_t s = h->stream;
   int rc, L = 0;
   const int* q_dev = plan ? &plan->nq : nullptr;
+  const int lk = (list_k && !plan) ? list_k : kc;       // entries per candidate list
+  int* sat = nullptr;
+  if (lk != kc) {
+    CUDA_TRY(h, h->sat.ensure(size_t(nb) * 4));
+    sat = h->sat.as<int>();
+  }
   if (!plan) {
-    if ((rc = run_scorer(h, RDB_ALGO_TC, nterms, v, kc, &L, timed))) return rc;
+    if ((rc = run_scorer(h, RDB_ALGO_TC, nterms, v, lk, &L, timed, lk != kc ? 1 : 0))) return rc;
   } else {
     const int ntiles = int((h->n + TC_BN - 1) / TC_BN);
     const int cg = nb > TC_BM ? 2 : 1;                       // must match plan_tc_kernel's cg (split3_search)
@@ -701,8 +711,8 @@ int certified_pass(rdb_handle* h, const QueryView& v, int k, int kc, int nterms,
   CUDA_TRY(h, h->rr_key2.ensure(size_t(nb) * kc * 4));
   CUDA_TRY(h, h->rr_idx2.ensure(size_t(nb) * kc * 8));
   // approximate top-kc per query (local ids, raw keys)
-  if ((rc = run_merge_local(h, nb, L, kc, kc, v.qnorm, false, nullptr, h->rr_idx.as<int64_t>(), nullptr, 0, nullptr,
-                            h->rr_key.as<float>(), nullptr, q_dev, plan ? &plan->L : nullptr))) return rc;
+  if ((rc = run_merge_local(h, nb, L, lk, kc, v.qnorm, false, nullptr, h->rr_idx.as<int64_t>(), nullptr, 0, nullptr,
+                            h->rr_key.as<float>(), nullptr, q_dev, plan ? &plan->L : nullptr, sat))) return rc;
   CUDA_TRY(h, cudaMemsetAsync(ucount, 0, 4, s));
   const int nks = (D + TC_BK - 1) / TC_BK;
   const float n_mma = float(nks * (TC_BK / 16) * nterms);
@@ -718,11 +728,11 @@ int certified_pass(rdb_handle* h, const QueryView& v, int k, int kc, int nterms,
   if (l2) rerank_exact_kernel<true><<<rgrid, rblock, 0, s>>>(
       h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, v.qf, h->master, h->ynorm, D, eps, v.qnorm,
       h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount, qres, h->d_ynorm_max + 1,
-      accum, q_dev, nullptr, f_dist, reinterpret_cast<long long*>(o_i), o_l, f_key, h->id_offset, labels);
+      accum, q_dev, nullptr, f_dist, reinterpret_cast<long long*>(o_i), o_l, f_key, h->id_offset, labels, sat);
   else rerank_exact_kernel<false><<<rgrid, rblock, 0, s>>>(
       h->rr_idx.as<long long>(), h->rr_key.as<float>(), nb, kc, k, v.qf, h->master, h->ynorm, D, eps, v.qnorm,
       h->d_ynorm_max, h->n, h->rr_key2.as<float>(), h->rr_idx2.as<long long>(), ulist, ucount, qres, h->d_ynorm_max + 1,
-      accum, q_dev, nullptr, f_dist, reinterpret_cast<long long*>(o_i), o_l, f_key, h->id_offset, labels);
+      accum, q_dev, nullptr, f_dist, reinterpret_cast<long long*>(o_i), o_l, f_key, h->id_offset, labels, sat);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return RDB_OK;
@@ -860,7 +870,10 @@ int exact_split_search(rdb_handle* h, const QueryView& qv, int k, bool shard_mod
   CUDA_TRY(h, h->uncert1.ensure(size_t(nb + 1) * 4));
   int* ucount = h->uncert1.as<int>();
   int* ulist = ucount + 1;
-  if ((rc = certified_pass(h, qv, k, kc1, 1, shard_mode, d_a, d_i, d_l, labels, ucount, ulist, true)))
+  // 32 candidates as a two-list cover of 16-entry lists: the epilogue keeps the register list of the k <= 16 searches
+  // (C2: 12.65 -> ~11.4 ms scorer) -- option "tier1_share2" = 0 keeps 32-entry lists
+  const int list_k = (kc1 == 32 && h->opt.tier1_share2) ? 16 : 0;
+  if ((rc = certified_pass(h, qv, k, kc1, 1, shard_mode, d_a, d_i, d_l, labels, ucount, ulist, true, nullptr, list_k)))
     return rc;
   // ---- tier 2 on the queries tier 1 could not certify: compacted on the device, every launch device-sized from ucount
   CUDA_TRY(h, h->t2_qf.ensure(size_t(nb) * D * 4));
@@ -1186,7 +1199,7 @@ const DevBufMember kScratch[] = {
     &rdb_handle::fb_i, &rdb_handle::fb_l, &rdb_handle::gthr, &rdb_handle::tcsync, &rdb_handle::stream_ctl,
     &rdb_handle::fkey, &rdb_handle::fidx, &rdb_handle::lk_scores, &rdb_handle::uncert1, &rdb_handle::t2_qf,
     &rdb_handle::t2_qhi, &rdb_handle::t2_qlo, &rdb_handle::t2_qnorm, &rdb_handle::t2_a, &rdb_handle::t2_i,
-    &rdb_handle::t2_l, &rdb_handle::dev_ctl, &rdb_handle::qext, &rdb_handle::qres,
+    &rdb_handle::t2_l, &rdb_handle::dev_ctl, &rdb_handle::qext, &rdb_handle::qres, &rdb_handle::sat,
     &rdb_handle::res_stage};
 
 }  // namespace
@@ -1659,6 +1672,7 @@ int rdb_set_option(rdb_handle* h, const char* name, int64_t value) {
   else if (n == "largek_sample") o.largek_sample = int(value);
   else if (n == "largek_split") o.largek_split = int(value);
   else if (n == "host_pipeline") o.host_pipeline = int(value);
+  else if (n == "tier1_share2") o.tier1_share2 = int(value);
 #ifdef RDB_PROFILING
   else if (n == "tc_debug") o.tc_debug = int(value);
   else if (n == "stream_prof") o.stream_prof = value;

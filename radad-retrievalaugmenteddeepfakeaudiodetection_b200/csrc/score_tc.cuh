@@ -72,6 +72,7 @@ struct TcParams {
   float* cand_key;        // [nq][S * TC_LISTS][kout]
   int* cand_idx;          // [nq][S * TC_LISTS][kout]  local row ids, -1 = empty
   uint32_t* gthr;         // [nq] shared lower bound of the global k-th best key (ordered uint, 0 = none), or null
+  int share2;             // two-list cover (SelectSmall<16, 2>): gthr is [nq][2], see common.cuh
   int nq, N, D;
   int nqt /* query-tile groups of 128 * CG queries */, S, tiles_per_chunk, ntiles, kout, num_units, nterms;
   uint32_t idesc;
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_select_tc_kernel(const __
       const int t0 = chunk * s_tpc, t1 = min(p.ntiles, t0 + s_tpc);
       const long long q = (long long)qtile * TC_BM + row;
       Sel sel;
-      sel.init(p.kout, (p.gthr && q < s_nq) ? p.gthr + q : nullptr);
+      sel.init(p.kout, (p.gthr && q < s_nq) ? p.gthr + q * Sel::kGthrWords : nullptr);
       if constexpr (Sel::kDump) sel.row = (q < s_nq) ? p.dump + q * p.dump_pitch - p.row_base : nullptr;
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&tfull_bar[acc], acc_phase);

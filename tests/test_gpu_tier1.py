@@ -176,3 +176,37 @@ def test_device_path_is_stream_ordered(pkg, oracle, scenario):
     if scenario == "clustered":
         assert uncert_host >= 3
 
+
+
+def test_two_list_cover_equals_32_entry_lists_and_flags_saturated_lists(pkg, oracle):
+    """Tier 1 keeps its 32 candidates as a two-list cover of 16-entry lists (SelectSmall<16, 2>).  (a) Same answers as
+    with 32-entry lists (option tier1_share2 = 0) and as the oracle.  (b) A query whose 40 nearest rows sit in ONE
+    candidate list (contiguous rows of one half-tile), spaced 0.004 apart in exact distance -- far above the fp32
+    tolerance, far below the bf16 error of the one-term keys -- saturates that list: the 16 entries it keeps are the
+    best by APPROXIMATE key, so the true top-10 is partly missing and the query must not be certified by tier 1 (the
+    merge flags it; tier 2 then finds the exact neighbours)."""
+    N, Dm, Q, k = 300_000, 64, 300, 10
+    rng = np.random.default_rng(21)
+    xb, xq = _gauss(N, Dm, 31), _gauss(Q, Dm, 32)
+    hard = list(range(0, 16, 2))
+    for t, qi in enumerate(hard):
+        r0 = 1024 * (3 + 7 * t)                                   # start of a database tile -> one 128-row half
+        u = rng.standard_normal((40, Dm)).astype(np.float32)
+        u /= np.linalg.norm(u, axis=1, keepdims=True)
+        xb[r0:r0 + 40] = xq[qi] + np.sqrt(0.004 * np.arange(40, dtype=np.float32))[:, None] * u
+    idx = pkg.FlatIndex(Dm, pkg.METRIC_L2, "f32")
+    for s in range(0, N, 65536):
+        idx.add(xb[s:s + 65536])
+    D, I = idx.search(xq, k)
+    t1q, t1u = idx.last_tier1
+    assert t1q == Q and idx.last_tier1_candidates == 32
+    assert t1u >= len(hard), (t1q, t1u)                           # every saturated query went on to tier 2
+    for t, qi in enumerate(hard):
+        r0 = 1024 * (3 + 7 * t)
+        np.testing.assert_array_equal(I[qi], np.arange(r0, r0 + k))
+    _check_vs_oracle(pkg, oracle, idx, xb, xq, D, I, k, pkg.METRIC_L2, False)
+    idx.set_option("tier1_share2", 0)
+    D0, I0 = idx.search(xq, k)
+    np.testing.assert_array_equal(I, I0)
+    np.testing.assert_array_equal(D, D0)
+    idx.close()
