@@ -181,6 +181,7 @@ int rdb_truncate(rdb_handle* h, int64_t n_keep);
  * "tc_lockstep_spins", "tc_stages", "tc_chunks" (0 = cost model), "tc_query_stationary" (0 | 1), "tc_pivot" (0 | 1), "tier1" (0 | 1), "tier1_kc"
  * (0 auto | 32 | 64 | 128), "largek_scorer" (0 auto | 1 CUDA cores | 2 tensor cores), "largek_rows" (rows per dense key
  * chunk, 0 = default), "largek_sample" (0 | 1), "largek_split" (0 | 1: split-precision tensor-core keys for fp32 stores),
+ * "tc_list10" (0 | 1: 10- or 16-entry register lists for k <= 10),
  * "tier1_share2" (0 | 1: tier 1 keeps its 32 candidates as a two-list cover of 16-entry lists; results identical),
  * "host_pipeline" (0 | 1: searches with HOST buffers of >= 4096 queries / 8 MB upload the batch in pieces on a second
  * stream so that the copy of piece i + 1 overlaps the search of piece i; results are identical either way).

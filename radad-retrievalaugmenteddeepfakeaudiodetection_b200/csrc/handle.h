@@ -53,6 +53,7 @@ struct rdb_options {
   int64_t largek_rows = 0;       // rows per dense key chunk (0 = default 1M)
   int largek_sample = 1;         // sampled-pivot fast path of the radix select
   int largek_split = 1;          // fp32 stores: split-precision tensor-core keys + certificate for k > 128
+  int tc_list10 = 1;             // k <= 10: 10-entry register lists in the tensor-core epilogue (0 = 16 entries)
   int tier1_share2 = 1;          // tier 1 with 32 candidates: two-list cover of 16-entry lists (0 = 32-entry lists)
   int host_pipeline = 1;         // host-buffer searches upload large query batches in pieces behind the running search
 };

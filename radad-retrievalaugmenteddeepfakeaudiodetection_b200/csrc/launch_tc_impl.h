@@ -44,6 +44,10 @@ int launch_tc_cg_t(rdb_handle* h, TcParams& p, int k) {
   if (p.dump)       return l2 ? launch_tc_kernel<SelectDump, true, CG>(h, p, groups) : launch_tc_kernel<SelectDump, false, CG>(h, p, groups);
   if (p.share2 && k <= 16)
     return l2 ? launch_tc_kernel<SelectSmall<16, 2>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<16, 2>, false, CG>(h, p, groups);
+  // k <= 10 (BASELINE's k): a 10-entry list -- the admission threshold is the 10th key instead of the 16th (a third fewer
+  // insertions) and an insertion is 9 compare-exchange steps instead of 15; option "tc_list10" = 0 keeps 16 entries
+  if (k <= 10 && h->opt.tc_list10)
+    return l2 ? launch_tc_kernel<SelectSmall<10>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<10>, false, CG>(h, p, groups);
   if (k <= 16)      return l2 ? launch_tc_kernel<SelectSmall<16>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<16>, false, CG>(h, p, groups);
   else if (k <= 32) return l2 ? launch_tc_kernel<SelectSmall<32>, true, CG>(h, p, groups) : launch_tc_kernel<SelectSmall<32>, false, CG>(h, p, groups);
   return l2 ? launch_tc_kernel<SelectReservoir<kReservoirCap>, true, CG>(h, p, groups)

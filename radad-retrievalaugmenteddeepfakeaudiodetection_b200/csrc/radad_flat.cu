@@ -1673,6 +1673,7 @@ int rdb_set_option(rdb_handle* h, const char* name, int64_t value) {
   else if (n == "largek_split") o.largek_split = int(value);
   else if (n == "host_pipeline") o.host_pipeline = int(value);
   else if (n == "tier1_share2") o.tier1_share2 = int(value);
+  else if (n == "tc_list10") o.tc_list10 = int(value);
 #ifdef RDB_PROFILING
   else if (n == "tc_debug") o.tc_debug = int(value);
   else if (n == "stream_prof") o.stream_prof = value;

@@ -27,7 +27,7 @@ pkg = importlib.import_module(PKG)
 
 DEFAULTS = {"tc_cta_group": 0, "tc_lockstep": 8, "tc_lockstep_spins": 4096, "tc_stages": 64, "tc_chunks": 0, "tc_query_stationary": 1,
             "tc_pivot": 1, "tc_debug": 0, "tier1": 1, "tier1_kc": 0, "largek_scorer": 0, "largek_rows": 0,
-            "largek_sample": 1, "largek_split": 1}
+            "largek_sample": 1, "largek_split": 1, "tc_list10": 1, "tier1_share2": 1, "host_pipeline": 1}
 
 
 def main():
