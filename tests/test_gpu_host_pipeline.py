@@ -66,3 +66,24 @@ def test_pipelined_host_search_through_vector_database(pkg, make_cfg):
     D0, I0 = db.search_batch(xq, 10)[:2]
     np.testing.assert_array_equal(np.asarray(I1), np.asarray(I0))
     np.testing.assert_array_equal(np.asarray(D1), np.asarray(D0))
+
+
+def test_copy_async_moves_bytes_in_stream_order(pkg):
+    """rdb_copy_async (the exchange primitive of the single-process multi-GPU search): a copy kernel on the index's own
+    GPU and the caller's stream -- 16-byte path and the byte path (odd sizes / unaligned views), ordered behind the
+    producer of the source.  The peer-memory case is covered by the multi-GPU tests."""
+    import torch
+    idx = pkg.FlatIndex(8, pkg.METRIC_L2, "f32", device=0)
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(3)
+    src = torch.randn((1000, 257), generator=g, device="cuda:0")
+    dst = torch.zeros_like(src)
+    idx.copy_async(dst, src * 2.0)                       # ordered behind the multiply on the same stream
+    assert torch.equal(dst, src * 2.0)
+    a = torch.arange(10_001, dtype=torch.uint8, device="cuda:0")
+    b = torch.zeros(10_001, dtype=torch.uint8, device="cuda:0")
+    idx.copy_async(b[1:], a[1:])                         # unaligned, odd length -> byte path
+    assert torch.equal(b[1:], a[1:]) and int(b[0]) == 0
+    with pytest.raises(RuntimeError):
+        idx.copy_async(dst[:10], src[:11])
+    idx.close()
